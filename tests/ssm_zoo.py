@@ -1,0 +1,222 @@
+"""State-space models used by the parity tests, in reference-callback form.
+
+Every model offers the reference's per-particle callables (``g(x,u)`` /
+``g(x,u,v)``, ``h(x)``, ``jac_h(x)``, ``log_trans_pdf(xk,xkm1)``,
+``log_like_pdf(z,x)`` -- SURVEY.md section 8b "operator API") and batched twins
+for the NumPy oracle.  Pure NumPy; no engine imports.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def sv_data(n, alpha, sigma, beta, seed):
+    """1-D stochastic-volatility series (x_t = a x + s v, y_t = b exp(x/2) w).
+
+    Same model as the reference's ``simulate_sv_1d``
+    (simulator/simulator_sto_volatility_model.py:51-122), independent code; used
+    where the reference simulator is not available (GPU box, bench).
+    """
+    rng = np.random.default_rng(seed)
+    x = np.empty(n)
+    x[0] = rng.normal(0.0, np.sqrt(sigma ** 2 / (1 - alpha ** 2)))
+    v = rng.standard_normal(n - 1)
+    for t in range(1, n):
+        x[t] = alpha * x[t - 1] + sigma * v[t - 1]
+    y = beta * np.exp(0.5 * x) * rng.standard_normal(n)
+    return x, y
+
+
+class SVModel:
+    """Additive-Gaussian SV form the reference tests/notebooks filter with:
+    g = alpha x, h = beta exp(x/2) (tests/integration_tests/test_pf_vs_simulator_sv.py:50-56)."""
+
+    nx = nz = 1
+
+    def __init__(self, alpha=0.95, sigma=0.2, beta=1.0, r=None):
+        self.alpha, self.sigma, self.beta = alpha, sigma, beta
+        self.Q = np.array([[sigma ** 2]])
+        self.R = np.array([[beta ** 2 if r is None else r]])
+
+    def g(self, x, u=None):
+        return np.array([self.alpha * x[0]])
+
+    def h(self, x):
+        return np.array([self.beta * np.exp(0.5 * x[0])])
+
+    def g_batch(self, X, u=None):
+        return self.alpha * X
+
+    def h_batch(self, X):
+        return self.beta * np.exp(0.5 * X)
+
+
+class LGSSMModel:
+    """README A/B/C/D linear-Gaussian model (reference README.md:104-113)."""
+
+    def __init__(self):
+        self.A = np.array([[0.9, 0.5], [0.0, 0.7]])
+        self.B = np.diag([np.sqrt(0.05), np.sqrt(0.02)])
+        self.C = np.eye(2)
+        self.D = np.diag([np.sqrt(0.1), np.sqrt(0.1)])
+        self.Q = self.B @ self.B.T
+        self.R = self.D @ self.D.T
+        self.nx = self.nz = 2
+
+    def simulate(self, T, seed):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(2)
+        X, Y = np.empty((T, 2)), np.empty((T, 2))
+        for t in range(T):
+            Y[t] = self.C @ x + self.D @ rng.standard_normal(2)
+            X[t] = x
+            x = self.A @ x + self.B @ rng.standard_normal(2)
+        return X, Y
+
+    def g(self, x, u=None):
+        return self.A @ x
+
+    def h(self, x):
+        return self.C @ x
+
+    def g_batch(self, X, u=None):
+        return X @ self.A.T
+
+    def h_batch(self, X):
+        return X @ self.C.T
+
+
+class AcousticCVModel:
+    """Constant-velocity targets observed by an amplitude sensor grid.
+
+    Joint state = ``n_targets`` x [x, y, vx, vy]; z_s = sum_targets psi / (|p - s|^2 + d0)
+    (reference simulator/simulator_Multi_acoustic_tracking.py:273-310 and the
+    single-target test model tests/integration_tests/test_filters_mat_simulator.py:44-66).
+    """
+
+    def __init__(self, n_targets=1, grid=(3, 3), area=(40.0, 40.0), psi=10.0, d0=0.1,
+                 q_scale=1.0, r_var=0.01):
+        self.n_targets = n_targets
+        self.nx = 4 * n_targets
+        gx = np.linspace(0.0, area[0], grid[0])
+        gy = np.linspace(0.0, area[1], grid[1])
+        self.S = np.array([[a, b] for a in gx for b in gy])
+        self.nz = self.S.shape[0]
+        self.psi, self.d0 = psi, d0
+        F1 = np.array([[1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+        Q1 = q_scale * np.array([[3.0, 0, 0.1, 0], [0, 3.0, 0, 0.1], [0.1, 0, 0.03, 0],
+                                 [0, 0.1, 0, 0.03]])
+        self.F = np.kron(np.eye(n_targets), F1)
+        self.Q = np.kron(np.eye(n_targets), Q1)
+        self.R = r_var * np.eye(self.nz)
+        self._Qinv = np.linalg.inv(self.Q)
+        self._Rinv = np.linalg.inv(self.R)
+        self._logdet2piQ = np.linalg.slogdet(2 * np.pi * self.Q)[1]
+        self._logdet2piR = np.linalg.slogdet(2 * np.pi * self.R)[1]
+
+    # per-particle (reference callback signatures)
+    def g(self, x, u=None, v=None):
+        return self.F @ x + (0.0 if v is None else v)
+
+    def g2(self, x, u=None):
+        return self.F @ x
+
+    def jac_g(self, x, u=None):
+        return self.F
+
+    def h(self, x):
+        return self.h_batch(x[None, :])[0]
+
+    def jac_h(self, x):
+        return self.jac_batch(x[None, :])[0]
+
+    def log_trans_pdf(self, xk, xkm1):
+        d = xk - self.F @ xkm1
+        return -0.5 * (d @ np.linalg.solve(self.Q, d) + self._logdet2piQ)
+
+    def log_like_pdf(self, z, x):
+        d = z - self.h(x)
+        return -0.5 * (d @ np.linalg.solve(self.R, d) + self._logdet2piR)
+
+    # batched (oracle)
+    def g_batch(self, X, u=None, V=None):
+        return X @ self.F.T + (0.0 if V is None else V)
+
+    def h_batch(self, X):
+        N = X.shape[0]
+        pos = X.reshape(N, self.n_targets, 4)[:, :, :2]            # (N, C, 2)
+        diff = pos[:, :, None, :] - self.S[None, None, :, :]       # (N, C, S, 2)
+        d2 = np.sum(diff ** 2, axis=-1)
+        return np.sum(self.psi / (d2 + self.d0), axis=1)           # (N, S)
+
+    def jac_batch(self, X):
+        N = X.shape[0]
+        pos = X.reshape(N, self.n_targets, 4)[:, :, :2]
+        diff = pos[:, :, None, :] - self.S[None, None, :, :]       # (N, C, S, 2)
+        d2 = np.sum(diff ** 2, axis=-1)
+        coef = -2.0 * self.psi / (d2 + self.d0) ** 2               # (N, C, S)
+        H = np.zeros((N, self.nz, self.nx))
+        for c in range(self.n_targets):
+            H[:, :, 4 * c + 0] = coef[:, c, :] * diff[:, c, :, 0]
+            H[:, :, 4 * c + 1] = coef[:, c, :] * diff[:, c, :, 1]
+        return H
+
+    def log_trans_batch(self, Xk, Xkm1):
+        d = Xk - Xkm1 @ self.F.T
+        return -0.5 * (np.einsum("ni,ij,nj->n", d, self._Qinv, d) + self._logdet2piQ)
+
+    def log_like_batch(self, z, X):
+        d = z[None, :] - self.h_batch(X)
+        return -0.5 * (np.einsum("ni,ij,nj->n", d, self._Rinv, d) + self._logdet2piR)
+
+
+class Linear1DModel:
+    """1-D linear system of the LEDH unit tests (tests/unit_tests/models/test_ledh_flow_pf.py:63-113)."""
+
+    nx = nz = 1
+
+    def __init__(self, alpha=0.9, sigma=0.2, r=0.1):
+        self.alpha = alpha
+        self.Q = np.array([[sigma ** 2]])
+        self.R = np.array([[r]])
+
+    def g(self, x, u=None, v=None):
+        return np.array([self.alpha * x[0] + (0.0 if v is None else v[0])])
+
+    def g2(self, x, u=None):
+        return np.array([self.alpha * x[0]])
+
+    def jac_g(self, x, u=None):
+        return np.array([[self.alpha]])
+
+    def h(self, x):
+        return np.array([x[0]])
+
+    def jac_h(self, x):
+        return np.array([[1.0]])
+
+    def log_trans_pdf(self, xk, xkm1):
+        d = xk - self.g2(xkm1)
+        return float(-0.5 * (d @ np.linalg.solve(self.Q, d) + np.log(2 * np.pi * self.Q[0, 0])))
+
+    def log_like_pdf(self, z, x):
+        d = z - self.h(x)
+        return float(-0.5 * (d @ np.linalg.solve(self.R, d) + np.log(2 * np.pi * self.R[0, 0])))
+
+    def g_batch(self, X, u=None, V=None):
+        return self.alpha * X + (0.0 if V is None else V)
+
+    def h_batch(self, X):
+        return X.copy()
+
+    def jac_batch(self, X):
+        return np.ones((X.shape[0], 1, 1))
+
+    def log_trans_batch(self, Xk, Xkm1):
+        d = (Xk - self.alpha * Xkm1)[:, 0]
+        return -0.5 * (d * d / self.Q[0, 0] + np.log(2 * np.pi * self.Q[0, 0]))
+
+    def log_like_batch(self, z, X):
+        d = z[0] - X[:, 0]
+        return -0.5 * (d * d / self.R[0, 0] + np.log(2 * np.pi * self.R[0, 0]))
