@@ -1,0 +1,195 @@
+/*
+ * libsmc -- C-ABI of the B200-native Sequential-Monte-Carlo engine.
+ *
+ * This is the drop-in boundary beneath the reference's Python filter classes
+ * (liyiyang-amber/Particle_filters).  The reference has no FFI of its own: the
+ * public interface is the class surface of models/particle_filter.py and
+ * models/LEDH_particle_filter.py.  Every entry point below names the reference
+ * method (file:line) whose arithmetic it replaces; INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer,
+ *     everything else is host memory;
+ *   - every call enqueues work on the caller's stream (cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and returns without synchronising;
+ *   - return value 0 = ok, non-zero = error, text via smc_last_error();
+ *   - particles are stored SoA: x[d * ld + i], d < nx, i < n, ld % 4 == 0 and
+ *     ld >= round_up(n, 4); log-weight arrays hold round_up(n, 4) elements;
+ *   - dtype selects the storage/arithmetic type of particles and log-weights
+ *     (SMC_F32 throughput mode, SMC_F64 parity mode).  Normalisers, ESS, moments
+ *     are always accumulated in fp64 and the resampling CDF in 64-bit fixed
+ *     point, so results do not depend on launch geometry or shard count.
+ */
+#ifndef SMC_H_
+#define SMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMC_ABI_VERSION 1
+
+enum { SMC_F32 = 0, SMC_F64 = 1 };
+
+/* State-space-model functors compiled into the fused kernel (K1). */
+enum {
+    SMC_MODEL_STOCH_VOL = 1,       /* g = alpha x, h = beta exp(x/2); nx = nz = 1           */
+    SMC_MODEL_LINEAR_GAUSSIAN = 2, /* g = A x, h = H x; nx, nz in {1, 2, 4}                 */
+    SMC_MODEL_LORENZ96 = 3         /* g = n_sub RK4 steps of Lorenz-96, h = x[obs_idx]      */
+};
+
+/* smc_sir_propagate_weight mode bits */
+enum { SMC_MODE_PROPAGATE = 1, SMC_MODE_WEIGHT = 2, SMC_MODE_STEP = 3 };
+
+/* smc_sir_desc.flags */
+enum {
+    SMC_FLAG_WRITE_ANCESTORS = 1, /* store int32 ancestor indices (additive trace output)   */
+    SMC_FLAG_NO_MOMENTS = 2,      /* skip mean/cov (not used by the reference-equivalent path) */
+    SMC_FLAG_GENERIC_MOMENTS = 4  /* block partials carry no moments; mean/cov come from the
+                                     any-nx moment kernel (bridge mode, nx > 4)               */
+};
+
+/* One shard of a particle population (the whole population when n == n_global). */
+typedef struct smc_sir_desc {
+    int64_t n;          /* particles held by this shard                                    */
+    int64_t n_global;   /* particles over all shards (<= 2^30)                             */
+    int64_t offset;     /* global index of local particle 0 (multiple of 4)                */
+    int64_t ld;         /* row stride of x0/x1 in elements                                 */
+    int32_t nx, nz;
+    int32_t dtype;      /* SMC_F32 | SMC_F64                                               */
+    int32_t flags;
+    void *x0_dev, *x1_dev; /* ping-pong particle buffers (ctrl.cur says which is current)  */
+    void *logw_dev;     /* un-normalised log-weights of the current step                   */
+    int32_t *ancestors_dev; /* n int32 or NULL                                             */
+    void *ws_dev;       /* workspace of smc_sir_workspace_bytes()                          */
+    uint64_t ws_bytes;
+} smc_sir_desc;
+
+/* Per-step statistics row written by the device (doubles):
+ *   [0] log normaliser  m + log sum exp(logw - m)     (particle_filter.py:262-263)
+ *   [1] ESS before resampling  1 / sum w^2            (particle_filter.py:203)
+ *   [2] 1.0 if the step resampled else 0.0            (particle_filter.py:204)
+ *   [3] the systematic-resampling uniform u           (particle_filter.py:160)
+ *   [4 .. 4+nx)            posterior mean             (particle_filter.py:266)
+ *   [4+nx .. 4+nx+nx*nx)   posterior covariance       (particle_filter.py:267)
+ */
+#define SMC_STATS_HEADER 4
+static inline int64_t smc_stats_stride(int nx) { return SMC_STATS_HEADER + nx + (int64_t)nx * nx; }
+
+int smc_abi_version(void);
+const char *smc_last_error(void);
+uint64_t smc_sizeof_sir_desc(void);
+
+/* Workspace size for a shard (control block, block partials, scan tile state). */
+uint64_t smc_sir_workspace_bytes(int64_t n, int32_t nx, int32_t dtype);
+
+/* Reset the control block: current buffer = x0, weights uniform, moment shift =
+ * prior mean (host pointer, nx doubles, may be NULL = 0). */
+int smc_sir_reset(const smc_sir_desc *d, const double *shift_host, void *stream);
+
+/* ParticleFilter.initialize (particle_filter.py:110-132): x = mean + Lc n with
+ * n ~ N(0, I) from Philox stream (seed, t = 0); weights uniform.  Lc_host is
+ * the nx*nx row-major lower Cholesky factor, mean_host nx doubles. */
+int smc_sir_init_gaussian(const smc_sir_desc *d, const double *mean_host, const double *Lc_host,
+                          uint64_t seed, void *stream);
+
+/* K1: fused ParticleFilter.predict + the likelihood half of update
+ * (particle_filter.py:223-237 and :253-261).  params_host holds the functor's
+ * parameters (layout per model in DESIGN.md), z_dev the nz-vector observation
+ * (doubles, device).  noise_dev: NULL = on-chip Philox4x32-10 keyed by
+ * (seed, t, global particle id); otherwise SoA standard normals (same dtype,
+ * same ld) -- the "reference-noise mode" used for parity.  Also emits per-block
+ * (max, sum exp, sum exp^2, weighted moment) partials into the workspace. */
+int smc_sir_propagate_weight(const smc_sir_desc *d, int32_t model_id, const double *params_host,
+                             int32_t n_params, int32_t mode, const double *z_dev,
+                             const void *noise_dev, uint64_t seed, int64_t t, void *stream);
+
+/* Host-callback bridge (opaque Python g/h evaluated by the caller exactly as the
+ * reference does; the engine's own arithmetic still runs here).
+ *  predict: x = gx + noise @ Lq^T                      (particle_filter.py:236-237)
+ *  loglik : logw = log(w_prev + 1e-300) - 0.5 |LR^-1 (z - zpred)|^2   (:258-261)
+ * gx_dev/noise_dev/zpred_dev are SoA arrays in the desc dtype (zpred: nz rows
+ * of ld); Lq_host / LRinv_host are row-major lower-triangular factors;
+ * wprev_dev = linear weights of the previous step or NULL for uniform.
+ * target_other = 0 writes the current buffer; 1 writes the other ping-pong buffer
+ * (the resampling destination) and then gx_dev may be NULL = "that buffer itself",
+ * which is the post-resample regularisation x += noise @ (scale Lq)^T (:212-218). */
+int smc_bridge_predict(const smc_sir_desc *d, const void *gx_dev, const void *noise_dev,
+                       const double *Lq_host, double scale, int32_t target_other, void *stream);
+int smc_bridge_loglik(const smc_sir_desc *d, const void *zpred_dev, const double *z_host,
+                      const double *LRinv_host, const void *wprev_dev, void *stream);
+
+/* K2: combine block partials -> log normaliser, ESS, weighted mean/cov; decide
+ * resampling (ESS < resample_thresh * n_global, particle_filter.py:203-204);
+ * fix the systematic uniform u (u_host in [0,1) = caller's draw for
+ * reference-noise mode, negative = Philox(seed, t)).  stats_row_dev receives
+ * smc_stats_stride(nx) doubles.  n_parts_override > 0: reduce that many
+ * partials found at parts_dev instead of this shard's own (multi-GPU: the
+ * all-gathered per-rank partials, see smc_sir_reduce_partials). */
+int smc_sir_finalize(const smc_sir_desc *d, double resample_thresh, double u_host, uint64_t seed,
+                     int64_t t, double *stats_row_dev, const double *parts_dev,
+                     int32_t n_parts_override, void *stream);
+
+/* Replace the systematic uniform chosen by smc_sir_finalize (reference-noise mode:
+ * the caller draws rng.random() only after learning that the step resamples, to
+ * keep the reference's RNG call order, particle_filter.py:204-206 then :160). */
+int smc_sir_set_uniform(const smc_sir_desc *d, double u, void *stream);
+
+/* Multi-GPU helper: fold this shard's block partials into ONE partial record of
+ * smc_partial_stride(nx) doubles at out_dev (to be all-gathered). */
+int64_t smc_partial_stride(int32_t nx);
+int smc_sir_reduce_partials(const smc_sir_desc *d, double *out_dev, void *stream);
+
+/* K3: systematic resampling (particle_filter.py:146-171 + gather :209-210;
+ * LEDH_particle_filter.py:25-37).  One pass: fixed-point decoupled-look-back
+ * scan of the normalised weights, closed-form search of the stratified
+ * positions with exact tie handling, shared-memory-staged ancestor gather into
+ * the other ping-pong buffer, post-resample moments.  A no-op when the control
+ * block says "do not resample".  cdf_offset_fix / total are used by sharded
+ * runs (exclusive prefix of lower ranks' weight totals in 2^-32 index units,
+ * see smc_sir_shard_weight_total); pass 0 for a single shard.  peer_x_dev:
+ * NULL, or n_shards device pointers (each shard's destination buffer for this
+ * step, peer-mapped) for fused cross-shard migration. */
+int smc_sir_resample(const smc_sir_desc *d, uint64_t cdf_offset_fix, double *stats_row_dev,
+                     void *const *peer_x_dev, int32_t n_shards, void *stream);
+
+/* Fixed-point total of this shard's normalised weights (index units * 2^32),
+ * written to total_dev (one uint64); input to the cross-shard exclusive scan. */
+int smc_sir_shard_weight_total(const smc_sir_desc *d, uint64_t *total_dev, void *stream);
+
+/* Finish a step: publish post-resample moments into stats_row_dev, flip the
+ * current buffer if the step resampled, refresh the moment shift.
+ * mom_parts_dev/n_mom_parts: NULL/0 = this shard's own tile partials. */
+int smc_sir_finish_step(const smc_sir_desc *d, double *stats_row_dev, const double *mom_parts_dev,
+                        int32_t n_mom_parts, void *stream);
+
+/* Whole SIR step on one shard = propagate_weight + finalize + resample +
+ * finish_step (ParticleFilter.step, particle_filter.py:271-287). */
+int smc_sir_step(const smc_sir_desc *d, int32_t model_id, const double *params_host,
+                 int32_t n_params, const double *z_dev, const void *noise_dev,
+                 double resample_thresh, double u_host, uint64_t seed, int64_t t,
+                 double *stats_row_dev, void *stream);
+
+/* Stand-alone pieces used by the drop-in classes' private helpers. */
+
+/* ParticleFilter._systematic_resample(weights) (particle_filter.py:146-171):
+ * w_dev = n normalised fp64 weights, ancestors_dev = n int32 out. */
+int smc_systematic_ancestors(const double *w_dev, int64_t n, double u, int32_t *ancestors_dev,
+                             void *ws_dev, uint64_t ws_bytes, void *stream);
+/* particles[idx] (particle_filter.py:209): dst[d*ld+i] = src[d*ld+idx[i]]. */
+int smc_gather(const void *src_dev, void *dst_dev, const int32_t *idx_dev, int64_t n, int64_t ld,
+               int32_t nx, int32_t dtype, void *stream);
+/* w = exp(logw - log_norm) as fp64 (particle_filter.py:263); reads the control
+ * block's log normaliser; if the current weights are uniform writes 1/n_global. */
+int smc_sir_export_weights(const smc_sir_desc *d, double *w_dev, void *stream);
+/* Which ping-pong buffer is current (synchronises the stream). */
+int smc_sir_current_buffer(const smc_sir_desc *d, int32_t *cur_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMC_H_ */

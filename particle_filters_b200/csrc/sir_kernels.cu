@@ -1,0 +1,1454 @@
+// SIR particle-filter hot path for sm_100a: K1 fused propagate+log-likelihood,
+// K2 normaliser/ESS/moment reduction, K3 single-pass systematic resampler.
+//
+// Reference semantics: models/particle_filter.py of liyiyang-amber/Particle_filters
+// (predict :223-237, update :239-269, _resample :188-220, _systematic_resample :146-171).
+#include "smc_common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace smc {
+
+// ----------------------------------------------------------------------------------------------
+// error string (per thread)
+// ----------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ==============================================================================================
+// Model functors.  x is one particle (NX registers); propagate() applies g and adds Lq * nrm.
+// ==============================================================================================
+template <typename real> struct StochVolModel {
+    static constexpr int NX = 1, NZ = 1;
+    real alpha, lq, beta, rinv;
+    __device__ inline void propagate(real (&x)[1], const real (&nrm)[1]) const {
+        x[0] = fma(lq, nrm[0], alpha * x[0]);
+    }
+    __device__ inline real loglik(const real (&x)[1], const real (&z)[1]) const {
+        real d = (z[0] - beta * fast_exp(real(0.5) * x[0])) * rinv;
+        return real(-0.5) * d * d;
+    }
+};
+
+template <typename real, int NX_, int NZ_> struct LinGaussModel {
+    static constexpr int NX = NX_, NZ = NZ_;
+    real A[NX_ * NX_], Lq[NX_ * NX_], H[NZ_ * NX_], LRinv[NZ_ * NZ_];
+    __device__ inline void propagate(real (&x)[NX_], const real (&nrm)[NX_]) const {
+        real y[NX_];
+#pragma unroll
+        for (int i = 0; i < NX_; ++i) {
+            real acc = 0;
+#pragma unroll
+            for (int j = 0; j < NX_; ++j) acc = fma(A[i * NX_ + j], x[j], acc);
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc = fma(Lq[i * NX_ + j], nrm[j], acc);
+            y[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX_; ++i) x[i] = y[i];
+    }
+    __device__ inline real loglik(const real (&x)[NX_], const real (&z)[NZ_]) const {
+        real d[NZ_];
+#pragma unroll
+        for (int i = 0; i < NZ_; ++i) {
+            real acc = z[i];
+#pragma unroll
+            for (int j = 0; j < NX_; ++j) acc = fma(-H[i * NX_ + j], x[j], acc);
+            d[i] = acc;
+        }
+        real quad = 0;
+#pragma unroll
+        for (int i = 0; i < NZ_; ++i) {   // y = LR^-1 d (lower triangular inverse)
+            real acc = 0;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc = fma(LRinv[i * NZ_ + j], d[j], acc);
+            quad = fma(acc, acc, quad);
+        }
+        return real(-0.5) * quad;
+    }
+};
+
+// ==============================================================================================
+// K1: fused propagate + log-likelihood + block partials
+// ==============================================================================================
+template <typename real> struct K1Args {
+    Ctrl* ctrl;
+    real* x0;
+    real* x1;
+    real* logw;
+    const real* noise;   // nullable: SoA standard normals, same ld
+    const double* z;     // device, NZ doubles
+    double* parts;       // block partials
+    int64_t n, n_global, offset, ld;
+    uint64_t seed;
+    uint32_t t;
+    int32_t mode;
+};
+
+template <typename real, int NX>
+__device__ inline void draw_normals(uint64_t seed, uint64_t gquad, uint32_t t, real (&nrm)[NX][4]);
+
+template <int NX> __device__ inline void draw_normals_f32(uint64_t seed, uint64_t gquad, uint32_t t,
+                                                          float (&nrm)[NX][4]) {
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+        uint32_t r[4];
+        philox_quad(seed, gquad, t, kStreamProcess | (uint32_t(d) << 8), r);
+        normals4_f32(r, nrm[d]);
+    }
+}
+template <int NX> __device__ inline void draw_normals_f64(uint64_t seed, uint64_t gquad, uint32_t t,
+                                                          double (&nrm)[NX][4]) {
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[4];
+            philox_quad(seed, gquad, t, kStreamProcess | (uint32_t(d) << 8) | (uint32_t(h) << 16), r);
+            double z2[2];
+            normals2_f64(r, z2);
+            nrm[d][2 * h] = z2[0];
+            nrm[d][2 * h + 1] = z2[1];
+        }
+    }
+}
+template <int NX> struct Draw {
+    static __device__ inline void run(uint64_t s, uint64_t q, uint32_t t, float (&n)[NX][4]) {
+        draw_normals_f32<NX>(s, q, t, n);
+    }
+    static __device__ inline void run(uint64_t s, uint64_t q, uint32_t t, double (&n)[NX][4]) {
+        draw_normals_f64<NX>(s, q, t, n);
+    }
+};
+
+__device__ inline float prev_logweight(float lw_old, float log_norm) { return lw_old - log_norm; }
+// fp64 parity mode follows the reference literally: log(w + 1e-300), particle_filter.py:261
+__device__ inline double prev_logweight(double lw_old, double log_norm) {
+    return log(exp(lw_old - log_norm) + 1e-300);
+}
+
+template <typename real, class Model>
+__global__ void __launch_bounds__(kThreads) k1_propagate_weight(K1Args<real> a, Model m) {
+    constexpr int NX = Model::NX, NZ = Model::NZ;
+    constexpr int NM = NX + NX * (NX + 1) / 2;   // moment accumulators
+    constexpr int NR = 2 + NM;                   // sum e, sum e^2, moments
+    __shared__ real s_max[kWarps];
+    __shared__ double s_red[kWarps][NR];
+
+    const Ctrl* ctrl = a.ctrl;
+    real* x = ctrl->cur ? a.x1 : a.x0;
+    const bool uniform = ctrl->uniform != 0;
+    const real log_norm_prev = (real)ctrl->log_norm;
+    const real lw_uniform = (real)(-log((double)a.n_global));
+    const bool do_prop = a.mode & SMC_MODE_PROPAGATE, do_w = a.mode & SMC_MODE_WEIGHT;
+
+    real z[NZ], shift[NX];
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) z[i] = do_w ? (real)a.z[i] : real(0);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) shift[d] = (real)ctrl->shift[d];
+
+    const int tid = threadIdx.x;
+    const int64_t blk_base = (int64_t)blockIdx.x * kK1Block;
+    real xs[kK1Quads][NX][4];
+    real lw[kK1Quads][4];
+    const real NEG_INF = -INFINITY;
+
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q) {
+        const int64_t i0 = blk_base + (int64_t)(q * kThreads + tid) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lw[q][j] = NEG_INF;
+        if (i0 < a.n) {
+#pragma unroll
+            for (int d = 0; d < NX; ++d) load4<real>(x + d * a.ld + i0, xs[q][d]);
+            if (do_prop) {
+                real nrm[NX][4];
+                if (a.noise) {
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
+                } else {
+                    Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    real xv[NX], nv[NX];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) { xv[d] = xs[q][d][j]; nv[d] = nrm[d][j]; }
+                    m.propagate(xv, nv);
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xs[q][d][j] = xv[d];
+                }
+#pragma unroll
+                for (int d = 0; d < NX; ++d) store4<real>(x + d * a.ld + i0, xs[q][d]);
+            }
+            if (do_w) {
+                real prev[4];
+                if (uniform) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prev[j] = lw_uniform;
+                } else {
+                    load4<real>(a.logw + i0, prev);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prev[j] = prev_logweight(prev[j], log_norm_prev);
+                }
+                real out[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    real xv[NX];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xv[d] = xs[q][d][j];
+                    real v = prev[j] + m.loglik(xv, z);
+                    const bool valid = (i0 + j) < a.n;
+                    out[j] = valid ? v : NEG_INF;
+                    lw[q][j] = (valid && v == v) ? v : NEG_INF;   // NaN counts as zero weight
+                }
+                store4<real>(a.logw + i0, out);
+            }
+        }
+    }
+    if (!do_w) return;
+
+    // ---- block max -------------------------------------------------------------------------
+    real tmax = NEG_INF;
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmax = lw[q][j] > tmax ? lw[q][j] : tmax;
+    tmax = warp_max(tmax);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) s_max[warp] = tmax;
+    __syncthreads();
+    real bmax = s_max[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) bmax = s_max[w] > bmax ? s_max[w] : bmax;
+    const real mref = (bmax == NEG_INF) ? real(0) : bmax;
+
+    // ---- sums relative to the block max ----------------------------------------------------
+    real acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) acc[k] = 0;
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            real e = fast_exp(lw[q][j] - mref);   // exp(-inf) = 0 for padding / zero weights
+            acc[0] += e;
+            acc[1] = fma(e, e, acc[1]);
+            real xc[NX];
+#pragma unroll
+            for (int d = 0; d < NX; ++d) xc[d] = (lw[q][j] == NEG_INF) ? real(0) : xs[q][d][j] - shift[d];
+            int k = 2;
+#pragma unroll
+            for (int d = 0; d < NX; ++d) { acc[k] = fma(e, xc[d], acc[k]); ++k; }
+#pragma unroll
+            for (int d = 0; d < NX; ++d)
+#pragma unroll
+                for (int d2 = 0; d2 <= d; ++d2) { acc[k] = fma(e * xc[d], xc[d2], acc[k]); ++k; }
+        }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        real v = warp_sum(acc[k]);
+        if (lane == 0) s_red[warp][k] = (double)v;
+    }
+    __syncthreads();
+    if (tid < NR + 1) {
+        double* out = a.parts + (int64_t)blockIdx.x * partial_stride(NX);
+        if (tid == 0) {
+            out[0] = (double)bmax;
+        } else {
+            double s = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += s_red[w][tid - 1];
+            out[tid] = s;
+        }
+    }
+}
+
+// ==============================================================================================
+// K2: finalize.  One CTA reduces the partial records in a fixed order.
+// ==============================================================================================
+struct K2Args {
+    Ctrl* ctrl;
+    const double* parts;
+    double* stats;     // nullable
+    int64_t n_global;
+    int32_t n_parts, nx, inline_moments;
+    double thresh, u_host;
+    uint64_t seed;
+    uint32_t t;
+};
+
+__device__ inline double block_sum_256(double v, double* s_tmp) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) r += s_tmp[w];
+    return r;
+}
+__device__ inline double block_max_256(double v, double* s_tmp) {
+    v = warp_max(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    double r = s_tmp[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) r = s_tmp[w] > r ? s_tmp[w] : r;
+    return r;
+}
+
+// Combine partial records (max-shifted sums) into one record `out` of the same layout
+// (out[0] = global max, sums relative to it).  All threads of the CTA return the record in smem.
+__device__ inline void combine_partials(const double* parts, int n_parts, int ps, double* s_out,
+                                        double* s_tmp) {
+    const int tid = threadIdx.x;
+    double m = -INFINITY;
+    for (int p = tid; p < n_parts; p += kThreads) {
+        double v = parts[(int64_t)p * ps];
+        m = v > m ? v : m;
+    }
+    const double M = block_max_256(m, s_tmp);
+    const double Mref = (M == -INFINITY) ? 0.0 : M;
+    for (int k = 1; k < ps; ++k) {
+        double acc = 0;
+        for (int p = tid; p < n_parts; p += kThreads) {
+            const double* r = parts + (int64_t)p * ps;
+            double sc = exp(r[0] - Mref);           // r[0] = -inf -> 0
+            if (k == 2) sc *= sc;                    // sum e^2 scales with the square
+            acc = fma(r[k], sc, acc);
+        }
+        double tot = block_sum_256(acc, s_tmp);
+        if (tid == 0) s_out[k] = tot;
+    }
+    if (tid == 0) s_out[0] = M;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) k2_reduce_partials(const double* parts, int n_parts, int ps,
+                                                               double* out) {
+    __shared__ double s_out[32];
+    __shared__ double s_tmp[kWarps];
+    combine_partials(parts, n_parts, ps, s_out, s_tmp);
+    if (threadIdx.x < ps) out[threadIdx.x] = s_out[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
+    __shared__ double s_out[32];
+    __shared__ double s_tmp[kWarps];
+    const int ps = a.inline_moments ? partial_stride(a.nx) : 3;
+    combine_partials(a.parts, a.n_parts, ps, s_out, s_tmp);
+    if (threadIdx.x != 0) return;
+    Ctrl* c = a.ctrl;
+    const double M = s_out[0], S = s_out[1], Q = s_out[2];
+    const double log_norm = M + log(S);
+    const double ess = (S * S) / Q;
+    const int do_res = ess < a.thresh * (double)a.n_global;   // strict <, particle_filter.py:204
+    double u = a.u_host;
+    if (u < 0.0) {
+        uint32_t r[4] = {0u, 0u, a.t, kStreamResample};
+        philox4x32_10(r, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        u = uniform53(r[0], r[1]);
+    }
+    c->log_norm = log_norm;
+    c->ess = ess;
+    c->u = u;
+    c->do_resample = do_res;
+    c->uniform = 0;
+    if (a.stats) {
+        a.stats[0] = log_norm;
+        a.stats[1] = ess;
+        a.stats[2] = (double)do_res;
+        a.stats[3] = u;
+        if (a.inline_moments) {
+            const int nx = a.nx;
+            double* mean = a.stats + SMC_STATS_HEADER;
+            double* cov = mean + nx;
+            double m1[kFusedNxMax];
+            for (int d = 0; d < nx; ++d) {
+                m1[d] = s_out[3 + d] / S;
+                mean[d] = c->shift[d] + m1[d];
+            }
+            int k = 3 + nx;
+            for (int d = 0; d < nx; ++d)
+                for (int d2 = 0; d2 <= d; ++d2) {
+                    double v = s_out[k++] / S - m1[d] * m1[d2];
+                    cov[d * nx + d2] = v;
+                    cov[d2 * nx + d] = v;
+                }
+        }
+    }
+}
+
+// ==============================================================================================
+// K3: single-pass systematic resampler
+// ==============================================================================================
+// Exact predicate "pos_i < c" with pos_i = fl(fl(u + i) / N) (particle_filter.py:160) and the
+// CDF value c = C / (N 2^32) given in fixed point.  Integer arithmetic only after the fp64 position.
+__device__ inline bool pos_less(int64_t i, unsigned long long C, double u, int64_t N) {
+    const double p = (u + (double)i) / (double)N;       // IEEE fp64, same two roundings as NumPy
+    if (!(p > 0.0)) return C > 0ull;                     // p == 0  (u = 0, i = 0)
+    int ex;
+    const double fr = frexp(p, &ex);                     // p = fr * 2^ex, fr in [0.5, 1)
+    const unsigned long long mant = (unsigned long long)ldexp(fr, 53);   // 53-bit integer
+    const int e2 = ex - 53;                              // p = mant * 2^e2
+    // p * N * 2^32 < C  <=>  floor(mant * N / 2^s) < C  with s = -(e2 + 32) > 0
+    const int s = -(e2 + kFracBits);
+    unsigned __int128 prod = (unsigned __int128)mant * (unsigned __int128)(unsigned long long)N;
+    if (s >= 128) return C > 0ull;
+    if (s > 0) prod >>= s; else prod <<= (-s);
+    return prod < (unsigned __int128)C;
+}
+
+struct SearchParams {
+    double u;
+    uint32_t uq;        // floor(u * 2^32)
+    uint32_t margin;    // |frac - uq| <= margin -> exact path
+    int64_t n_global;
+};
+
+// e(C) = #{ i in [0, N) : pos_i < C }  (first output index NOT owned by CDF value C)
+__device__ inline int64_t outputs_below(unsigned long long C, const SearchParams& sp) {
+    const int64_t I = (int64_t)(C >> kFracBits);
+    const uint32_t f = (uint32_t)C;
+    int64_t e = I + (f > sp.uq ? 1 : 0);
+    const uint32_t diff = f > sp.uq ? f - sp.uq : sp.uq - f;
+    if (e > sp.n_global) e = sp.n_global;
+    if (diff <= sp.margin || diff >= 0xffffffffu - sp.margin) {
+        while (e > 0 && !pos_less(e - 1, C, sp.u, sp.n_global)) --e;
+        while (e < sp.n_global && pos_less(e, C, sp.u, sp.n_global)) ++e;
+    }
+    return e;
+}
+
+template <typename real> struct K3Args {
+    Ctrl* ctrl;
+    const real* wsrc;           // log-weights (or linear normalised weights)
+    const real* x0;
+    const real* x1;
+    real* dst0;                 // destination when ctrl->cur == 1  (i.e. buffer 0)
+    real* dst1;                 // destination when ctrl->cur == 0  (i.e. buffer 1)
+    real* const* peer0;         // nullable: per-shard destination pointers (cur == 1 / cur == 0)
+    real* const* peer1;
+    int32_t* ancestors;         // nullable
+    unsigned long long* agg;
+    unsigned long long* incl;
+    unsigned int* ticket;
+    double* mom_parts;          // nullable
+    unsigned long long cdf_offset;
+    int64_t n, n_global, offset, ld, shard_n;
+    int32_t force;              // ignore ctrl->do_resample (stand-alone use)
+};
+
+template <typename real> struct K3Geom;
+template <> struct K3Geom<float> {
+    static constexpr int IPT = 16, EPU = 4;
+    using unit = float4;
+};
+template <> struct K3Geom<double> {
+    static constexpr int IPT = 8, EPU = 2;
+    using unit = double2;
+};
+
+__device__ inline void unit_to_array(const float4& u, float* v) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
+__device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; v[1] = u.y; }
+
+__device__ inline unsigned long long to_fixed(float v) { return __float2ull_rn(v * 4294967296.0f); }
+__device__ inline unsigned long long to_fixed(double v) { return __double2ull_rn(v * 4294967296.0); }
+
+// decoupled look-back over tile aggregates / inclusive prefixes (integer -> order independent)
+__device__ inline unsigned long long lookback(volatile unsigned long long* agg,
+                                              volatile unsigned long long* incl, int64_t tile, int lane) {
+    unsigned long long sum = 0;
+    int64_t p = tile - 1 - lane;
+    while (true) {
+        unsigned long long vi = kValidBit, va = 0;   // tiles before 0: inclusive prefix 0
+        if (p >= 0) {
+            vi = incl[p];
+            va = (vi & kValidBit) ? 0ull : agg[p];
+        }
+        const bool have_i = (vi & kValidBit) != 0, have_a = (va & kValidBit) != 0;
+        const unsigned mask_i = __ballot_sync(0xffffffffu, have_i);
+        const int first = mask_i ? (__ffs(mask_i) - 1) : 32;
+        const bool missing = (lane < first) && !have_a;
+        if (__ballot_sync(0xffffffffu, missing)) continue;     // someone not published yet: re-read
+        unsigned long long contrib = 0;
+        if (lane < first) contrib = va & ~kValidBit;
+        else if (lane == first) contrib = vi & ~kValidBit;
+        sum += warp_sum(contrib);
+        if (first < 32) break;
+        p -= 32;
+    }
+    return sum;
+}
+
+template <typename real, int NXF, bool LINEAR_W>
+__global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
+    using G = K3Geom<real>;
+    using unit = typename G::unit;
+    constexpr int IPT = G::IPT, EPU = G::EPU;
+    constexpr int TILE = kThreads * IPT;
+    constexpr int UPT = IPT / EPU;                    // 16-byte units per thread (= 4)
+    constexpr int CH = IPT + 2;                       // fill chunk per thread (even)
+    constexpr int W = kThreads * CH;                  // output window (tile + 12.5 % / 25 % slack)
+    constexpr int NM = NXF + NXF * (NXF + 1) / 2;
+    static_assert(UPT == 4, "layout assumes 4 x 16B units per thread");
+    static_assert(CH % 2 == 0, "fill chunk must be word aligned");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unit* lw_s = reinterpret_cast<unit*>(smem_raw);                       // TILE reals, swizzled
+    unsigned short* out_s = reinterpret_cast<unsigned short*>(smem_raw);  // aliases lw_s (W * 2 B)
+    real* x_s = reinterpret_cast<real*>(smem_raw + sizeof(real) * TILE);  // NXF * TILE reals
+    __shared__ unsigned long long s_warp_tot[kWarps];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_E[2];
+    __shared__ unsigned int s_tile;
+    __shared__ int s_wmax[kWarps];
+    __shared__ double s_mom[kWarps][NM > 0 ? NM : 1];
+
+    Ctrl* ctrl = a.ctrl;
+    if (!a.force && !ctrl->do_resample) return;
+    const int cur = ctrl->cur;
+    const real* xsrc = cur ? a.x1 : a.x0;
+    real* xdst = cur ? a.dst0 : a.dst1;
+    real* const* peer = cur ? a.peer0 : a.peer1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t tile_base = tile * TILE;
+
+    SearchParams sp;
+    sp.u = ctrl->u;
+    sp.uq = (uint32_t)__double2ull_rd(sp.u * 4294967296.0);
+    sp.margin = 4u + (uint32_t)(a.n_global >> 19);
+    sp.n_global = a.n_global;
+    // weight = exp(lw - log_norm) * N  =  exp(lw - (log_norm - log N))
+    const real lw_ref = LINEAR_W ? real(0) : (real)(ctrl->log_norm - log((double)a.n_global));
+    const real n_real = (real)a.n_global;
+
+    // ---- phase A: coalesced loads -> shared ------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < UPT; ++r) {
+        const int f = r * kThreads + tid;                       // logical 16B unit in the tile
+        const int64_t i0 = tile_base + (int64_t)f * EPU;
+        unit v;
+        real fill = LINEAR_W ? real(0) : real(-INFINITY);
+        real tmp[EPU];
+        if (i0 < a.n) {
+            v = *reinterpret_cast<const unit*>(a.wsrc + i0);
+            unit_to_array(v, tmp);
+#pragma unroll
+            for (int j = 0; j < EPU; ++j) if (i0 + j >= a.n) tmp[j] = fill;
+        } else {
+#pragma unroll
+            for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+        }
+        real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & 3)]);
+#pragma unroll
+        for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
+        if (NXF > 0 && i0 < a.n) {
+#pragma unroll
+            for (int d = 0; d < NXF; ++d)
+                *reinterpret_cast<unit*>(x_s + d * TILE + f * EPU) =
+                    *reinterpret_cast<const unit*>(xsrc + d * a.ld + i0);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: fixed-point weights, block scan, look-back ---------------------------------
+    unsigned long long c[IPT];
+    {
+        unsigned long long run = 0;
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+            const int g = UPT * tid + k;
+            real tmp[EPU];
+            unit_to_array(lw_s[g ^ ((g >> 3) & 3)], tmp);
+#pragma unroll
+            for (int j = 0; j < EPU; ++j) {
+                real v = LINEAR_W ? tmp[j] * n_real : fast_exp(tmp[j] - lw_ref);
+                v = (v > real(0)) ? v : real(0);             // NaN / negative -> 0
+                v = v < n_real ? v : n_real;
+                run += to_fixed(v);
+                c[k * EPU + j] = run;                        // inclusive within thread
+            }
+        }
+        unsigned long long incl_w = run;                     // warp inclusive scan of thread totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
+            if (lane >= o) incl_w += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl_w;
+        __syncthreads();   // also: everyone is done reading lw_s
+        unsigned long long warp_excl = 0, tile_agg = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            unsigned long long t = s_warp_tot[w];
+            if (w < warp) warp_excl += t;
+            tile_agg += t;
+        }
+        if (warp == 0) {
+            volatile unsigned long long* vagg = a.agg;
+            volatile unsigned long long* vincl = a.incl;
+            if (tile == 0) {
+                if (lane == 0) {
+                    vincl[0] = kValidBit | (a.cdf_offset + tile_agg);
+                    s_prefix = a.cdf_offset;
+                }
+            } else {
+                if (lane == 0) vagg[tile] = kValidBit | tile_agg;
+                unsigned long long pre = lookback(vagg, vincl, tile, lane);
+                if (lane == 0) {
+                    vincl[tile] = kValidBit | (pre + tile_agg);
+                    s_prefix = pre;
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long base = s_prefix + warp_excl + (incl_w - run);   // exclusive of thread
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) c[k] += base;
+        // ---- phase C: output boundaries ------------------------------------------------------
+        // e[k] = number of outputs whose position lies below the CDF value after item k
+        long long e_prev = outputs_below(base, sp);
+        long long e[IPT];
+        const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;     // global index of item 0
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            long long v = outputs_below(c[k], sp);
+            if (j0 + k >= a.n_global - 1) v = a.n_global;    // cumsum[-1] = 1.0 clamp, :163
+            e[k] = v;
+        }
+        // (padding items beyond the shard carry zero weight, hence no outputs of their own)
+        if (tid == 0) s_E[0] = e_prev;
+        if (tid == kThreads - 1) s_E[1] = e[IPT - 1];
+        __syncthreads();
+        const long long E0 = s_E[0], E1 = s_E[1];
+        const long long count = E1 - E0;
+
+        real macc[NM > 0 ? NM : 1];
+#pragma unroll
+        for (int k = 0; k < (NM > 0 ? NM : 1); ++k) macc[k] = 0;
+        real shift[NXF > 0 ? NXF : 1];
+#pragma unroll
+        for (int d = 0; d < NXF; ++d) shift[d] = (real)ctrl->shift[d];
+
+        for (long long wbase = 0; wbase < count; wbase += W) {
+            // 1. clear the window
+            {
+                uint4* o4 = reinterpret_cast<uint4*>(out_s);
+                for (int p = tid; p < W * 2 / 16; p += kThreads) o4[p] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+            // 2. head markers (local index + 1) at the first output of every item with offspring
+            {
+                long long ep = e_prev;
+#pragma unroll
+                for (int k = 0; k < IPT; ++k) {
+                    const long long r0 = ep - E0, r1 = e[k] - E0;
+                    if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
+                        const long long pos = (r0 > wbase ? r0 : wbase) - wbase;
+                        out_s[pos] = (unsigned short)(tid * IPT + k + 1);
+                    }
+                    ep = e[k];
+                }
+            }
+            __syncthreads();
+            // 3. forward fill = inclusive max-scan (markers increase with position)
+            {
+                uint32_t* o32 = reinterpret_cast<uint32_t*>(out_s) + tid * (CH / 2);
+                uint32_t wv[CH / 2];
+                int tmax = 0;
+#pragma unroll
+                for (int k = 0; k < CH / 2; ++k) {
+                    wv[k] = o32[k];
+                    int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                    tmax = max(tmax, max(lo, hi));
+                }
+                int inc = tmax;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc = max(inc, t);
+                }
+                int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+                if (lane == 0) excl = 0;
+                if (lane == 31) s_wmax[warp] = inc;
+                __syncthreads();
+                int carry = excl;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
+#pragma unroll
+                for (int k = 0; k < CH / 2; ++k) {
+                    int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                    lo = max(lo, carry); carry = lo;
+                    hi = max(hi, carry); carry = hi;
+                    o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+                }
+            }
+            __syncthreads();
+            // 4. coalesced copy-out with the shared-memory-staged gather
+            {
+                const long long rem = count - wbase;
+                const int cnt = rem < W ? (int)rem : W;
+                for (int p = tid; p < cnt; p += kThreads) {
+                    const int li = (int)out_s[p] - 1;                    // local ancestor
+                    const int64_t gi = E0 + wbase + p;                   // global output index
+                    int64_t di = gi - a.offset;                          // local destination index
+                    real* dbase = xdst;
+                    if (peer) {
+                        const int64_t r = gi / a.shard_n;
+                        dbase = peer[r];
+                        di = gi - r * a.shard_n;
+                    }
+                    if (a.ancestors && !peer) a.ancestors[di] = (int32_t)(a.offset + tile_base + li);
+                    if (NXF > 0) {
+                        real xv[NXF > 0 ? NXF : 1];
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d) {
+                            xv[d] = x_s[d * TILE + li];
+                            dbase[d * a.ld + di] = xv[d];
+                        }
+                        int k = 0;
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d)
+#pragma unroll
+                            for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- per-tile post-resample moment partials -------------------------------------------
+        if (NM > 0 && a.mom_parts) {
+#pragma unroll
+            for (int k = 0; k < NM; ++k) {
+                double v = warp_sum((double)macc[k]);
+                if (lane == 0) s_mom[warp][k] = v;
+            }
+            __syncthreads();
+            if (tid < NM) {
+                double s = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) s += s_mom[w][tid];
+                a.mom_parts[tile * NM + tid] = s;
+            }
+        }
+    }
+}
+
+// shard total of the fixed-point weights (integer atomics: order independent)
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_shard_total(const Ctrl* ctrl, const real* logw, int64_t n,
+                                                          int64_t n_global, unsigned long long* total) {
+    const real lw_ref = (real)(ctrl->log_norm - log((double)n_global));
+    const real n_real = (real)n_global;
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        real v = fast_exp(logw[i] - lw_ref);
+        v = (v > real(0)) ? v : real(0);
+        v = v < n_real ? v : n_real;
+        acc += to_fixed(v);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+
+// ==============================================================================================
+// finish step: post-resample moments, buffer flip, shift refresh
+// ==============================================================================================
+__global__ void __launch_bounds__(kThreads) k_finish_step(Ctrl* ctrl, double* stats, const double* mom_parts,
+                                                          int n_mom_parts, int nx, int inline_moments,
+                                                          int64_t n_global, int no_moments) {
+    __shared__ double s_tmp[kWarps];
+    __shared__ double s_m[16];
+    const int tid = threadIdx.x;
+    const int do_res = ctrl->do_resample;
+    if (do_res && inline_moments && !no_moments && stats) {
+        const int nm = moment_stride(nx);
+        for (int k = 0; k < nm; ++k) {
+            double acc = 0;
+            for (int p = tid; p < n_mom_parts; p += kThreads) acc += mom_parts[(int64_t)p * nm + k];
+            double tot = block_sum_256(acc, s_tmp);
+            if (tid == 0) s_m[k] = tot;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double* mean = stats + SMC_STATS_HEADER;
+            double* cov = mean + nx;
+            const double inv = 1.0 / (double)n_global;
+            double m1[kFusedNxMax];
+            for (int d = 0; d < nx; ++d) { m1[d] = s_m[d] * inv; mean[d] = ctrl->shift[d] + m1[d]; }
+            int k = nx;
+            for (int d = 0; d < nx; ++d)
+                for (int d2 = 0; d2 <= d; ++d2) {
+                    double v = s_m[k++] * inv - m1[d] * m1[d2];
+                    cov[d * nx + d2] = v;
+                    cov[d2 * nx + d] = v;
+                }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (do_res) { ctrl->cur ^= 1; ctrl->uniform = 1; }
+        if (stats && !no_moments)
+            for (int d = 0; d < nx && d < kMaxNx; ++d) ctrl->shift[d] = stats[SMC_STATS_HEADER + d];
+    }
+}
+
+// ==============================================================================================
+// generic (any nx) moments: one CTA per mean entry / per lower-triangular covariance entry.
+// Reads ctrl: weighted by exp(logw - log_norm) when the step did not resample, uniform otherwise.
+// ==============================================================================================
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_moments_generic(const Ctrl* ctrl, const real* x0, const real* x1,
+                                                              const real* logw, int64_t n, int64_t n_global,
+                                                              int64_t ld, int nx, double* stats, int post_flip) {
+    // post_flip: 1 = called after finish_step flipped `cur` (use cur as is); 0 = before
+    __shared__ double s_tmp[kWarps];
+    const int cur = ctrl->cur ^ ((ctrl->do_resample && !post_flip) ? 1 : 0);
+    const real* x = cur ? x1 : x0;
+    const bool weighted = !ctrl->do_resample;
+    const double log_norm = ctrl->log_norm;
+    const int b = blockIdx.x;
+    int d, d2;
+    if (b < nx) { d = b; d2 = -1; }
+    else {
+        int t = b - nx; d = 0;
+        while (t >= d + 1) { t -= d + 1; ++d; }
+        d2 = t;
+    }
+    const double c1 = ctrl->shift[d < kMaxNx ? d : 0] * (d < kMaxNx);
+    const double c2 = d2 >= 0 ? ctrl->shift[d2 < kMaxNx ? d2 : 0] * (d2 < kMaxNx) : 0.0;
+    double acc = 0, accw = 0;
+    for (int64_t i = threadIdx.x; i < n; i += kThreads) {
+        double w = weighted ? exp((double)logw[i] - log_norm) : 1.0;
+        double a = (double)x[d * ld + i] - c1;
+        double v = d2 >= 0 ? a * ((double)x[d2 * ld + i] - c2) : a;
+        acc = fma(w, v, acc);
+        accw += w;
+    }
+    double tot = block_sum_256(acc, s_tmp);
+    double totw = block_sum_256(accw, s_tmp);
+    if (threadIdx.x == 0) {
+        // raw shifted moments; k_moments_generic_fix turns them into mean / cov
+        double* raw = stats + SMC_STATS_HEADER;
+        if (d2 < 0) raw[d] = tot / totw;
+        else raw[nx + d * nx + d2] = tot / totw;
+    }
+    (void)n_global;
+}
+__global__ void k_moments_generic_fix(const Ctrl* ctrl, int nx, double* stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double* mean = stats + SMC_STATS_HEADER;
+    double* cov = mean + nx;
+    for (int d = 0; d < nx; ++d)
+        for (int d2 = 0; d2 <= d; ++d2) {
+            double v = cov[d * nx + d2] - mean[d] * mean[d2];
+            cov[d * nx + d2] = v;
+            cov[d2 * nx + d] = v;
+        }
+    for (int d = 0; d < nx; ++d) mean[d] += (d < kMaxNx ? ctrl->shift[d] : 0.0);
+}
+
+// ==============================================================================================
+// small utility kernels
+// ==============================================================================================
+__global__ void k_reset_ctrl(Ctrl* c, const double* shift, int nx) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        c->log_norm = 0.0; c->ess = 0.0; c->u = 0.0; c->cur = 0; c->uniform = 1; c->do_resample = 0; c->pad = 0;
+        for (int d = 0; d < kMaxNx; ++d) c->shift[d] = (shift && d < nx) ? shift[d] : 0.0;
+    }
+}
+__global__ void k_set_uniform(Ctrl* c, double u) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) c->u = u;
+}
+__global__ void k_set_resample(Ctrl* c, double u) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { c->u = u; c->do_resample = 1; c->cur = 0; c->log_norm = 0.0; }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_init_gaussian(Ctrl* ctrl, real* x0, real* x1, int64_t n, int64_t offset,
+                                                            int64_t ld, int nx, const double* mean, const double* Lc,
+                                                            uint64_t seed) {
+    real* x = ctrl->cur ? x1 : x0;
+    const int64_t quad = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t i0 = quad * 4;
+    if (i0 >= n) return;
+    // nx can be large here: draw dimension by dimension, accumulate the triangular product
+    for (int d = 0; d < nx; ++d) {
+        double acc[4] = {mean[d], mean[d], mean[d], mean[d]};
+        for (int k = 0; k <= d; ++k) {
+            double z4[4];
+            uint32_t r[4];
+            philox_quad(seed, (uint64_t)(offset + i0) >> 2, 0u, kStreamInit | (uint32_t(k) << 8), r);
+            double z2[2];
+            normals2_f64(r, z2); z4[0] = z2[0]; z4[1] = z2[1];
+            philox_quad(seed, (uint64_t)(offset + i0) >> 2, 0u, kStreamInit | (uint32_t(k) << 8) | (1u << 16), r);
+            normals2_f64(r, z2); z4[2] = z2[0]; z4[3] = z2[1];
+            const double l = Lc[d * nx + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fma(l, z4[j], acc[j]);
+        }
+        real out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = (real)acc[j];
+        store4<real>(x + d * ld + i0, out);
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_bridge_predict(Ctrl* ctrl, real* x0, real* x1, const real* gx,
+                                                             const real* noise, const double* Lq, double scale,
+                                                             int64_t n, int64_t ld, int nx, int target_other) {
+    real* x = (ctrl->cur ^ target_other) ? x1 : x0;
+    if (!gx) gx = x;   // in-place jitter: each thread reads then writes its own elements only
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    for (int d = nx - 1; d >= 0; --d) {
+        // (noise @ Lq.T)[i, d] = sum_k noise[i, k] Lq[d, k]   (particle_filter.py:236)
+        double acc = 0;
+        for (int k = 0; k <= d; ++k) acc = fma((double)noise[k * ld + i], Lq[d * nx + k] * scale, acc);
+        x[d * ld + i] = (real)((double)gx[d * ld + i] + acc);
+    }
+}
+
+// log-likelihood from host-evaluated h(x): one thread per particle, block partials as in K1
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_bridge_loglik(Ctrl* ctrl, real* logw, const real* zpred, const double* z,
+                                                            const double* LRinv, const real* wprev, int64_t n,
+                                                            int64_t n_global, int64_t ld, int nz, double* parts) {
+    __shared__ double s_tmp[kWarps];
+    const int tid = threadIdx.x;
+    double lw[kK1Block / kThreads];
+    double m = -INFINITY;
+    const double lw_uniform = log(1.0 / (double)n_global + 1e-300);
+#pragma unroll 1
+    for (int q = 0; q < kK1Block / kThreads; ++q) {
+        const int64_t i = (int64_t)blockIdx.x * kK1Block + q * kThreads + tid;
+        double v = -INFINITY;
+        if (i < n) {
+            double quad = 0;
+            for (int r = 0; r < nz; ++r) {        // y = LR^-1 (z - zpred), particle_filter.py:258-260
+                double acc = 0;
+                for (int k = 0; k <= r; ++k) acc = fma(LRinv[r * nz + k], z[k] - (double)zpred[k * ld + i], acc);
+                quad = fma(acc, acc, quad);
+            }
+            const double prev = wprev ? log((double)wprev[i] + 1e-300) : lw_uniform;   // :261
+            v = prev - 0.5 * quad;
+            logw[i] = (real)v;
+            if (!(v == v)) v = -INFINITY;
+        }
+        lw[q] = v;
+        m = v > m ? v : m;
+    }
+    const double bmax = block_max_256(m, s_tmp);
+    const double mref = bmax == -INFINITY ? 0.0 : bmax;
+    double s = 0, s2 = 0;
+#pragma unroll 1
+    for (int q = 0; q < kK1Block / kThreads; ++q) {
+        double e = exp(lw[q] - mref);
+        s += e;
+        s2 = fma(e, e, s2);
+    }
+    s = block_sum_256(s, s_tmp);
+    s2 = block_sum_256(s2, s_tmp);
+    if (tid == 0) {
+        double* out = parts + (int64_t)blockIdx.x * 3;
+        out[0] = bmax; out[1] = s; out[2] = s2;
+    }
+    (void)ctrl;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_export_weights(const Ctrl* ctrl, const real* logw, int64_t n,
+                                                             int64_t n_global, double* w) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    w[i] = ctrl->uniform ? 1.0 / (double)n_global : exp((double)logw[i] - ctrl->log_norm);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_gather(const real* src, real* dst, const int32_t* idx, int64_t n,
+                                                     int64_t ld, int nx) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = idx[i];
+    for (int d = 0; d < nx; ++d) dst[d * ld + i] = src[d * ld + j];
+}
+
+// gather for the non-fused (nx > kFusedNxMax) resampling path; honours ctrl->do_resample / cur
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_gather_step(const Ctrl* ctrl, const real* x0, const real* x1,
+                                                          real* d0, real* d1, const int32_t* idx, int64_t n,
+                                                          int64_t ld, int nx) {
+    if (!ctrl->do_resample) return;
+    const real* src = ctrl->cur ? x1 : x0;
+    real* dst = ctrl->cur ? d0 : d1;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = idx[i];
+    for (int d = 0; d < nx; ++d) dst[d * ld + i] = src[d * ld + j];
+}
+
+}  // namespace smc
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+using namespace smc;
+
+namespace {
+
+struct Launch {
+    const smc_sir_desc* d;
+    WsLayout L;
+    unsigned char* ws;
+    cudaStream_t st;
+    Ctrl* ctrl() const { return reinterpret_cast<Ctrl*>(ws + L.ctrl); }
+    double* slot(int k) const { return reinterpret_cast<double*>(ws + L.params) + (size_t)k * kParamSlotDoubles; }
+    double* k1_parts() const { return reinterpret_cast<double*>(ws + L.k1_parts); }
+    unsigned long long* agg() const { return reinterpret_cast<unsigned long long*>(ws + L.tile_agg); }
+    unsigned long long* incl() const { return reinterpret_cast<unsigned long long*>(ws + L.tile_incl); }
+    unsigned int* ticket() const { return reinterpret_cast<unsigned int*>(ws + L.ticket); }
+    double* mom_parts() const { return reinterpret_cast<double*>(ws + L.mom_parts); }
+};
+
+int check_desc(const smc_sir_desc* d, Launch* out, void* stream) {
+    SMC_REQUIRE(d != nullptr, "smc: null descriptor");
+    SMC_REQUIRE(d->n > 0 && d->n_global >= d->n, "smc: need 0 < n <= n_global (n=%lld n_global=%lld)",
+                (long long)d->n, (long long)d->n_global);
+    SMC_REQUIRE(d->n_global <= (1ll << 30), "smc: n_global=%lld exceeds 2^30", (long long)d->n_global);
+    SMC_REQUIRE(d->dtype == SMC_F32 || d->dtype == SMC_F64, "smc: bad dtype %d", d->dtype);
+    SMC_REQUIRE(d->ld % 4 == 0 && d->ld >= ((d->n + 3) / 4) * 4,
+                "smc: ld=%lld must be a multiple of 4 and >= round_up(n,4)", (long long)d->ld);
+    SMC_REQUIRE(d->offset % 4 == 0 && d->offset >= 0, "smc: shard offset must be a non-negative multiple of 4");
+    SMC_REQUIRE(d->nx >= 1, "smc: nx must be >= 1");
+    SMC_REQUIRE(d->ws_dev != nullptr, "smc: workspace missing");
+    out->d = d;
+    out->L = ws_layout(d->n, d->nx, d->dtype);
+    SMC_REQUIRE(d->ws_bytes >= out->L.total, "smc: workspace too small (%llu < %llu)",
+                (unsigned long long)d->ws_bytes, (unsigned long long)out->L.total);
+    out->ws = static_cast<unsigned char*>(d->ws_dev);
+    out->st = static_cast<cudaStream_t>(stream);
+    return 0;
+}
+
+// moments accumulated inside K1 / K3 (true) or by the any-nx kernel (false)
+inline bool inline_moments(const smc_sir_desc* d) {
+    return d->nx <= kFusedNxMax && !(d->flags & SMC_FLAG_GENERIC_MOMENTS);
+}
+
+// Small host arrays (matrices, observation) are staged into a parameter slot of the workspace.
+// cudaMemcpyAsync from pageable memory copies the source before returning, so the host buffer may
+// be reused at once; stream order protects the slot between consecutive calls.
+int stage(const Launch& l, int slot, const double* host, int count, double** dev) {
+    SMC_REQUIRE(count <= kParamSlotDoubles, "smc: parameter array too large (%d doubles)", count);
+    *dev = l.slot(slot);
+    SMC_CHECK_CUDA(cudaMemcpyAsync(*dev, host, sizeof(double) * count, cudaMemcpyHostToDevice, l.st));
+    return 0;
+}
+
+template <typename real, class Model>
+int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, const void* noise_dev, uint64_t seed,
+              int64_t t) {
+    const smc_sir_desc* d = l.d;
+    K1Args<real> a;
+    a.ctrl = l.ctrl();
+    a.x0 = static_cast<real*>(d->x0_dev);
+    a.x1 = static_cast<real*>(d->x1_dev);
+    a.logw = static_cast<real*>(d->logw_dev);
+    a.noise = static_cast<const real*>(noise_dev);
+    a.z = z_dev;
+    a.parts = l.k1_parts();
+    a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
+    a.seed = seed; a.t = (uint32_t)t; a.mode = mode;
+    k1_propagate_weight<real, Model><<<(unsigned)l.L.n_k1_blocks, kThreads, 0, l.st>>>(a, m);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename real> int dispatch_k1(const Launch& l, int model_id, const double* p, int np, int mode,
+                                         const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t) {
+    const smc_sir_desc* d = l.d;
+    if (model_id == SMC_MODEL_STOCH_VOL) {
+        // params: alpha, lq (= chol(Q)), beta, lr (= chol(R + 1e-12))
+        SMC_REQUIRE(np == 4 && d->nx == 1 && d->nz == 1, "smc: STOCH_VOL needs 4 params and nx = nz = 1");
+        StochVolModel<real> m;
+        m.alpha = (real)p[0]; m.lq = (real)p[1]; m.beta = (real)p[2]; m.rinv = (real)(1.0 / p[3]);
+        return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t);
+    }
+    if (model_id == SMC_MODEL_LINEAR_GAUSSIAN) {
+        // params: A (nx*nx), Lq (nx*nx lower), H (nz*nx), LRinv (nz*nz lower), all row-major
+        const int nx = d->nx, nz = d->nz;
+        SMC_REQUIRE(np == nx * nx * 2 + nz * nx + nz * nz, "smc: LINEAR_GAUSSIAN parameter count mismatch");
+#define SMC_LG_CASE(NX_, NZ_)                                                                     \
+        if (nx == NX_ && nz == NZ_) {                                                             \
+            LinGaussModel<real, NX_, NZ_> m;                                                      \
+            const double* q = p;                                                                  \
+            for (int i = 0; i < NX_ * NX_; ++i) m.A[i] = (real)*q++;                              \
+            for (int i = 0; i < NX_ * NX_; ++i) m.Lq[i] = (real)*q++;                             \
+            for (int i = 0; i < NZ_ * NX_; ++i) m.H[i] = (real)*q++;                              \
+            for (int i = 0; i < NZ_ * NZ_; ++i) m.LRinv[i] = (real)*q++;                          \
+            return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t);                        \
+        }
+        SMC_LG_CASE(1, 1) SMC_LG_CASE(2, 1) SMC_LG_CASE(2, 2) SMC_LG_CASE(4, 1) SMC_LG_CASE(4, 2) SMC_LG_CASE(4, 4)
+#undef SMC_LG_CASE
+        SMC_REQUIRE(false, "smc: LINEAR_GAUSSIAN supports (nx,nz) in {(1,1),(2,1),(2,2),(4,1),(4,2),(4,4)}, got (%d,%d)",
+                    nx, nz);
+    }
+    SMC_REQUIRE(false, "smc: unknown model id %d", model_id);
+}
+
+template <typename real, int NXF, bool LIN>
+int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
+    using G = K3Geom<real>;
+    const size_t smem = sizeof(real) * kThreads * G::IPT * (1 + NXF);
+    auto kern = k3_resample<real, NXF, LIN>;
+    static bool attr_set = false;   // one flag per template instantiation
+    if (!attr_set) {
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<(unsigned)n_tiles, kThreads, smem, l.st>>>(a);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename real>
+int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
+              void* const* peer, int n_shards, bool want_moments) {
+    const smc_sir_desc* d = l.d;
+    // clear tile state + ticket (contiguous in the layout)
+    SMC_CHECK_CUDA(cudaMemsetAsync(l.ws + l.L.tile_agg, 0, l.L.mom_parts - l.L.tile_agg, l.st));
+    K3Args<real> a;
+    a.ctrl = l.ctrl();
+    a.wsrc = static_cast<const real*>(wsrc);
+    a.x0 = static_cast<const real*>(d->x0_dev);
+    a.x1 = static_cast<const real*>(d->x1_dev);
+    a.dst0 = static_cast<real*>(d->x0_dev);
+    a.dst1 = static_cast<real*>(d->x1_dev);
+    a.peer0 = nullptr; a.peer1 = nullptr;
+    if (peer) {   // device array: [n_shards pointers to buffer 0][n_shards pointers to buffer 1]
+        a.peer0 = reinterpret_cast<real* const*>(peer);
+        a.peer1 = reinterpret_cast<real* const*>(peer) + n_shards;
+    }
+    a.ancestors = ((d->flags & SMC_FLAG_WRITE_ANCESTORS) || nxf == 0) ? d->ancestors_dev : nullptr;
+    a.agg = l.agg(); a.incl = l.incl(); a.ticket = l.ticket();
+    a.mom_parts = want_moments ? l.mom_parts() : nullptr;
+    a.cdf_offset = cdf_offset;
+    a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
+    a.shard_n = n_shards > 0 ? d->n_global / n_shards : d->n_global;
+    a.force = force;
+    const int64_t nt = l.L.n_tiles;
+    if (linear_w) {
+        SMC_REQUIRE(nxf == 0, "smc: linear-weight resampling is ancestors-only");
+        return launch_k3_t<real, 0, true>(l, a, nt);
+    }
+    switch (nxf) {
+        case 0: return launch_k3_t<real, 0, false>(l, a, nt);
+        case 1: return launch_k3_t<real, 1, false>(l, a, nt);
+        case 2: return launch_k3_t<real, 2, false>(l, a, nt);
+        case 3: return launch_k3_t<real, 3, false>(l, a, nt);
+        case 4: return launch_k3_t<real, 4, false>(l, a, nt);
+    }
+    SMC_REQUIRE(false, "smc: bad fused nx %d", nxf);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smc_abi_version(void) { return SMC_ABI_VERSION; }
+const char* smc_last_error(void) { return smc::g_err; }
+uint64_t smc_sizeof_sir_desc(void) { return sizeof(smc_sir_desc); }
+int64_t smc_partial_stride(int32_t nx) { return partial_stride(nx); }
+
+uint64_t smc_sir_workspace_bytes(int64_t n, int32_t nx, int32_t dtype) {
+    if (n < 1) n = 1;
+    return ws_layout(n, nx, dtype).total;
+}
+
+int smc_sir_reset(const smc_sir_desc* d, const double* shift_host, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    double* dev_shift = nullptr;
+    if (shift_host)
+        if (int rc = stage(l, 0, shift_host, d->nx < kMaxNx ? d->nx : kMaxNx, &dev_shift)) return rc;
+    k_reset_ctrl<<<1, 32, 0, l.st>>>(l.ctrl(), dev_shift, d->nx);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_init_gaussian(const smc_sir_desc* d, const double* mean_host, const double* Lc_host, uint64_t seed,
+                          void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const int nx = d->nx;
+    double *mean_dev, *lc_dev;
+    if (int rc = stage(l, 0, mean_host, nx, &mean_dev)) return rc;
+    if (int rc = stage(l, 1, Lc_host, nx * nx, &lc_dev)) return rc;
+    const int64_t quads = (d->n + 3) / 4;
+    const unsigned grid = (unsigned)cdiv64(quads, kThreads);
+    if (d->dtype == SMC_F32)
+        k_init_gaussian<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (float*)d->x0_dev, (float*)d->x1_dev, d->n, d->offset,
+                                                           d->ld, nx, mean_dev, lc_dev, seed);
+    else
+        k_init_gaussian<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (double*)d->x0_dev, (double*)d->x1_dev, d->n,
+                                                            d->offset, d->ld, nx, mean_dev, lc_dev, seed);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_propagate_weight(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
+                             int32_t mode, const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t,
+                             void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(mode >= 1 && mode <= 3, "smc: bad mode %d", mode);
+    SMC_REQUIRE(!(mode & SMC_MODE_WEIGHT) || z_dev, "smc: z_dev required when weighting");
+    SMC_REQUIRE(params_host != nullptr, "smc: params missing");
+    SMC_REQUIRE(!(d->flags & SMC_FLAG_GENERIC_MOMENTS), "smc: fused K1 carries inline moments; clear GENERIC_MOMENTS");
+    return d->dtype == SMC_F32 ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t)
+                               : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t);
+}
+
+int smc_bridge_predict(const smc_sir_desc* d, const void* gx_dev, const void* noise_dev, const double* Lq_host,
+                       double scale, int32_t target_other, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const int nx = d->nx;
+    SMC_REQUIRE(gx_dev || target_other, "smc: gx_dev may be NULL only with target_other = 1");
+    SMC_REQUIRE(noise_dev && Lq_host, "smc: noise / Lq missing");
+    double* lq_dev;
+    if (int rc = stage(l, 1, Lq_host, nx * nx, &lq_dev)) return rc;
+    const unsigned grid = (unsigned)cdiv64(d->n, kThreads);
+    if (d->dtype == SMC_F32)
+        k_bridge_predict<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (float*)d->x0_dev, (float*)d->x1_dev,
+                                                            (const float*)gx_dev, (const float*)noise_dev, lq_dev, scale,
+                                                            d->n, d->ld, nx, target_other ? 1 : 0);
+    else
+        k_bridge_predict<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (double*)d->x0_dev, (double*)d->x1_dev,
+                                                             (const double*)gx_dev, (const double*)noise_dev, lq_dev, scale,
+                                                             d->n, d->ld, nx, target_other ? 1 : 0);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_bridge_loglik(const smc_sir_desc* d, const void* zpred_dev, const double* z_host, const double* LRinv_host,
+                      const void* wprev_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(d->flags & SMC_FLAG_GENERIC_MOMENTS, "smc: bridge mode needs SMC_FLAG_GENERIC_MOMENTS");
+    const int nz = d->nz;
+    double *z_dev, *lr_dev;
+    if (int rc = stage(l, 2, z_host, nz, &z_dev)) return rc;
+    if (int rc = stage(l, 3, LRinv_host, nz * nz, &lr_dev)) return rc;
+    const unsigned grid = (unsigned)l.L.n_k1_blocks;
+    if (d->dtype == SMC_F32)
+        k_bridge_loglik<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (float*)d->logw_dev, (const float*)zpred_dev, z_dev,
+                                                           lr_dev, (const float*)wprev_dev, d->n, d->n_global, d->ld, nz,
+                                                           l.k1_parts());
+    else
+        k_bridge_loglik<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (double*)d->logw_dev, (const double*)zpred_dev, z_dev,
+                                                            lr_dev, (const double*)wprev_dev, d->n, d->n_global, d->ld, nz,
+                                                            l.k1_parts());
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_reduce_partials(const smc_sir_desc* d, double* out_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const int ps = inline_moments(d) ? partial_stride(d->nx) : 3;
+    k2_reduce_partials<<<1, kThreads, 0, l.st>>>(l.k1_parts(), (int)l.L.n_k1_blocks, ps, out_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_finalize(const smc_sir_desc* d, double resample_thresh, double u_host, uint64_t seed, int64_t t,
+                     double* stats_row_dev, const double* parts_dev, int32_t n_parts_override, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    K2Args a;
+    a.ctrl = l.ctrl();
+    a.parts = n_parts_override > 0 ? parts_dev : l.k1_parts();
+    a.n_parts = n_parts_override > 0 ? n_parts_override : (int)l.L.n_k1_blocks;
+    a.stats = stats_row_dev;
+    a.n_global = d->n_global;
+    a.nx = d->nx;
+    a.inline_moments = inline_moments(d) ? 1 : 0;
+    a.thresh = resample_thresh; a.u_host = u_host; a.seed = seed; a.t = (uint32_t)t;
+    k2_finalize<<<1, kThreads, 0, l.st>>>(a);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_set_uniform(const smc_sir_desc* d, double u, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
+    k_set_uniform<<<1, 32, 0, l.st>>>(l.ctrl(), u);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_shard_weight_total(const smc_sir_desc* d, uint64_t* total_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_CHECK_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), l.st));
+    int64_t g = cdiv64(d->n, kThreads * 16);
+    if (g > 148 * 8) g = 148 * 8;
+    const unsigned grid = (unsigned)g;
+    if (d->dtype == SMC_F32)
+        k_shard_total<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const float*)d->logw_dev, d->n, d->n_global,
+                                                         (unsigned long long*)total_dev);
+    else
+        k_shard_total<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const double*)d->logw_dev, d->n, d->n_global,
+                                                          (unsigned long long*)total_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* stats_row_dev, void* const* peer_x_dev,
+                     int32_t n_shards, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    (void)stats_row_dev;
+    const bool fused = d->nx <= kFusedNxMax;
+    const int nxf = fused ? d->nx : 0;
+    SMC_REQUIRE(fused || d->ancestors_dev, "smc: nx > %d needs an ancestors buffer for the two-pass gather", kFusedNxMax);
+    SMC_REQUIRE(!peer_x_dev || fused, "smc: cross-shard migration requires nx <= %d", kFusedNxMax);
+    SMC_REQUIRE(!peer_x_dev || (n_shards > 0 && d->n_global % n_shards == 0), "smc: bad shard count");
+    const bool want_m = inline_moments(d) && !(d->flags & SMC_FLAG_NO_MOMENTS);
+    int rc = d->dtype == SMC_F32
+                 ? launch_k3<float>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m)
+                 : launch_k3<double>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m);
+    if (rc) return rc;
+    if (!fused) {
+        const unsigned grid = (unsigned)cdiv64(d->n, kThreads);
+        if (d->dtype == SMC_F32)
+            k_gather_step<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const float*)d->x0_dev, (const float*)d->x1_dev,
+                                                             (float*)d->x0_dev, (float*)d->x1_dev, d->ancestors_dev, d->n,
+                                                             d->ld, d->nx);
+        else
+            k_gather_step<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const double*)d->x0_dev, (const double*)d->x1_dev,
+                                                              (double*)d->x0_dev, (double*)d->x1_dev, d->ancestors_dev,
+                                                              d->n, d->ld, d->nx);
+        SMC_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const double* mom_parts_dev, int32_t n_mom_parts,
+                        void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const int no_m = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0;
+    const bool inl = inline_moments(d);
+    if (!inl && !no_m && stats_row_dev) {
+        // any-nx moments straight into the stats row (weighted or uniform, decided on device)
+        SMC_REQUIRE(d->n == d->n_global, "smc: generic moments are single-shard only");
+        const int nx = d->nx;
+        const unsigned grid = (unsigned)(nx + nx * (nx + 1) / 2);
+        if (d->dtype == SMC_F32)
+            k_moments_generic<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const float*)d->x0_dev, (const float*)d->x1_dev,
+                                                                 (const float*)d->logw_dev, d->n, d->n_global, d->ld, nx,
+                                                                 stats_row_dev, 0);
+        else
+            k_moments_generic<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const double*)d->x0_dev,
+                                                                  (const double*)d->x1_dev, (const double*)d->logw_dev, d->n,
+                                                                  d->n_global, d->ld, nx, stats_row_dev, 0);
+        SMC_CHECK_CUDA(cudaGetLastError());
+        k_moments_generic_fix<<<1, 32, 0, l.st>>>(l.ctrl(), nx, stats_row_dev);
+        SMC_CHECK_CUDA(cudaGetLastError());
+    }
+    k_finish_step<<<1, kThreads, 0, l.st>>>(l.ctrl(), stats_row_dev, mom_parts_dev ? mom_parts_dev : l.mom_parts(),
+                                           n_mom_parts > 0 ? n_mom_parts : (int)l.L.n_tiles, d->nx, inl ? 1 : 0,
+                                           d->n_global, no_m);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_step(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
+                 const double* z_dev, const void* noise_dev, double resample_thresh, double u_host, uint64_t seed,
+                 int64_t t, double* stats_row_dev, void* stream) {
+    if (int rc = smc_sir_propagate_weight(d, model_id, params_host, n_params, SMC_MODE_STEP, z_dev, noise_dev, seed, t,
+                                          stream))
+        return rc;
+    if (int rc = smc_sir_finalize(d, resample_thresh, u_host, seed, t, stats_row_dev, nullptr, 0, stream)) return rc;
+    if (resample_thresh > 0.0)
+        if (int rc = smc_sir_resample(d, 0, stats_row_dev, nullptr, 0, stream)) return rc;
+    return smc_sir_finish_step(d, stats_row_dev, nullptr, 0, stream);
+}
+
+int smc_systematic_ancestors(const double* w_dev, int64_t n, double u, int32_t* ancestors_dev, void* ws_dev,
+                             uint64_t ws_bytes, void* stream) {
+    smc_sir_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = n; d.n_global = n; d.offset = 0; d.ld = ((n + 3) / 4) * 4; d.nx = 1; d.nz = 1; d.dtype = SMC_F64;
+    d.flags = SMC_FLAG_WRITE_ANCESTORS | SMC_FLAG_NO_MOMENTS;
+    d.ancestors_dev = ancestors_dev; d.ws_dev = ws_dev; d.ws_bytes = ws_bytes;
+    Launch l;
+    if (int rc = check_desc(&d, &l, stream)) return rc;
+    SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
+    SMC_REQUIRE(w_dev && ancestors_dev, "smc: null buffer");
+    k_set_resample<<<1, 32, 0, l.st>>>(l.ctrl(), u);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return launch_k3<double>(l, true, w_dev, 0, 0ull, 1, nullptr, 0, false);
+}
+
+int smc_gather(const void* src_dev, void* dst_dev, const int32_t* idx_dev, int64_t n, int64_t ld, int32_t nx,
+               int32_t dtype, void* stream) {
+    SMC_REQUIRE(n > 0 && nx > 0 && ld >= n, "smc_gather: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)cdiv64(n, kThreads);
+    if (dtype == SMC_F32)
+        k_gather<float><<<grid, kThreads, 0, st>>>((const float*)src_dev, (float*)dst_dev, idx_dev, n, ld, nx);
+    else if (dtype == SMC_F64)
+        k_gather<double><<<grid, kThreads, 0, st>>>((const double*)src_dev, (double*)dst_dev, idx_dev, n, ld, nx);
+    else
+        SMC_REQUIRE(false, "smc_gather: bad dtype");
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_export_weights(const smc_sir_desc* d, double* w_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const unsigned grid = (unsigned)cdiv64(d->n, kThreads);
+    if (d->dtype == SMC_F32)
+        k_export_weights<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const float*)d->logw_dev, d->n, d->n_global, w_dev);
+    else
+        k_export_weights<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const double*)d->logw_dev, d->n, d->n_global,
+                                                             w_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_current_buffer(const smc_sir_desc* d, int32_t* cur_host, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    Ctrl h;
+    SMC_CHECK_CUDA(cudaMemcpyAsync(&h, l.ctrl(), sizeof(Ctrl), cudaMemcpyDeviceToHost, l.st));
+    SMC_CHECK_CUDA(cudaStreamSynchronize(l.st));
+    *cur_host = h.cur;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+"""Device-resident SIR engine: torch tensors hold the particle arrays, every
+operation is a libsmc (CUDA, sm_100a) call enqueued on the current stream.
+
+PyTorch is plumbing here (allocation, streams, H2D/D2H); no torch op touches
+the particle data on the hot path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import SirDesc, check
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise _lib.SmcError("the SMC engine needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def _round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class SirEngine:
+    """One shard of an SIR particle population on one GPU.
+
+    Arrays (SoA, see include/smc.h): ``x0/x1`` ping-pong particles ``(nx, ld)``,
+    ``logw`` ``(ld,)``, optional int32 ``ancestors``, a byte workspace, and a
+    device trace of per-step statistic rows.
+    """
+
+    def __init__(self, n: int, nx: int, nz: int, *, dtype: str = "f32", device=None,
+                 n_global: Optional[int] = None, offset: int = 0, write_ancestors: bool = False,
+                 generic_moments: bool = False, trace_len: int = 1):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.nx, self.nz = int(n), int(nx), int(nz)
+        self.n_global = self.n if n_global is None else int(n_global)
+        self.offset = int(offset)
+        self.dtype_code = {"f32": _lib.SMC_F32, "f64": _lib.SMC_F64}[dtype]
+        self.tdtype = torch.float32 if dtype == "f32" else torch.float64
+        self.npdtype = np.float32 if dtype == "f32" else np.float64
+        self.ld = _round4(self.n)
+        self.generic_moments = bool(generic_moments) or self.nx > 4
+        with torch.cuda.device(self.device):
+            self.x = [torch.zeros((self.nx, self.ld), dtype=self.tdtype, device=self.device) for _ in range(2)]
+            self.logw = torch.zeros((self.ld,), dtype=self.tdtype, device=self.device)
+            need_anc = write_ancestors or self.nx > 4
+            self.ancestors = (torch.zeros((self.ld,), dtype=torch.int32, device=self.device)
+                              if need_anc else None)
+            ws_bytes = int(self.lib.smc_sir_workspace_bytes(self.n, self.nx, self.dtype_code))
+            self.ws = torch.zeros((ws_bytes,), dtype=torch.uint8, device=self.device)
+            self.stride = _lib.stats_stride(self.nx)
+            self.trace = torch.zeros((max(1, trace_len), self.stride), dtype=torch.float64, device=self.device)
+            self.zbuf = torch.zeros((max(1, trace_len), self.nz), dtype=torch.float64, device=self.device)
+        flags = 0
+        if write_ancestors:
+            flags |= _lib.SMC_FLAG_WRITE_ANCESTORS
+        if self.generic_moments:
+            flags |= _lib.SMC_FLAG_GENERIC_MOMENTS
+        self.desc = SirDesc(
+            n=self.n, n_global=self.n_global, offset=self.offset, ld=self.ld, nx=self.nx, nz=self.nz,
+            dtype=self.dtype_code, flags=flags, x0_dev=self.x[0].data_ptr(), x1_dev=self.x[1].data_ptr(),
+            logw_dev=self.logw.data_ptr(),
+            ancestors_dev=self.ancestors.data_ptr() if self.ancestors is not None else None,
+            ws_dev=self.ws.data_ptr(), ws_bytes=ws_bytes)
+        self._d = C.byref(self.desc)
+        self.reset()
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _row(self, t: int = 0):
+        return C.c_void_p(self.trace.data_ptr() + 8 * self.stride * (t % self.trace.shape[0]))
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ state
+    def reset(self, shift=None):
+        if shift is None:
+            check(self.lib.smc_sir_reset(self._d, None, self.stream))
+        else:
+            keep, p = _lib.as_doubles(shift)
+            check(self.lib.smc_sir_reset(self._d, p, self.stream))
+
+    def current_buffer(self) -> int:
+        cur = C.c_int32(0)
+        check(self.lib.smc_sir_current_buffer(self._d, C.byref(cur), self.stream))
+        return int(cur.value)
+
+    def set_particles(self, particles: np.ndarray, shift=None):
+        """Upload host particles ``(n, nx)`` into buffer 0 and reset the control block
+        (weights uniform)."""
+        torch = self.torch
+        p = np.ascontiguousarray(np.asarray(particles, dtype=np.float64).reshape(self.n, self.nx).T)
+        host = torch.from_numpy(p.astype(self.npdtype, copy=False))
+        self.x[0][:, : self.n].copy_(host, non_blocking=False)
+        self.reset(shift)
+
+    def get_particles(self) -> np.ndarray:
+        """Current particles as host float64 ``(n, nx)``."""
+        cur = self.current_buffer()
+        return self.x[cur][:, : self.n].to("cpu", dtype=self.torch.float64).numpy().T.copy()
+
+    def init_gaussian(self, mean, Lc, seed: int):
+        km, pm = _lib.as_doubles(mean)
+        kl, pl = _lib.as_doubles(Lc)
+        self.reset(mean)
+        check(self.lib.smc_sir_init_gaussian(self._d, pm, pl, C.c_uint64(seed), self.stream))
+
+    def weights(self) -> np.ndarray:
+        w = self.torch.empty((self.n,), dtype=self.torch.float64, device=self.device)
+        check(self.lib.smc_sir_export_weights(self._d, C.c_void_p(w.data_ptr()), self.stream))
+        return w.cpu().numpy()
+
+    def upload_soa(self, a: np.ndarray, rows: int):
+        """Host ``(n, rows)`` -> device SoA ``(rows, ld)`` in the engine dtype."""
+        torch = self.torch
+        t = torch.zeros((rows, self.ld), dtype=self.tdtype, device=self.device)
+        src = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(self.n, rows).T)
+        t[:, : self.n].copy_(torch.from_numpy(src.astype(self.npdtype, copy=False)))
+        return t
+
+    def set_observations(self, Z: np.ndarray):
+        """Stage a block of observations ``(T, nz)`` on the device (fp64)."""
+        torch = self.torch
+        Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64).reshape(-1, self.nz))
+        if Z.shape[0] > self.zbuf.shape[0]:
+            self.zbuf = torch.zeros(Z.shape, dtype=torch.float64, device=self.device)
+        self.zbuf[: Z.shape[0]].copy_(torch.from_numpy(Z))
+        return Z.shape[0]
+
+    def _zptr(self, t: int):
+        return C.c_void_p(self.zbuf.data_ptr() + 8 * self.nz * t)
+
+    # ------------------------------------------------------------------ kernels
+    def propagate_weight(self, model_id: int, params, mode: int, z_index: int = 0, noise=None,
+                         seed: int = 0, t: int = 0):
+        kp, pp = _lib.as_doubles(params)
+        check(self.lib.smc_sir_propagate_weight(
+            self._d, model_id, pp, kp.size, mode, self._zptr(z_index),
+            C.c_void_p(noise.data_ptr()) if noise is not None else None,
+            C.c_uint64(seed), t, self.stream))
+
+    def finalize(self, thresh: float, u: float = -1.0, seed: int = 0, t: int = 0, row: int = 0,
+                 parts=None, n_parts: int = 0):
+        check(self.lib.smc_sir_finalize(
+            self._d, float(thresh), float(u), C.c_uint64(seed), t, self._row(row),
+            C.c_void_p(parts.data_ptr()) if parts is not None else None, n_parts, self.stream))
+
+    def set_uniform(self, u: float):
+        check(self.lib.smc_sir_set_uniform(self._d, float(u), self.stream))
+
+    def resample(self, row: int = 0, cdf_offset: int = 0, peers=None, n_shards: int = 0):
+        check(self.lib.smc_sir_resample(
+            self._d, C.c_uint64(cdf_offset), self._row(row),
+            C.c_void_p(peers.data_ptr()) if peers is not None else None, n_shards, self.stream))
+
+    def finish_step(self, row: int = 0, mom_parts=None, n_mom_parts: int = 0):
+        check(self.lib.smc_sir_finish_step(
+            self._d, self._row(row),
+            C.c_void_p(mom_parts.data_ptr()) if mom_parts is not None else None, n_mom_parts, self.stream))
+
+    def step(self, model_id: int, params, thresh: float, z_index: int = 0, noise=None, u: float = -1.0,
+             seed: int = 0, t: int = 0, row: int = 0):
+        kp, pp = _lib.as_doubles(params)
+        check(self.lib.smc_sir_step(
+            self._d, model_id, pp, kp.size, self._zptr(z_index),
+            C.c_void_p(noise.data_ptr()) if noise is not None else None,
+            float(thresh), float(u), C.c_uint64(seed), t, self._row(row), self.stream))
+
+    def read_row(self, row: int = 0) -> np.ndarray:
+        return self.trace[row % self.trace.shape[0]].cpu().numpy()
+
+    def run(self, model_id: int, params, Z: np.ndarray, thresh: float, seed: int, t0: int = 0) -> np.ndarray:
+        """Enqueue ``len(Z)`` SIR steps without any host synchronisation and return
+        the statistic rows ``(T, stats_stride)`` (one D2H at the end)."""
+        torch = self.torch
+        T = self.set_observations(Z)
+        if self.trace.shape[0] < T:
+            self.trace = torch.zeros((T, self.stride), dtype=torch.float64, device=self.device)
+        for k in range(T):
+            self.step(model_id, params, thresh, z_index=k, seed=seed, t=t0 + k, row=k)
+        return self.trace[:T].cpu().numpy()
+
+    # ------------------------------------------------------------------ bridge (host callbacks)
+    def bridge_predict(self, gx: Optional[np.ndarray], noise: np.ndarray, Lq: np.ndarray, scale: float = 1.0,
+                       target_other: bool = False):
+        """``x = gx + noise @ (scale Lq)^T``; ``gx=None`` with ``target_other`` jitters the
+        resampling destination in place (particle_filter.py:212-218)."""
+        g = self.upload_soa(gx, self.nx) if gx is not None else None
+        nz = self.upload_soa(noise, self.nx)
+        kl, pl = _lib.as_doubles(Lq)
+        check(self.lib.smc_bridge_predict(self._d, C.c_void_p(g.data_ptr()) if g is not None else None,
+                                          C.c_void_p(nz.data_ptr()), pl, float(scale), int(target_other),
+                                          self.stream))
+
+    def bridge_loglik(self, zpred: np.ndarray, z: np.ndarray, LRinv: np.ndarray, wprev: Optional[np.ndarray]):
+        torch = self.torch
+        zp = self.upload_soa(zpred, self.nz)
+        kz, pz = _lib.as_doubles(z)
+        kl, pl = _lib.as_doubles(LRinv)
+        wp = None
+        if wprev is not None:
+            wp = torch.zeros((self.ld,), dtype=self.tdtype, device=self.device)
+            wp[: self.n].copy_(torch.from_numpy(np.asarray(wprev, dtype=self.npdtype)))
+        check(self.lib.smc_bridge_loglik(self._d, C.c_void_p(zp.data_ptr()), pz, pl,
+                                         C.c_void_p(wp.data_ptr()) if wp is not None else None, self.stream))
+
+
+# ---------------------------------------------------------------------- stand-alone helpers
+def systematic_ancestors(weights: np.ndarray, u: float, device=None) -> np.ndarray:
+    """GPU systematic resampling of normalised fp64 weights -> int64 ancestors
+    (reference ``ParticleFilter._systematic_resample``, particle_filter.py:146-171)."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+    n = w.shape[0]
+    ld = _round4(n)
+    wd = torch.zeros((ld,), dtype=torch.float64, device=dev)
+    wd[:n].copy_(torch.from_numpy(w))
+    anc = torch.zeros((ld,), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.smc_sir_workspace_bytes(n, 1, _lib.SMC_F64))
+    ws = torch.zeros((ws_bytes,), dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.smc_systematic_ancestors(C.c_void_p(wd.data_ptr()), n, float(u), C.c_void_p(anc.data_ptr()),
+                                       C.c_void_p(ws.data_ptr()), C.c_uint64(ws_bytes), st))
+    return anc[:n].cpu().numpy().astype(np.int64)
+
+
+def gather_rows(particles: np.ndarray, idx: np.ndarray, device=None) -> np.ndarray:
+    """``particles[idx]`` on the GPU (reference particle_filter.py:209)."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    p = np.asarray(particles, dtype=np.float64)
+    n, nx = p.shape
+    ld = _round4(n)
+    src = torch.zeros((nx, ld), dtype=torch.float64, device=dev)
+    src[:, :n].copy_(torch.from_numpy(np.ascontiguousarray(p.T)))
+    dst = torch.zeros_like(src)
+    ix = torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.smc_gather(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_void_p(ix.data_ptr()),
+                         n, ld, nx, _lib.SMC_F64, st))
+    return dst[:, :n].cpu().numpy().T.copy()

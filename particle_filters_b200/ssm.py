@@ -1,0 +1,87 @@
+"""State-space-model specs: reference-style callables that also carry a device functor.
+
+The reference's plugin API is a pair of per-particle Python callables
+``g(x, u) -> (nx,)`` and ``h(x) -> (nz,)`` (models/particle_filter.py:21-22,
+:237, :257).  A spec object offers exactly those callables (so it can be passed
+to the reference as well) plus ``device_functor(Q, R)``, which names the
+compiled functor of the fused propagate+log-likelihood kernel (K1) and packs its
+parameters.  ``ParticleFilter(g=spec.g, h=spec.h, ...)`` detects the spec through
+the bound methods and runs fully on the GPU; any other callable goes through
+the host-callback bridge.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _chol_jitter(M, eps):
+    try:
+        return np.linalg.cholesky(M)
+    except np.linalg.LinAlgError:
+        return np.linalg.cholesky(M + eps * np.eye(M.shape[0]))
+
+
+class _Spec:
+    smc_model_id = 0
+
+    def device_functor(self, Q, R):
+        raise NotImplementedError
+
+
+class StochVolSSM(_Spec):
+    """1-D stochastic volatility in the additive-Gaussian form the reference's tests
+    and notebooks filter with: ``g = alpha x``, ``h = beta exp(x / 2)``
+    (tests/integration_tests/test_pf_vs_simulator_sv.py:50-56)."""
+
+    smc_model_id = _lib.SMC_MODEL_STOCH_VOL
+    nx = nz = 1
+
+    def __init__(self, alpha: float, beta: float):
+        self.alpha, self.beta = float(alpha), float(beta)
+
+    def g(self, x, u=None):
+        return np.array([self.alpha * x[0]])
+
+    def h(self, x):
+        return np.array([self.beta * np.exp(0.5 * x[0])])
+
+    def device_functor(self, Q, R):
+        Lq = _chol_jitter(np.asarray(Q, float), 1e-10)                      # particle_filter.py:232-235
+        LR = np.linalg.cholesky(np.asarray(R, float) + 1e-12 * np.eye(1))   # :107
+        return self.smc_model_id, np.array([self.alpha, Lq[0, 0], self.beta, LR[0, 0]])
+
+
+class LinearGaussianSSM(_Spec):
+    """``g = A x``, ``h = H x`` (README LGSSM, reference README.md:104-113)."""
+
+    smc_model_id = _lib.SMC_MODEL_LINEAR_GAUSSIAN
+
+    def __init__(self, A, H):
+        self.A = np.atleast_2d(np.asarray(A, float))
+        self.H = np.atleast_2d(np.asarray(H, float))
+        self.nx, self.nz = self.A.shape[0], self.H.shape[0]
+
+    def g(self, x, u=None):
+        return self.A @ x
+
+    def h(self, x):
+        return self.H @ x
+
+    def device_functor(self, Q, R):
+        Lq = _chol_jitter(np.asarray(Q, float), 1e-10)
+        LR = np.linalg.cholesky(np.asarray(R, float) + 1e-12 * np.eye(self.nz))
+        LRinv = np.linalg.solve(LR, np.eye(self.nz))
+        return self.smc_model_id, np.concatenate(
+            [self.A.ravel(), np.tril(Lq).ravel(), self.H.ravel(), np.tril(LRinv).ravel()])
+
+
+def spec_of(g, h):
+    """Return the spec object if ``g`` and ``h`` are bound methods of one spec."""
+    sg, sh = getattr(g, "__self__", None), getattr(h, "__self__", None)
+    if isinstance(sg, _Spec) and sg is sh and getattr(g, "__func__", None) is type(sg).g \
+            and getattr(h, "__func__", None) is type(sg).h:
+        return sg
+    return None
