@@ -49,8 +49,11 @@ enum { SMC_MODE_PROPAGATE = 1, SMC_MODE_WEIGHT = 2, SMC_MODE_STEP = 3 };
 enum {
     SMC_FLAG_WRITE_ANCESTORS = 1, /* store int32 ancestor indices (additive trace output)   */
     SMC_FLAG_NO_MOMENTS = 2,      /* skip mean/cov (not used by the reference-equivalent path) */
-    SMC_FLAG_GENERIC_MOMENTS = 4  /* block partials carry no moments; mean/cov come from the
+    SMC_FLAG_GENERIC_MOMENTS = 4, /* block partials carry no moments; mean/cov come from the
                                      any-nx moment kernel (bridge mode, nx > 4)               */
+    SMC_FLAG_POST_MOMENTS_GENERIC = 8 /* post-resample moments are recomputed from memory by
+                                     smc_sir_finish_step (set when the resampled set is
+                                     jittered or gathered outside K3)                         */
 };
 
 /* One shard of a particle population (the whole population when n == n_global). */

@@ -17,6 +17,7 @@ SMC_F32, SMC_F64 = 0, 1
 SMC_MODEL_STOCH_VOL, SMC_MODEL_LINEAR_GAUSSIAN, SMC_MODEL_LORENZ96 = 1, 2, 3
 SMC_MODE_PROPAGATE, SMC_MODE_WEIGHT, SMC_MODE_STEP = 1, 2, 3
 SMC_FLAG_WRITE_ANCESTORS, SMC_FLAG_NO_MOMENTS, SMC_FLAG_GENERIC_MOMENTS = 1, 2, 4
+SMC_FLAG_POST_MOMENTS_GENERIC = 8
 SMC_STATS_HEADER = 4
 
 

@@ -155,106 +155,121 @@ __global__ void __launch_bounds__(kThreads) k1_propagate_weight(K1Args<real> a, 
     for (int d = 0; d < NX; ++d) shift[d] = (real)ctrl->shift[d];
 
     const int tid = threadIdx.x;
-    const int64_t blk_base = (int64_t)blockIdx.x * kK1Block;
-    real xs[kK1Quads][NX][4];
-    real lw[kK1Quads][4];
     const real NEG_INF = -INFINITY;
+    // thread-local online accumulators: sums are kept relative to the running thread max `tm`
+    real tm = NEG_INF;
+    real acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) acc[k] = 0;
 
+    const int64_t n_chunks = cdiv64(a.n, kK1Block);
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const int64_t blk_base = chunk * kK1Block;
+        real xs[kK1Quads][NX][4];
+        real lw[kK1Quads][4];
 #pragma unroll
-    for (int q = 0; q < kK1Quads; ++q) {
-        const int64_t i0 = blk_base + (int64_t)(q * kThreads + tid) * 4;
+        for (int q = 0; q < kK1Quads; ++q) {
+            const int64_t i0 = blk_base + (int64_t)(q * kThreads + tid) * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) lw[q][j] = NEG_INF;
-        if (i0 < a.n) {
+            for (int j = 0; j < 4; ++j) lw[q][j] = NEG_INF;
+            if (i0 < a.n) {
 #pragma unroll
-            for (int d = 0; d < NX; ++d) load4<real>(x + d * a.ld + i0, xs[q][d]);
-            if (do_prop) {
-                real nrm[NX][4];
-                if (a.noise) {
+                for (int d = 0; d < NX; ++d) load4<real>(x + d * a.ld + i0, xs[q][d]);
+                if (do_prop) {
+                    real nrm[NX][4];
+                    if (a.noise) {
 #pragma unroll
-                    for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
-                } else {
-                    Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
+                        for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
+                    } else {
+                        Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        real xv[NX], nv[NX];
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) { xv[d] = xs[q][d][j]; nv[d] = nrm[d][j]; }
+                        m.propagate(xv, nv);
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xs[q][d][j] = xv[d];
+                    }
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) store4<real>(x + d * a.ld + i0, xs[q][d]);
                 }
+                if (do_w) {
+                    real prev[4];
+                    if (uniform) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    real xv[NX], nv[NX];
+                        for (int j = 0; j < 4; ++j) prev[j] = lw_uniform;
+                    } else {
+                        load4<real>(a.logw + i0, prev);
 #pragma unroll
-                    for (int d = 0; d < NX; ++d) { xv[d] = xs[q][d][j]; nv[d] = nrm[d][j]; }
-                    m.propagate(xv, nv);
+                        for (int j = 0; j < 4; ++j) prev[j] = prev_logweight(prev[j], log_norm_prev);
+                    }
+                    real out[4];
 #pragma unroll
-                    for (int d = 0; d < NX; ++d) xs[q][d][j] = xv[d];
+                    for (int j = 0; j < 4; ++j) {
+                        real xv[NX];
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xv[d] = xs[q][d][j];
+                        real v = prev[j] + m.loglik(xv, z);
+                        const bool valid = (i0 + j) < a.n;
+                        out[j] = valid ? v : NEG_INF;
+                        lw[q][j] = (valid && v == v) ? v : NEG_INF;   // NaN counts as zero weight
+                    }
+                    store4<real>(a.logw + i0, out);
                 }
-#pragma unroll
-                for (int d = 0; d < NX; ++d) store4<real>(x + d * a.ld + i0, xs[q][d]);
-            }
-            if (do_w) {
-                real prev[4];
-                if (uniform) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) prev[j] = lw_uniform;
-                } else {
-                    load4<real>(a.logw + i0, prev);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) prev[j] = prev_logweight(prev[j], log_norm_prev);
-                }
-                real out[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    real xv[NX];
-#pragma unroll
-                    for (int d = 0; d < NX; ++d) xv[d] = xs[q][d][j];
-                    real v = prev[j] + m.loglik(xv, z);
-                    const bool valid = (i0 + j) < a.n;
-                    out[j] = valid ? v : NEG_INF;
-                    lw[q][j] = (valid && v == v) ? v : NEG_INF;   // NaN counts as zero weight
-                }
-                store4<real>(a.logw + i0, out);
             }
         }
+        if (!do_w) continue;
+        // ---- fold this chunk into the thread's running (max, sums) ------------------------------
+        real cmax = NEG_INF;
+#pragma unroll
+        for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cmax = lw[q][j] > cmax ? lw[q][j] : cmax;
+        if (cmax > tm) {
+            const real sc = fast_exp(tm - cmax);          // tm = -inf -> 0
+            acc[0] *= sc;
+            acc[1] *= sc * sc;
+#pragma unroll
+            for (int k = 2; k < NR; ++k) acc[k] *= sc;
+            tm = cmax;
+        }
+        if (tm == NEG_INF) continue;                       // nothing but zero weights so far
+#pragma unroll
+        for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const real e = fast_exp(lw[q][j] - tm);    // exp(-inf) = 0 for padding / zero weights
+                acc[0] += e;
+                acc[1] = fma(e, e, acc[1]);
+                real xc[NX];
+#pragma unroll
+                for (int d = 0; d < NX; ++d) xc[d] = (lw[q][j] == NEG_INF) ? real(0) : xs[q][d][j] - shift[d];
+                int k = 2;
+#pragma unroll
+                for (int d = 0; d < NX; ++d) { acc[k] = fma(e, xc[d], acc[k]); ++k; }
+#pragma unroll
+                for (int d = 0; d < NX; ++d)
+#pragma unroll
+                    for (int d2 = 0; d2 <= d; ++d2) { acc[k] = fma(e * xc[d], xc[d2], acc[k]); ++k; }
+            }
     }
     if (!do_w) return;
 
-    // ---- block max -------------------------------------------------------------------------
-    real tmax = NEG_INF;
-#pragma unroll
-    for (int q = 0; q < kK1Quads; ++q)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tmax = lw[q][j] > tmax ? lw[q][j] : tmax;
-    tmax = warp_max(tmax);
+    // ---- block combine: common max, rescale, fixed-tree sums -----------------------------------
     const int warp = tid >> 5, lane = tid & 31;
-    if (lane == 0) s_max[warp] = tmax;
+    real wmax = warp_max(tm);
+    if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     real bmax = s_max[0];
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) bmax = s_max[w] > bmax ? s_max[w] : bmax;
-    const real mref = (bmax == NEG_INF) ? real(0) : bmax;
-
-    // ---- sums relative to the block max ----------------------------------------------------
-    real acc[NR];
-#pragma unroll
-    for (int k = 0; k < NR; ++k) acc[k] = 0;
-#pragma unroll
-    for (int q = 0; q < kK1Quads; ++q)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            real e = fast_exp(lw[q][j] - mref);   // exp(-inf) = 0 for padding / zero weights
-            acc[0] += e;
-            acc[1] = fma(e, e, acc[1]);
-            real xc[NX];
-#pragma unroll
-            for (int d = 0; d < NX; ++d) xc[d] = (lw[q][j] == NEG_INF) ? real(0) : xs[q][d][j] - shift[d];
-            int k = 2;
-#pragma unroll
-            for (int d = 0; d < NX; ++d) { acc[k] = fma(e, xc[d], acc[k]); ++k; }
-#pragma unroll
-            for (int d = 0; d < NX; ++d)
-#pragma unroll
-                for (int d2 = 0; d2 <= d; ++d2) { acc[k] = fma(e * xc[d], xc[d2], acc[k]); ++k; }
-        }
+    const real sc = (tm == NEG_INF) ? real(0) : fast_exp(tm - bmax);
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        real v = warp_sum(acc[k]);
+        real v = acc[k] * (k == 1 ? sc * sc : sc);
+        v = warp_sum(v);
         if (lane == 0) s_red[warp][k] = (double)v;
     }
     __syncthreads();
@@ -394,16 +409,16 @@ __global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
 // K3: single-pass systematic resampler
 // ==============================================================================================
 // Exact predicate "pos_i < c" with pos_i = fl(fl(u + i) / N) (particle_filter.py:160) and the
-// CDF value c = C / (N 2^32) given in fixed point.  Integer arithmetic only after the fp64 position.
-__device__ inline bool pos_less(int64_t i, unsigned long long C, double u, int64_t N) {
+// CDF value c = C / (N 2^F) given in fixed point.  Integer arithmetic only after the fp64 position.
+__device__ inline bool pos_less(int64_t i, unsigned long long C, double u, int64_t N, int F) {
     const double p = (u + (double)i) / (double)N;       // IEEE fp64, same two roundings as NumPy
     if (!(p > 0.0)) return C > 0ull;                     // p == 0  (u = 0, i = 0)
     int ex;
     const double fr = frexp(p, &ex);                     // p = fr * 2^ex, fr in [0.5, 1)
     const unsigned long long mant = (unsigned long long)ldexp(fr, 53);   // 53-bit integer
     const int e2 = ex - 53;                              // p = mant * 2^e2
-    // p * N * 2^32 < C  <=>  floor(mant * N / 2^s) < C  with s = -(e2 + 32) > 0
-    const int s = -(e2 + kFracBits);
+    // p * N * 2^F < C  <=>  floor(mant * N / 2^s) < C  with s = -(e2 + F)
+    const int s = -(e2 + F);
     unsigned __int128 prod = (unsigned __int128)mant * (unsigned __int128)(unsigned long long)N;
     if (s >= 128) return C > 0ull;
     if (s > 0) prod >>= s; else prod <<= (-s);
@@ -412,21 +427,44 @@ __device__ inline bool pos_less(int64_t i, unsigned long long C, double u, int64
 
 struct SearchParams {
     double u;
-    uint32_t uq;        // floor(u * 2^32)
-    uint32_t margin;    // |frac - uq| <= margin -> exact path
+    unsigned long long uq;        // floor(u * 2^F)
+    unsigned long long margin;    // |frac - uq| <= margin -> exact path
+    unsigned long long fmask;     // 2^F - 1
     int64_t n_global;
+    int F;
 };
+
+// Fractional bits of the fixed-point CDF ("index units" N*w): as many as fit below the status bit.
+__host__ __device__ inline int frac_bits_for(int64_t n_global) {
+    int lg = 0;
+    while ((1ll << lg) < n_global) ++lg;
+    int F = 62 - lg;
+    return F < 32 ? 32 : (F > 60 ? 60 : F);
+}
+
+__device__ inline SearchParams make_search(double u, int64_t n_global) {
+    SearchParams sp;
+    sp.F = frac_bits_for(n_global);
+    sp.u = u;
+    sp.uq = __double2ull_rd(ldexp(u, sp.F));
+    sp.fmask = (1ull << sp.F) - 1ull;
+    // fp64 round-off of (u + i) / N is <= N 2^-52 index units = N 2^(F-52) fraction units
+    const int sh = sp.F - 50;
+    sp.margin = 8ull + (sh >= 0 ? ((unsigned long long)n_global << sh) : ((unsigned long long)n_global >> (-sh)));
+    sp.n_global = n_global;
+    return sp;
+}
 
 // e(C) = #{ i in [0, N) : pos_i < C }  (first output index NOT owned by CDF value C)
 __device__ inline int64_t outputs_below(unsigned long long C, const SearchParams& sp) {
-    const int64_t I = (int64_t)(C >> kFracBits);
-    const uint32_t f = (uint32_t)C;
+    const int64_t I = (int64_t)(C >> sp.F);
+    const unsigned long long f = C & sp.fmask;
     int64_t e = I + (f > sp.uq ? 1 : 0);
-    const uint32_t diff = f > sp.uq ? f - sp.uq : sp.uq - f;
+    const unsigned long long diff = f > sp.uq ? f - sp.uq : sp.uq - f;
     if (e > sp.n_global) e = sp.n_global;
-    if (diff <= sp.margin || diff >= 0xffffffffu - sp.margin) {
-        while (e > 0 && !pos_less(e - 1, C, sp.u, sp.n_global)) --e;
-        while (e < sp.n_global && pos_less(e, C, sp.u, sp.n_global)) ++e;
+    if (diff <= sp.margin || diff >= sp.fmask - sp.margin) {
+        while (e > 0 && !pos_less(e - 1, C, sp.u, sp.n_global, sp.F)) --e;
+        while (e < sp.n_global && pos_less(e, C, sp.u, sp.n_global, sp.F)) ++e;
     }
     return e;
 }
@@ -463,8 +501,6 @@ template <> struct K3Geom<double> {
 __device__ inline void unit_to_array(const float4& u, float* v) { v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; }
 __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; v[1] = u.y; }
 
-__device__ inline unsigned long long to_fixed(float v) { return __float2ull_rn(v * 4294967296.0f); }
-__device__ inline unsigned long long to_fixed(double v) { return __double2ull_rn(v * 4294967296.0); }
 
 // decoupled look-back over tile aggregates / inclusive prefixes (integer -> order independent)
 __device__ inline unsigned long long lookback(volatile unsigned long long* agg,
@@ -492,6 +528,56 @@ __device__ inline unsigned long long lookback(volatile unsigned long long* agg,
     return sum;
 }
 
+// Per-item quantisation of the weights.
+//  fp32 mode: each weight carries 24 significant bits, so it is converted on its own (one F2I);
+//  fp64 mode (parity): the thread's fp64 running sum is quantised instead, so the round-off of
+//  2^-F index units does not accumulate over a run of tiny weights.
+template <typename real> struct Quant;
+template <> struct Quant<float> {
+    float fscale;
+    __device__ inline void init(int F) { fscale = __uint_as_float((127u + (uint32_t)F) << 23); }   // 2^F
+    __device__ inline unsigned long long add(unsigned long long run, float v, double&) const {
+        return run + __float2ull_rn(v * fscale);
+    }
+};
+template <> struct Quant<double> {
+    double fscale, nmax;
+    __device__ inline void init(int F) { fscale = ldexp(1.0, F); }
+    __device__ inline unsigned long long add(unsigned long long, double v, double& runf) const {
+        runf += v;
+        return __double2ull_rn(runf * fscale);
+    }
+};
+
+// Fast boundary search in 32-bit arithmetic.  With C' = C + (2^F - 1 - uq):
+//   e(C) = C' >> F           (number of stratified positions below the CDF value C)
+// and the position is within fp64 round-off of the CDF value iff the top 32 fraction bits of C'
+// lie within m32 of 0 (mod 2^32); only then is the exact predicate evaluated.
+struct FastSearch {
+    unsigned long long bias;   // 2^F - 1 - uq
+    uint32_t sh;               // F - 32
+    uint32_t m32;              // margin in units of 2^(F-32), rounded up, + 1
+    uint32_t n_global;
+};
+// rare path, kept out of line so that it costs the hot loop neither registers nor I-cache
+__device__ __noinline__ uint32_t exact_outputs_below(unsigned long long C, uint32_t e0, double u, int64_t n_global,
+                                                     int F) {
+    long long ee = e0;
+    while (ee > 0 && !pos_less(ee - 1, C, u, n_global, F)) --ee;
+    while (ee < n_global && pos_less(ee, C, u, n_global, F)) ++ee;
+    return (uint32_t)ee;
+}
+__device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bias */, const FastSearch& fs,
+                                              const SearchParams& sp) {
+    const uint32_t hi = (uint32_t)(Cb >> 32), lo = (uint32_t)Cb;
+    uint32_t e = hi >> fs.sh;
+    const uint32_t frac_hi = __funnelshift_r(lo, hi, fs.sh);    // bits [F-32, F) of Cb
+    e = e < fs.n_global ? e : fs.n_global;
+    if (frac_hi + fs.m32 <= 2u * fs.m32)                         // near 0 or near 2^32 (wraps)
+        e = exact_outputs_below(Cb - fs.bias, e, sp.u, sp.n_global, sp.F);
+    return e;
+}
+
 template <typename real, int NXF, bool LINEAR_W>
 __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
     using G = K3Geom<real>;
@@ -511,7 +597,7 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
     real* x_s = reinterpret_cast<real*>(smem_raw + sizeof(real) * TILE);  // NXF * TILE reals
     __shared__ unsigned long long s_warp_tot[kWarps];
     __shared__ unsigned long long s_prefix;
-    __shared__ long long s_E[2];
+    __shared__ uint32_t s_E[2];
     __shared__ unsigned int s_tile;
     __shared__ int s_wmax[kWarps];
     __shared__ double s_mom[kWarps][NM > 0 ? NM : 1];
@@ -529,11 +615,14 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
     const int64_t tile = s_tile;
     const int64_t tile_base = tile * TILE;
 
-    SearchParams sp;
-    sp.u = ctrl->u;
-    sp.uq = (uint32_t)__double2ull_rd(sp.u * 4294967296.0);
-    sp.margin = 4u + (uint32_t)(a.n_global >> 19);
-    sp.n_global = a.n_global;
+    const SearchParams sp = make_search(ctrl->u, a.n_global);
+    FastSearch fs;
+    fs.bias = sp.fmask - sp.uq;
+    fs.sh = (uint32_t)(sp.F - 32);
+    fs.m32 = (uint32_t)(sp.margin >> fs.sh) + 2u;
+    fs.n_global = (uint32_t)a.n_global;
+    Quant<real> quant;
+    quant.init(sp.F);
     // weight = exp(lw - log_norm) * N  =  exp(lw - (log_norm - log N))
     const real lw_ref = LINEAR_W ? real(0) : (real)(ctrl->log_norm - log((double)a.n_global));
     const real n_real = (real)a.n_global;
@@ -569,8 +658,9 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
 
     // ---- phase B: fixed-point weights, block scan, look-back ---------------------------------
     unsigned long long c[IPT];
+    unsigned long long run = 0;
     {
-        unsigned long long run = 0;
+        double runf = 0.0;
 #pragma unroll
         for (int k = 0; k < UPT; ++k) {
             const int g = UPT * tid + k;
@@ -581,140 +671,170 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
                 real v = LINEAR_W ? tmp[j] * n_real : fast_exp(tmp[j] - lw_ref);
                 v = (v > real(0)) ? v : real(0);             // NaN / negative -> 0
                 v = v < n_real ? v : n_real;
-                run += to_fixed(v);
+                run = quant.add(run, v, runf);
                 c[k * EPU + j] = run;                        // inclusive within thread
             }
         }
-        unsigned long long incl_w = run;                     // warp inclusive scan of thread totals
+    }
+    unsigned long long incl_w = run;                         // warp inclusive scan of thread totals
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
-            if (lane >= o) incl_w += t;
-        }
-        if (lane == 31) s_warp_tot[warp] = incl_w;
-        __syncthreads();   // also: everyone is done reading lw_s
-        unsigned long long warp_excl = 0, tile_agg = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
+        if (lane >= o) incl_w += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl_w;
+    __syncthreads();   // also: everyone is done reading lw_s
+    unsigned long long warp_excl = 0, tile_agg = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            unsigned long long t = s_warp_tot[w];
-            if (w < warp) warp_excl += t;
-            tile_agg += t;
+    for (int w = 0; w < kWarps; ++w) {
+        unsigned long long t = s_warp_tot[w];
+        if (w < warp) warp_excl += t;
+        tile_agg += t;
+    }
+    if (warp == 0) {
+        volatile unsigned long long* vagg = a.agg;
+        volatile unsigned long long* vincl = a.incl;
+        if (tile == 0) {
+            if (lane == 0) {
+                vincl[0] = kValidBit | (a.cdf_offset + tile_agg);
+                s_prefix = a.cdf_offset;
+            }
+        } else {
+            if (lane == 0) vagg[tile] = kValidBit | tile_agg;
+            unsigned long long pre = lookback(vagg, vincl, tile, lane);
+            if (lane == 0) {
+                vincl[tile] = kValidBit | (pre + tile_agg);
+                s_prefix = pre;
+            }
         }
-        if (warp == 0) {
-            volatile unsigned long long* vagg = a.agg;
-            volatile unsigned long long* vincl = a.incl;
-            if (tile == 0) {
-                if (lane == 0) {
-                    vincl[0] = kValidBit | (a.cdf_offset + tile_agg);
-                    s_prefix = a.cdf_offset;
+    }
+    __syncthreads();
+
+    // ---- phase C: output boundaries (32-bit) -------------------------------------------------
+    // e[k] = number of outputs whose stratified position lies below the CDF value after item k
+    const unsigned long long base_b = s_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
+    const uint32_t e_start = fast_outputs_below(base_b, fs, sp);
+    uint32_t e[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) e[k] = fast_outputs_below(base_b + c[k], fs, sp);
+    {   // cumsum[-1] = 1.0 clamp (particle_filter.py:163): the globally last particle owns the tail
+        const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;
+        if (j0 + IPT >= a.n_global) {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) if (j0 + k >= a.n_global - 1) e[k] = fs.n_global;
+        }
+    }
+    // (padding items beyond the shard carry zero weight, hence no outputs of their own)
+    if (tid == 0) s_E[0] = e_start;
+    if (tid == kThreads - 1) s_E[1] = e[IPT - 1];
+    __syncthreads();
+    const uint32_t E0 = s_E[0], E1 = s_E[1];
+    const uint32_t count = E1 - E0;
+
+    real macc[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int k = 0; k < (NM > 0 ? NM : 1); ++k) macc[k] = 0;
+    real shift[NXF > 0 ? NXF : 1];
+#pragma unroll
+    for (int d = 0; d < NXF; ++d) shift[d] = (real)ctrl->shift[d];
+
+    for (uint32_t wbase = 0; wbase < count; wbase += W) {
+        // 1. clear the window
+        {
+            uint4* o4 = reinterpret_cast<uint4*>(out_s);
+            for (int p = tid; p < W * 2 / 16; p += kThreads) o4[p] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        // 2. head markers (local index + 1) at the first output of every item with offspring
+        if (count <= (uint32_t)W) {            // common case: the whole tile fits one window
+            uint32_t r0 = e_start - E0;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const uint32_t r1 = e[k] - E0;
+                if (r1 > r0) out_s[r0] = (unsigned short)(tid * IPT + k + 1);
+                r0 = r1;
+            }
+        } else {
+            uint32_t r0 = e_start - E0;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const uint32_t r1 = e[k] - E0;
+                if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
+                    const uint32_t pos = (r0 > wbase ? r0 : wbase) - wbase;
+                    out_s[pos] = (unsigned short)(tid * IPT + k + 1);
+                }
+                r0 = r1;
+            }
+        }
+        __syncthreads();
+        // 3. forward fill = inclusive max-scan (markers increase with position)
+        {
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out_s) + tid * (CH / 2);
+            uint32_t wv[CH / 2];
+            int tmax = 0;
+#pragma unroll
+            for (int k = 0; k < CH / 2; ++k) {
+                wv[k] = o32[k];
+                int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                tmax = max(tmax, max(lo, hi));
+            }
+            int inc = tmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = max(inc, t);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) excl = 0;
+            if (lane == 31) s_wmax[warp] = inc;
+            __syncthreads();
+            int carry = excl;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
+#pragma unroll
+            for (int k = 0; k < CH / 2; ++k) {
+                int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                lo = max(lo, carry); carry = lo;
+                hi = max(hi, carry); carry = hi;
+                o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+            }
+        }
+        __syncthreads();
+        // 4. coalesced copy-out with the shared-memory-staged gather
+        {
+            const uint32_t rem = count - wbase;
+            const int cnt = rem < (uint32_t)W ? (int)rem : W;
+            const int64_t g0 = (int64_t)E0 + wbase;                  // global index of window slot 0
+            if (!peer) {
+                real* dwin = xdst + (g0 - a.offset);                 // local destination of slot 0
+                int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) : nullptr;
+                const int32_t abase = (int32_t)(a.offset + tile_base);
+                for (int p = tid; p < cnt; p += kThreads) {
+                    const int li = (int)out_s[p] - 1;                // local ancestor
+                    if (awin) awin[p] = abase + li;
+                    if (NXF > 0) {
+                        real xv[NXF > 0 ? NXF : 1];
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d) {
+                            xv[d] = x_s[d * TILE + li];
+                            dwin[d * a.ld + p] = xv[d];
+                        }
+                        int k = 0;
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
+#pragma unroll
+                        for (int d = 0; d < NXF; ++d)
+#pragma unroll
+                            for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
+                    }
                 }
             } else {
-                if (lane == 0) vagg[tile] = kValidBit | tile_agg;
-                unsigned long long pre = lookback(vagg, vincl, tile, lane);
-                if (lane == 0) {
-                    vincl[tile] = kValidBit | (pre + tile_agg);
-                    s_prefix = pre;
-                }
-            }
-        }
-        __syncthreads();
-        const unsigned long long base = s_prefix + warp_excl + (incl_w - run);   // exclusive of thread
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) c[k] += base;
-        // ---- phase C: output boundaries ------------------------------------------------------
-        // e[k] = number of outputs whose position lies below the CDF value after item k
-        long long e_prev = outputs_below(base, sp);
-        long long e[IPT];
-        const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;     // global index of item 0
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            long long v = outputs_below(c[k], sp);
-            if (j0 + k >= a.n_global - 1) v = a.n_global;    // cumsum[-1] = 1.0 clamp, :163
-            e[k] = v;
-        }
-        // (padding items beyond the shard carry zero weight, hence no outputs of their own)
-        if (tid == 0) s_E[0] = e_prev;
-        if (tid == kThreads - 1) s_E[1] = e[IPT - 1];
-        __syncthreads();
-        const long long E0 = s_E[0], E1 = s_E[1];
-        const long long count = E1 - E0;
-
-        real macc[NM > 0 ? NM : 1];
-#pragma unroll
-        for (int k = 0; k < (NM > 0 ? NM : 1); ++k) macc[k] = 0;
-        real shift[NXF > 0 ? NXF : 1];
-#pragma unroll
-        for (int d = 0; d < NXF; ++d) shift[d] = (real)ctrl->shift[d];
-
-        for (long long wbase = 0; wbase < count; wbase += W) {
-            // 1. clear the window
-            {
-                uint4* o4 = reinterpret_cast<uint4*>(out_s);
-                for (int p = tid; p < W * 2 / 16; p += kThreads) o4[p] = make_uint4(0, 0, 0, 0);
-            }
-            __syncthreads();
-            // 2. head markers (local index + 1) at the first output of every item with offspring
-            {
-                long long ep = e_prev;
-#pragma unroll
-                for (int k = 0; k < IPT; ++k) {
-                    const long long r0 = ep - E0, r1 = e[k] - E0;
-                    if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
-                        const long long pos = (r0 > wbase ? r0 : wbase) - wbase;
-                        out_s[pos] = (unsigned short)(tid * IPT + k + 1);
-                    }
-                    ep = e[k];
-                }
-            }
-            __syncthreads();
-            // 3. forward fill = inclusive max-scan (markers increase with position)
-            {
-                uint32_t* o32 = reinterpret_cast<uint32_t*>(out_s) + tid * (CH / 2);
-                uint32_t wv[CH / 2];
-                int tmax = 0;
-#pragma unroll
-                for (int k = 0; k < CH / 2; ++k) {
-                    wv[k] = o32[k];
-                    int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
-                    tmax = max(tmax, max(lo, hi));
-                }
-                int inc = tmax;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc = max(inc, t);
-                }
-                int excl = __shfl_up_sync(0xffffffffu, inc, 1);
-                if (lane == 0) excl = 0;
-                if (lane == 31) s_wmax[warp] = inc;
-                __syncthreads();
-                int carry = excl;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
-#pragma unroll
-                for (int k = 0; k < CH / 2; ++k) {
-                    int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
-                    lo = max(lo, carry); carry = lo;
-                    hi = max(hi, carry); carry = hi;
-                    o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
-                }
-            }
-            __syncthreads();
-            // 4. coalesced copy-out with the shared-memory-staged gather
-            {
-                const long long rem = count - wbase;
-                const int cnt = rem < W ? (int)rem : W;
-                for (int p = tid; p < cnt; p += kThreads) {
-                    const int li = (int)out_s[p] - 1;                    // local ancestor
-                    const int64_t gi = E0 + wbase + p;                   // global output index
-                    int64_t di = gi - a.offset;                          // local destination index
-                    real* dbase = xdst;
-                    if (peer) {
-                        const int64_t r = gi / a.shard_n;
-                        dbase = peer[r];
-                        di = gi - r * a.shard_n;
-                    }
-                    if (a.ancestors && !peer) a.ancestors[di] = (int32_t)(a.offset + tile_base + li);
+                for (int p = tid; p < cnt; p += kThreads) {          // cross-shard migration path
+                    const int li = (int)out_s[p] - 1;
+                    const int64_t gi = g0 + p;
+                    const int64_t r = gi / a.shard_n;
+                    real* dbase = peer[r];
+                    const int64_t di = gi - r * a.shard_n;
                     if (NXF > 0) {
                         real xv[NXF > 0 ? NXF : 1];
 #pragma unroll
@@ -732,22 +852,22 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
                     }
                 }
             }
-            __syncthreads();
         }
-        // ---- per-tile post-resample moment partials -------------------------------------------
-        if (NM > 0 && a.mom_parts) {
+        __syncthreads();
+    }
+    // ---- per-tile post-resample moment partials -------------------------------------------
+    if (NM > 0 && a.mom_parts) {
 #pragma unroll
-            for (int k = 0; k < NM; ++k) {
-                double v = warp_sum((double)macc[k]);
-                if (lane == 0) s_mom[warp][k] = v;
-            }
-            __syncthreads();
-            if (tid < NM) {
-                double s = 0;
+        for (int k = 0; k < NM; ++k) {
+            double v = warp_sum((double)macc[k]);
+            if (lane == 0) s_mom[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < NM) {
+            double s = 0;
 #pragma unroll
-                for (int w = 0; w < kWarps; ++w) s += s_mom[w][tid];
-                a.mom_parts[tile * NM + tid] = s;
-            }
+            for (int w = 0; w < kWarps; ++w) s += s_mom[w][tid];
+            a.mom_parts[tile * NM + tid] = s;
         }
     }
 }
@@ -756,14 +876,27 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_shard_total(const Ctrl* ctrl, const real* logw, int64_t n,
                                                           int64_t n_global, unsigned long long* total) {
+    // same quantisation as k3_resample: one thread owns IPT consecutive items and quantises
+    // its running sum, so the shard total equals the last inclusive prefix K3 will compute
+    constexpr int IPT = K3Geom<real>::IPT;
     const real lw_ref = (real)(ctrl->log_norm - log((double)n_global));
     const real n_real = (real)n_global;
+    Quant<real> quant;
+    quant.init(frac_bits_for(n_global));
     unsigned long long acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-        real v = fast_exp(logw[i] - lw_ref);
-        v = (v > real(0)) ? v : real(0);
-        v = v < n_real ? v : n_real;
-        acc += to_fixed(v);
+    const int64_t n_groups = cdiv64(n, IPT);
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kThreads) {
+        double runf = 0.0;
+        unsigned long long run = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int64_t i = g * IPT + k;
+            real v = i < n ? fast_exp(logw[i] - lw_ref) : real(0);
+            v = (v > real(0)) ? v : real(0);
+            v = v < n_real ? v : n_real;
+            run = quant.add(run, v, runf);
+        }
+        acc += run;
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
@@ -928,49 +1061,41 @@ __global__ void __launch_bounds__(kThreads) k_bridge_predict(Ctrl* ctrl, real* x
     }
 }
 
-// log-likelihood from host-evaluated h(x): one thread per particle, block partials as in K1
+// log-likelihood from host-evaluated h(x): grid-stride over particles, online (max, sum, sum^2)
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_bridge_loglik(Ctrl* ctrl, real* logw, const real* zpred, const double* z,
                                                             const double* LRinv, const real* wprev, int64_t n,
                                                             int64_t n_global, int64_t ld, int nz, double* parts) {
     __shared__ double s_tmp[kWarps];
-    const int tid = threadIdx.x;
-    double lw[kK1Block / kThreads];
-    double m = -INFINITY;
     const double lw_uniform = log(1.0 / (double)n_global + 1e-300);
-#pragma unroll 1
-    for (int q = 0; q < kK1Block / kThreads; ++q) {
-        const int64_t i = (int64_t)blockIdx.x * kK1Block + q * kThreads + tid;
-        double v = -INFINITY;
-        if (i < n) {
-            double quad = 0;
-            for (int r = 0; r < nz; ++r) {        // y = LR^-1 (z - zpred), particle_filter.py:258-260
-                double acc = 0;
-                for (int k = 0; k <= r; ++k) acc = fma(LRinv[r * nz + k], z[k] - (double)zpred[k * ld + i], acc);
-                quad = fma(acc, acc, quad);
-            }
-            const double prev = wprev ? log((double)wprev[i] + 1e-300) : lw_uniform;   // :261
-            v = prev - 0.5 * quad;
-            logw[i] = (real)v;
-            if (!(v == v)) v = -INFINITY;
+    double m = -INFINITY, s = 0, s2 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        double quad = 0;
+        for (int r = 0; r < nz; ++r) {        // y = LR^-1 (z - zpred), particle_filter.py:258-260
+            double acc = 0;
+            for (int k = 0; k <= r; ++k) acc = fma(LRinv[r * nz + k], z[k] - (double)zpred[k * ld + i], acc);
+            quad = fma(acc, acc, quad);
         }
-        lw[q] = v;
-        m = v > m ? v : m;
+        const double prev = wprev ? log((double)wprev[i] + 1e-300) : lw_uniform;   // :261
+        double v = prev - 0.5 * quad;
+        logw[i] = (real)v;
+        if (!(v == v)) continue;              // NaN counts as zero weight
+        if (v > m) {
+            const double sc = exp(m - v);     // m = -inf -> 0
+            s *= sc; s2 *= sc * sc; m = v;
+        }
+        if (m != -INFINITY) {
+            const double e = exp(v - m);
+            s += e; s2 = fma(e, e, s2);
+        }
     }
     const double bmax = block_max_256(m, s_tmp);
-    const double mref = bmax == -INFINITY ? 0.0 : bmax;
-    double s = 0, s2 = 0;
-#pragma unroll 1
-    for (int q = 0; q < kK1Block / kThreads; ++q) {
-        double e = exp(lw[q] - mref);
-        s += e;
-        s2 = fma(e, e, s2);
-    }
-    s = block_sum_256(s, s_tmp);
-    s2 = block_sum_256(s2, s_tmp);
-    if (tid == 0) {
+    const double sc = (m == -INFINITY) ? 0.0 : exp(m - bmax);
+    const double bs = block_sum_256(s * sc, s_tmp);
+    const double bs2 = block_sum_256(s2 * sc * sc, s_tmp);
+    if (threadIdx.x == 0) {
         double* out = parts + (int64_t)blockIdx.x * 3;
-        out[0] = bmax; out[1] = s; out[2] = s2;
+        out[0] = bmax; out[1] = bs; out[2] = bs2;
     }
     (void)ctrl;
 }
@@ -1360,7 +1485,9 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     const int no_m = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0;
-    const bool inl = inline_moments(d);
+    // POST_MOMENTS_GENERIC: the particle set was modified after K3 (regularisation jitter) or was
+    // not produced by K3 at all (multinomial gather), so its moments are recomputed from memory
+    const bool inl = inline_moments(d) && !(d->flags & SMC_FLAG_POST_MOMENTS_GENERIC);
     if (!inl && !no_m && stats_row_dev) {
         // any-nx moments straight into the stats row (weighted or uniform, decided on device)
         SMC_REQUIRE(d->n == d->n_global, "smc: generic moments are single-shard only");

@@ -38,12 +38,13 @@ void set_error(const char* fmt, ...);
 constexpr int kThreads = 256;          // CTA size of every streaming kernel
 constexpr int kWarps = kThreads / 32;
 constexpr int kK1Quads = 4;            // quads (4 particles) per thread per K1 block
-constexpr int kK1Block = kThreads * 4 * kK1Quads;   // particles per K1 block (4096)
+constexpr int kK1Block = kThreads * 4 * kK1Quads;   // particles per K1 chunk (4096)
+constexpr int kK1MaxBlocks = 148 * 4;  // persistent K1 grid: CTAs loop over chunks (B200: 148 SMs)
 constexpr int kMaxNx = 64;             // control block moment shift capacity
 constexpr int kFusedNxMax = 4;         // K3 moves the payload itself up to this many dims
 
-// Fixed-point CDF: "index units" (N * w) with 32 fractional bits.
-constexpr int kFracBits = 32;
+// Fixed-point CDF: "index units" (N * w) with F = 62 - ceil(log2 N) fractional bits (>= 32);
+// bit 63 of a published tile word is its "valid" flag.
 constexpr unsigned long long kValidBit = 1ull << 63;
 
 // ----------------------------------------------------------------------------------------------
@@ -89,6 +90,7 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     WsLayout L;
     L.n_k1_blocks = cdiv64(n, kK1Block);
     if (L.n_k1_blocks < 1) L.n_k1_blocks = 1;
+    if (L.n_k1_blocks > kK1MaxBlocks) L.n_k1_blocks = kK1MaxBlocks;
     L.n_tiles = cdiv64(n, k3_tile_items(dtype));
     if (L.n_tiles < 1) L.n_tiles = 1;
     size_t off = 0;

@@ -38,7 +38,7 @@ class SirEngine:
 
     def __init__(self, n: int, nx: int, nz: int, *, dtype: str = "f32", device=None,
                  n_global: Optional[int] = None, offset: int = 0, write_ancestors: bool = False,
-                 generic_moments: bool = False, trace_len: int = 1):
+                 generic_moments: bool = False, post_moments_generic: bool = False, trace_len: int = 1):
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
@@ -67,6 +67,8 @@ class SirEngine:
             flags |= _lib.SMC_FLAG_WRITE_ANCESTORS
         if self.generic_moments:
             flags |= _lib.SMC_FLAG_GENERIC_MOMENTS
+        if post_moments_generic:
+            flags |= _lib.SMC_FLAG_POST_MOMENTS_GENERIC
         self.desc = SirDesc(
             n=self.n, n_global=self.n_global, offset=self.offset, ld=self.ld, nx=self.nx, nz=self.nz,
             dtype=self.dtype_code, flags=flags, x0_dev=self.x[0].data_ptr(), x1_dev=self.x[1].data_ptr(),

@@ -156,8 +156,9 @@ class ParticleFilter:
         from .engine import SirEngine
 
         if self._eng is None:
+            post_generic = self.resample_method != "systematic" or bool(self.regularize_after_resample)
             self._eng = SirEngine(self.Np, self.nx, self.nz, dtype=self._dtype, device=self._device,
-                                  write_ancestors=self._record_ancestors)
+                                  write_ancestors=self._record_ancestors, post_moments_generic=post_generic)
             self._functor = self._spec.device_functor(self.Q, self.R)
         return self._eng
 

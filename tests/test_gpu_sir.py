@@ -139,9 +139,18 @@ def test_fp32_single_step_from_identical_state():
     np.testing.assert_allclose(pf2.last_ess, o.info["ess_pre"], rtol=1e-5)
     np.testing.assert_allclose(pf2.last_log_norm, o.info["log_norm"], rtol=0, atol=2e-6)
 
+    # deterministic part: the weighted (pre-resample) mean / variance from identical inputs
+    x_pre = 0.95 * x0.astype(np.float32).astype(np.float64) + 0.2 * noise
+    mean_ref = np.average(x_pre[:, 0], weights=w_ref)
+    var_ref = np.average((x_pre[:, 0] - mean_ref) ** 2, weights=w_ref)
+    np.testing.assert_allclose(st2.mean[0], mean_ref, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(st2.cov[0, 0], var_ref, rtol=1e-5)
+
+    # after resampling the particle set depends on which ancestors fp32 weights select: the
+    # resampled mean is the same estimator with O(1/sqrt(N)) Monte-Carlo spread
     st = pf.step(z)
-    np.testing.assert_allclose(st.mean, o.mean, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(st.cov, o.cov, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(st.mean, o.mean, rtol=0, atol=5 * np.sqrt(var_ref / N))
+    np.testing.assert_allclose(st.cov, o.cov, rtol=0.02)
     # ancestors exact when the resampler is fed the oracle's fp64 weights and u
     got = systematic_ancestors(w_ref, 0.4321)
     assert_ancestors(got, o.info["ancestors"], w_ref, 0.4321, max_mismatch=0)
