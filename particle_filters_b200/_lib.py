@@ -43,7 +43,7 @@ class LedhDesc(C.Structure):
         ("n", C.c_int64), ("ld", C.c_int64),
         ("nx", C.c_int32), ("nz", C.c_int32), ("dtype", C.c_int32), ("n_lambda_steps", C.c_int32),
         ("eta0_dev", C.c_void_p), ("eta_dev", C.c_void_p), ("theta_log_dev", C.c_void_p),
-        ("cond_dev", C.c_void_p),
+        ("s0_dev", C.c_void_p),
     ]
 
 
@@ -82,7 +82,10 @@ _LEDH_SIG = {
     "smc_ledh_flow": (C.c_int, [C.POINTER(LedhDesc), _D, _D, _D, C.c_int32, _D, C.c_int32, _P]),
     "smc_ledh_flow_step_supplied": (C.c_int, [C.POINTER(LedhDesc), _D, _D, _D, _P, _P, C.c_double,
                                               C.c_double, C.c_int32, _P]),
+    "smc_ledh_weights": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P, _P]),
+    "smc_weighted_moments": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P]),
 }
+SMC_LEDH_H_LINEAR, SMC_LEDH_H_ACOUSTIC, SMC_LEDH_H_EXP = 1, 2, 3
 
 
 class SmcError(RuntimeError):
@@ -105,8 +108,6 @@ def load() -> C.CDLL:
     for table in (_SIG, _LEDH_SIG):
         for name, (res, args) in table.items():
             if not hasattr(lib, name):
-                if table is _LEDH_SIG:
-                    continue
                 raise SmcError(f"libsmc.so does not export {name}")
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
@@ -114,7 +115,7 @@ def load() -> C.CDLL:
         raise SmcError("libsmc.so ABI version mismatch; rebuild")
     if lib.smc_sizeof_sir_desc() != C.sizeof(SirDesc):
         raise SmcError("smc_sir_desc layout mismatch between include/smc.h and _lib.py")
-    if hasattr(lib, "smc_sizeof_ledh_desc") and lib.smc_sizeof_ledh_desc() != C.sizeof(LedhDesc):
+    if lib.smc_sizeof_ledh_desc() != C.sizeof(LedhDesc):
         raise SmcError("smc_ledh_desc layout mismatch between include/smc_ledh.h and _lib.py")
     _lib = lib
     return lib

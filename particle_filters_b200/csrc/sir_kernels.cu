@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kThreads) k1_propagate_weight(K1Args<real> a, 
 // ==============================================================================================
 // K2: finalize.  One CTA reduces the partial records in a fixed order.
 // ==============================================================================================
+__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global);   // defined with the resampler
+
 struct K2Args {
     Ctrl* ctrl;
     const double* parts;
@@ -299,29 +301,6 @@ struct K2Args {
     uint64_t seed;
     uint32_t t;
 };
-
-__device__ inline double block_sum_256(double v, double* s_tmp) {
-    v = warp_sum(v);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) s_tmp[warp] = v;
-    __syncthreads();
-    double r = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) r += s_tmp[w];
-    return r;
-}
-__device__ inline double block_max_256(double v, double* s_tmp) {
-    v = warp_max(v);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) s_tmp[warp] = v;
-    __syncthreads();
-    double r = s_tmp[0];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) r = s_tmp[w] > r ? s_tmp[w] : r;
-    return r;
-}
 
 // Combine partial records (max-shifted sums) into one record `out` of the same layout
 // (out[0] = global max, sums relative to it).  All threads of the CTA return the record in smem.
@@ -380,6 +359,7 @@ __global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
     c->u = u;
     c->do_resample = do_res;
     c->uniform = 0;
+    ctrl_prepare_search(c, a.n_global);
     if (a.stats) {
         a.stats[0] = log_norm;
         a.stats[1] = ess;
@@ -455,6 +435,26 @@ __device__ inline SearchParams make_search(double u, int64_t n_global) {
     return sp;
 }
 
+// Once per step (finalize / set_uniform): cache the resampler constants in the control block so
+// that the 16 K resampling CTAs do not each redo the fp64 log / ldexp work.
+__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global) {
+    const SearchParams sp = make_search(c->u, n_global);
+    c->frac_bits = sp.F;
+    c->uq = sp.uq;
+    c->margin = sp.margin;
+    c->lw_ref = c->log_norm - log((double)n_global);
+}
+__device__ inline SearchParams load_search(const Ctrl* c, int64_t n_global) {
+    SearchParams sp;
+    sp.F = c->frac_bits;
+    sp.u = c->u;
+    sp.uq = c->uq;
+    sp.fmask = (1ull << sp.F) - 1ull;
+    sp.margin = c->margin;
+    sp.n_global = n_global;
+    return sp;
+}
+
 // e(C) = #{ i in [0, N) : pos_i < C }  (first output index NOT owned by CDF value C)
 __device__ inline int64_t outputs_below(unsigned long long C, const SearchParams& sp) {
     const int64_t I = (int64_t)(C >> sp.F);
@@ -479,8 +479,7 @@ template <typename real> struct K3Args {
     real* const* peer0;         // nullable: per-shard destination pointers (cur == 1 / cur == 0)
     real* const* peer1;
     int32_t* ancestors;         // nullable
-    unsigned long long* agg;
-    unsigned long long* incl;
+    ulonglong2* state;          // per-tile {aggregate, inclusive prefix} words
     unsigned int* ticket;
     double* mom_parts;          // nullable
     unsigned long long cdf_offset;
@@ -502,28 +501,48 @@ __device__ inline void unit_to_array(const float4& u, float* v) { v[0] = u.x; v[
 __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; v[1] = u.y; }
 
 
-// decoupled look-back over tile aggregates / inclusive prefixes (integer -> order independent)
-__device__ inline unsigned long long lookback(volatile unsigned long long* agg,
-                                              volatile unsigned long long* incl, int64_t tile, int lane) {
+// Decoupled look-back over tile state records (integer sums -> order independent).
+// One 16-byte record per tile: .x = aggregate word, .y = inclusive-prefix word, bit 63 = valid.
+// Each lane inspects kLookPerLane predecessors per round with independent 128-bit loads, so one
+// L2 round trip covers a window of 32 * kLookPerLane tiles.
+constexpr int kLookPerLane = 4;
+__device__ inline ulonglong2 ld_tile_state(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+__device__ inline unsigned long long lookback(const ulonglong2* state, int64_t tile, int lane) {
     unsigned long long sum = 0;
-    int64_t p = tile - 1 - lane;
+    int64_t p0 = tile - 1;                       // nearest predecessor of this round
     while (true) {
-        unsigned long long vi = kValidBit, va = 0;   // tiles before 0: inclusive prefix 0
-        if (p >= 0) {
-            vi = incl[p];
-            va = (vi & kValidBit) ? 0ull : agg[p];
+        // lane l looks at predecessors p0 - (l * kLookPerLane + q), q = 0..kLookPerLane-1 (nearest first)
+        ulonglong2 st[kLookPerLane];
+#pragma unroll
+        for (int q = 0; q < kLookPerLane; ++q) {
+            const int64_t p = p0 - (lane * kLookPerLane + q);
+            st[q] = p >= 0 ? ld_tile_state(state + p) : make_ulonglong2(0ull, kValidBit);   // before tile 0: prefix 0
         }
-        const bool have_i = (vi & kValidBit) != 0, have_a = (va & kValidBit) != 0;
-        const unsigned mask_i = __ballot_sync(0xffffffffu, have_i);
-        const int first = mask_i ? (__ffs(mask_i) - 1) : 32;
-        const bool missing = (lane < first) && !have_a;
-        if (__ballot_sync(0xffffffffu, missing)) continue;     // someone not published yet: re-read
+        // per lane: contribution of its run up to (and including) its first inclusive prefix
         unsigned long long contrib = 0;
-        if (lane < first) contrib = va & ~kValidBit;
-        else if (lane == first) contrib = vi & ~kValidBit;
-        sum += warp_sum(contrib);
-        if (first < 32) break;
-        p -= 32;
+        bool lane_has_incl = false, lane_missing = false;
+#pragma unroll
+        for (int q = 0; q < kLookPerLane; ++q) {
+            if (lane_has_incl || lane_missing) continue;
+            if (st[q].y & kValidBit) { contrib += st[q].y & ~kValidBit; lane_has_incl = true; }
+            else if (st[q].x & kValidBit) contrib += st[q].x & ~kValidBit;
+            else lane_missing = true;
+        }
+        const unsigned mask_i = __ballot_sync(0xffffffffu, lane_has_incl);
+        const unsigned mask_m = __ballot_sync(0xffffffffu, lane_missing);
+        const int first_i = mask_i ? (__ffs(mask_i) - 1) : 32;
+        const int first_m = mask_m ? (__ffs(mask_m) - 1) : 32;
+        // a lane sets at most one of the two flags; an unpublished tile nearer than the first
+        // inclusive prefix means the window is not complete yet: read it again
+        if (first_m < first_i) continue;
+        const unsigned long long take = (lane <= first_i) ? contrib : 0ull;
+        sum += warp_sum(take);
+        if (first_i < 32) break;
+        p0 -= 32 * kLookPerLane;
     }
     return sum;
 }
@@ -579,7 +598,7 @@ __device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bia
 }
 
 template <typename real, int NXF, bool LINEAR_W>
-__global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
+__global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 : 2) k3_resample(K3Args<real> a) {
     using G = K3Geom<real>;
     using unit = typename G::unit;
     constexpr int IPT = G::IPT, EPU = G::EPU;
@@ -615,7 +634,7 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
     const int64_t tile = s_tile;
     const int64_t tile_base = tile * TILE;
 
-    const SearchParams sp = make_search(ctrl->u, a.n_global);
+    const SearchParams sp = load_search(ctrl, a.n_global);
     FastSearch fs;
     fs.bias = sp.fmask - sp.uq;
     fs.sh = (uint32_t)(sp.F - 32);
@@ -624,34 +643,56 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
     Quant<real> quant;
     quant.init(sp.F);
     // weight = exp(lw - log_norm) * N  =  exp(lw - (log_norm - log N))
-    const real lw_ref = LINEAR_W ? real(0) : (real)(ctrl->log_norm - log((double)a.n_global));
+    const real lw_ref = LINEAR_W ? real(0) : (real)ctrl->lw_ref;
     const real n_real = (real)a.n_global;
 
     // ---- phase A: coalesced loads -> shared ------------------------------------------------
+    // particle payload: asynchronous global->shared copies (LDGSTS, no register staging); they are
+    // only awaited after the look-back, so their HBM latency overlaps the scan
+    const bool interior = tile_base + TILE <= a.n;          // no per-element bounds checks needed
+    const int n_in_tile = interior ? TILE : (int)(a.n - tile_base);
+    if (NXF > 0) {
 #pragma unroll
-    for (int r = 0; r < UPT; ++r) {
-        const int f = r * kThreads + tid;                       // logical 16B unit in the tile
-        const int64_t i0 = tile_base + (int64_t)f * EPU;
-        unit v;
-        real fill = LINEAR_W ? real(0) : real(-INFINITY);
-        real tmp[EPU];
-        if (i0 < a.n) {
-            v = *reinterpret_cast<const unit*>(a.wsrc + i0);
-            unit_to_array(v, tmp);
+        for (int r = 0; r < UPT; ++r) {
+            const int f = r * kThreads + tid;
+            if (f * EPU < n_in_tile) {
 #pragma unroll
-            for (int j = 0; j < EPU; ++j) if (i0 + j >= a.n) tmp[j] = fill;
-        } else {
-#pragma unroll
-            for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+                for (int d = 0; d < NXF; ++d) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + f * EPU);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst),
+                                 "l"(xsrc + d * a.ld + tile_base + f * EPU) : "memory");
+                }
+            }
         }
-        real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & 3)]);
+    }
+    {
+        const unit* wtile = reinterpret_cast<const unit*>(a.wsrc + tile_base);
+        if (interior) {
+            unit v[UPT];
 #pragma unroll
-        for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
-        if (NXF > 0 && i0 < a.n) {
+            for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kThreads + tid];
 #pragma unroll
-            for (int d = 0; d < NXF; ++d)
-                *reinterpret_cast<unit*>(x_s + d * TILE + f * EPU) =
-                    *reinterpret_cast<const unit*>(xsrc + d * a.ld + i0);
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * kThreads + tid;
+                lw_s[f ^ ((f >> 3) & 3)] = v[r];
+            }
+        } else {
+            const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * kThreads + tid;
+                real tmp[EPU];
+#pragma unroll
+                for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+                if (f * EPU < n_in_tile) {
+                    unit_to_array(wtile[f], tmp);
+#pragma unroll
+                    for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
+                }
+                real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & 3)]);
+#pragma unroll
+                for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
+            }
         }
     }
     __syncthreads();
@@ -669,8 +710,7 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
 #pragma unroll
             for (int j = 0; j < EPU; ++j) {
                 real v = LINEAR_W ? tmp[j] * n_real : fast_exp(tmp[j] - lw_ref);
-                v = (v > real(0)) ? v : real(0);             // NaN / negative -> 0
-                v = v < n_real ? v : n_real;
+                v = fmin(fmax(v, real(0)), n_real);          // NaN / negative -> 0, cap at N
                 run = quant.add(run, v, runf);
                 c[k * EPU + j] = run;                        // inclusive within thread
             }
@@ -692,22 +732,22 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
         tile_agg += t;
     }
     if (warp == 0) {
-        volatile unsigned long long* vagg = a.agg;
-        volatile unsigned long long* vincl = a.incl;
+        volatile unsigned long long* words = reinterpret_cast<volatile unsigned long long*>(a.state + tile);
         if (tile == 0) {
             if (lane == 0) {
-                vincl[0] = kValidBit | (a.cdf_offset + tile_agg);
+                words[1] = kValidBit | (a.cdf_offset + tile_agg);
                 s_prefix = a.cdf_offset;
             }
         } else {
-            if (lane == 0) vagg[tile] = kValidBit | tile_agg;
-            unsigned long long pre = lookback(vagg, vincl, tile, lane);
+            if (lane == 0) words[0] = kValidBit | tile_agg;
+            unsigned long long pre = lookback(a.state, tile, lane);
             if (lane == 0) {
-                vincl[tile] = kValidBit | (pre + tile_agg);
+                words[1] = kValidBit | (pre + tile_agg);
                 s_prefix = pre;
             }
         }
     }
+    if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
 
     // ---- phase C: output boundaries (32-bit) -------------------------------------------------
@@ -809,23 +849,27 @@ __global__ void __launch_bounds__(kThreads) k3_resample(K3Args<real> a) {
                 real* dwin = xdst + (g0 - a.offset);                 // local destination of slot 0
                 int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) : nullptr;
                 const int32_t abase = (int32_t)(a.offset + tile_base);
-                for (int p = tid; p < cnt; p += kThreads) {
-                    const int li = (int)out_s[p] - 1;                // local ancestor
-                    if (awin) awin[p] = abase + li;
-                    if (NXF > 0) {
-                        real xv[NXF > 0 ? NXF : 1];
 #pragma unroll
-                        for (int d = 0; d < NXF; ++d) {
-                            xv[d] = x_s[d * TILE + li];
-                            dwin[d * a.ld + p] = xv[d];
+                for (int it = 0; it < CH; ++it) {
+                    const int p = it * kThreads + tid;
+                    if (p < cnt) {
+                        const int li = (int)out_s[p] - 1;            // local ancestor
+                        if (awin) awin[p] = abase + li;
+                        if (NXF > 0) {
+                            real xv[NXF > 0 ? NXF : 1];
+#pragma unroll
+                            for (int d = 0; d < NXF; ++d) {
+                                xv[d] = x_s[d * TILE + li];
+                                dwin[d * a.ld + p] = xv[d];
+                            }
+                            int k = 0;
+#pragma unroll
+                            for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
+#pragma unroll
+                            for (int d = 0; d < NXF; ++d)
+#pragma unroll
+                                for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
                         }
-                        int k = 0;
-#pragma unroll
-                        for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
-#pragma unroll
-                        for (int d = 0; d < NXF; ++d)
-#pragma unroll
-                            for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
                     }
                 }
             } else {
@@ -879,10 +923,10 @@ __global__ void __launch_bounds__(kThreads) k_shard_total(const Ctrl* ctrl, cons
     // same quantisation as k3_resample: one thread owns IPT consecutive items and quantises
     // its running sum, so the shard total equals the last inclusive prefix K3 will compute
     constexpr int IPT = K3Geom<real>::IPT;
-    const real lw_ref = (real)(ctrl->log_norm - log((double)n_global));
+    const real lw_ref = (real)ctrl->lw_ref;
     const real n_real = (real)n_global;
     Quant<real> quant;
-    quant.init(frac_bits_for(n_global));
+    quant.init(ctrl->frac_bits);
     unsigned long long acc = 0;
     const int64_t n_groups = cdiv64(n, IPT);
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kThreads) {
@@ -1004,15 +1048,19 @@ __global__ void k_moments_generic_fix(const Ctrl* ctrl, int nx, double* stats) {
 // ==============================================================================================
 __global__ void k_reset_ctrl(Ctrl* c, const double* shift, int nx) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        c->log_norm = 0.0; c->ess = 0.0; c->u = 0.0; c->cur = 0; c->uniform = 1; c->do_resample = 0; c->pad = 0;
+        c->log_norm = 0.0; c->ess = 0.0; c->u = 0.0; c->cur = 0; c->uniform = 1; c->do_resample = 0;
+        c->frac_bits = 32; c->lw_ref = 0.0; c->uq = 0ull; c->margin = 0ull;
         for (int d = 0; d < kMaxNx; ++d) c->shift[d] = (shift && d < nx) ? shift[d] : 0.0;
     }
 }
-__global__ void k_set_uniform(Ctrl* c, double u) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) c->u = u;
+__global__ void k_set_uniform(Ctrl* c, double u, int64_t n_global) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { c->u = u; ctrl_prepare_search(c, n_global); }
 }
-__global__ void k_set_resample(Ctrl* c, double u) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { c->u = u; c->do_resample = 1; c->cur = 0; c->log_norm = 0.0; }
+__global__ void k_set_resample(Ctrl* c, double u, int64_t n_global) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        c->u = u; c->do_resample = 1; c->cur = 0; c->log_norm = 0.0;
+        ctrl_prepare_search(c, n_global);
+    }
 }
 
 template <typename real>
@@ -1149,7 +1197,6 @@ struct Launch {
     double* slot(int k) const { return reinterpret_cast<double*>(ws + L.params) + (size_t)k * kParamSlotDoubles; }
     double* k1_parts() const { return reinterpret_cast<double*>(ws + L.k1_parts); }
     unsigned long long* agg() const { return reinterpret_cast<unsigned long long*>(ws + L.tile_agg); }
-    unsigned long long* incl() const { return reinterpret_cast<unsigned long long*>(ws + L.tile_incl); }
     unsigned int* ticket() const { return reinterpret_cast<unsigned int*>(ws + L.ticket); }
     double* mom_parts() const { return reinterpret_cast<double*>(ws + L.mom_parts); }
 };
@@ -1248,6 +1295,8 @@ int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
     static bool attr_set = false;   // one flag per template instantiation
     if (!attr_set) {
         SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     kern<<<(unsigned)n_tiles, kThreads, smem, l.st>>>(a);
@@ -1274,7 +1323,7 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
         a.peer1 = reinterpret_cast<real* const*>(peer) + n_shards;
     }
     a.ancestors = ((d->flags & SMC_FLAG_WRITE_ANCESTORS) || nxf == 0) ? d->ancestors_dev : nullptr;
-    a.agg = l.agg(); a.incl = l.incl(); a.ticket = l.ticket();
+    a.state = reinterpret_cast<ulonglong2*>(l.agg()); a.ticket = l.ticket();
     a.mom_parts = want_moments ? l.mom_parts() : nullptr;
     a.cdf_offset = cdf_offset;
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
@@ -1428,7 +1477,7 @@ int smc_sir_set_uniform(const smc_sir_desc* d, double u, void* stream) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
-    k_set_uniform<<<1, 32, 0, l.st>>>(l.ctrl(), u);
+    k_set_uniform<<<1, 32, 0, l.st>>>(l.ctrl(), u, d->n_global);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1535,7 +1584,7 @@ int smc_systematic_ancestors(const double* w_dev, int64_t n, double u, int32_t* 
     if (int rc = check_desc(&d, &l, stream)) return rc;
     SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
     SMC_REQUIRE(w_dev && ancestors_dev, "smc: null buffer");
-    k_set_resample<<<1, 32, 0, l.st>>>(l.ctrl(), u);
+    k_set_resample<<<1, 32, 0, l.st>>>(l.ctrl(), u, d.n_global);
     SMC_CHECK_CUDA(cudaGetLastError());
     return launch_k3<double>(l, true, w_dev, 0, 0ull, 1, nullptr, 0, false);
 }

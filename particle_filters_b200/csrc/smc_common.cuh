@@ -58,13 +58,17 @@ struct Ctrl {
     int32_t cur;         // which ping-pong buffer holds the current particles
     int32_t uniform;     // 1: current weights are exactly uniform (fresh / just resampled)
     int32_t do_resample; // decision of the last finalize
-    int32_t pad;
+    int32_t frac_bits;   // F of the fixed-point CDF for this population size
+    // resampler constants derived once per step from (u, log_norm, N) by the finalize kernel
+    double lw_ref;                 // log_norm - log N : N w = exp(lw - lw_ref)
+    unsigned long long uq;         // floor(u 2^F)
+    unsigned long long margin;     // near-tie margin in fraction units
 };
 static_assert(sizeof(Ctrl) <= 1024, "control block must fit its slot");
 
 // Workspace layout (all offsets 256-B aligned), computed identically on host and device.
 struct WsLayout {
-    size_t ctrl, params, k1_parts, tile_agg, tile_incl, ticket, mom_parts, total;
+    size_t ctrl, params, k1_parts, tile_agg, ticket, mom_parts, total;   // tile_agg: 16-B {aggregate, inclusive} records
     int64_t n_k1_blocks, n_tiles;
 };
 constexpr int kParamSlots = 4;            // host->device staging slots for small matrices
@@ -97,8 +101,7 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     L.ctrl = off;      off = align256(off + 1024);
     L.params = off;    off = align256(off + size_t(kParamSlots) * kParamSlotDoubles * sizeof(double));
     L.k1_parts = off;  off = align256(off + size_t(L.n_k1_blocks) * partial_stride(nx) * sizeof(double));
-    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 8);
-    L.tile_incl = off; off = align256(off + size_t(L.n_tiles) * 8);
+    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16);
     L.ticket = off;    off = align256(off + 256);
     L.mom_parts = off; off = align256(off + size_t(L.n_tiles) * moment_stride(nx) * sizeof(double));
     L.total = off;
@@ -190,6 +193,30 @@ template <typename T> __device__ inline T warp_max(T v) {
         v = w > v ? w : v;
     }
     return v;
+}
+
+// CTA-wide (256 threads) reductions through a kWarps-slot shared scratch; every thread gets the result
+__device__ inline double block_sum_256(double v, double* s_tmp) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) r += s_tmp[w];
+    return r;
+}
+__device__ inline double block_max_256(double v, double* s_tmp) {
+    v = warp_max(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    double r = s_tmp[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) r = s_tmp[w] > r ? s_tmp[w] : r;
+    return r;
 }
 
 // vector type helper

@@ -85,3 +85,84 @@ def spec_of(g, h):
             and getattr(h, "__func__", None) is type(sg).h:
         return sg
     return None
+
+
+# ---------------------------------------------------------------------------------------------
+# measurement specs for the LEDH flow kernel (h and its Jacobian evaluated on chip)
+# ---------------------------------------------------------------------------------------------
+class _MeasurementSpec:
+    def ledh_functor(self):
+        raise NotImplementedError
+
+
+class LinearMeasurement(_MeasurementSpec):
+    """``h(x) = H x``, ``jacobian_h(x) = H``."""
+
+    def __init__(self, H):
+        self.H = np.atleast_2d(np.asarray(H, float))
+
+    def h(self, x):
+        return self.H @ x
+
+    def jacobian_h(self, x):
+        return self.H
+
+    def ledh_functor(self):
+        return _lib.SMC_LEDH_H_LINEAR, self.H.ravel()
+
+
+class AcousticMeasurement(_MeasurementSpec):
+    """Amplitude sensors over constant-velocity targets: state = n_targets x [x, y, vx, vy],
+    ``z_s = sum_c psi / (|p_c - s|^2 + d0)`` (reference
+    simulator/simulator_Multi_acoustic_tracking.py:273-310; single-target form in
+    tests/integration_tests/test_filters_mat_simulator.py:44-66)."""
+
+    def __init__(self, sensors, psi: float, d0: float, n_targets: int = 1):
+        self.S = np.asarray(sensors, float).reshape(-1, 2)
+        self.psi, self.d0, self.n_targets = float(psi), float(d0), int(n_targets)
+
+    def _parts(self, x):
+        pos = np.asarray(x, float).reshape(self.n_targets, 4)[:, :2]
+        diff = pos[:, None, :] - self.S[None, :, :]
+        den = np.sum(diff ** 2, axis=-1) + self.d0
+        return diff, den
+
+    def h(self, x):
+        _, den = self._parts(x)
+        return np.sum(self.psi / den, axis=0)
+
+    def jacobian_h(self, x):
+        diff, den = self._parts(x)
+        coef = -2.0 * self.psi / den ** 2
+        H = np.zeros((self.S.shape[0], 4 * self.n_targets))
+        for c in range(self.n_targets):
+            H[:, 4 * c] = coef[c] * diff[c, :, 0]
+            H[:, 4 * c + 1] = coef[c] * diff[c, :, 1]
+        return H
+
+    def ledh_functor(self):
+        return _lib.SMC_LEDH_H_ACOUSTIC, np.concatenate([[self.psi, self.d0], self.S.ravel()])
+
+
+class ExpMeasurement(_MeasurementSpec):
+    """``h_i(x) = beta exp(x_i / 2)`` (stochastic volatility, additive-noise form)."""
+
+    def __init__(self, beta: float):
+        self.beta = float(beta)
+
+    def h(self, x):
+        return self.beta * np.exp(0.5 * np.asarray(x, float))
+
+    def jacobian_h(self, x):
+        return np.diag(0.5 * self.beta * np.exp(0.5 * np.asarray(x, float)))
+
+    def ledh_functor(self):
+        return _lib.SMC_LEDH_H_EXP, np.array([self.beta])
+
+
+def measurement_spec_of(h, jacobian_h):
+    sh, sj = getattr(h, "__self__", None), getattr(jacobian_h, "__self__", None)
+    if isinstance(sh, _MeasurementSpec) and sh is sj and getattr(h, "__func__", None) is type(sh).h \
+            and getattr(jacobian_h, "__func__", None) is type(sh).jacobian_h:
+        return sh
+    return None

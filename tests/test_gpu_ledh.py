@@ -1,0 +1,227 @@
+"""GPU parity tests of the LEDH particle-flow path (K4 + weight tail) against the
+reference runs stored in tests/golden/ledh_*.npz and the NumPy oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import ledh_weighted_stats
+from oracle.ledh_numpy import ledh_flow
+from parity import assert_ancestors
+from ssm_zoo import AcousticCVModel, Linear1DModel
+
+pytestmark = pytest.mark.gpu
+
+
+class ScriptedTracker:
+    """GaussianTracker protocol (reference LEDH_particle_filter.py:13-16) replaying (m, P)."""
+
+    def __init__(self, Ps, nx):
+        self.Ps, self.k, self.nx, self.updates = Ps, 0, nx, 0
+
+    def predict(self):
+        P = self.Ps[self.k]
+        self.k += 1
+        return np.zeros(self.nx), P
+
+    def update(self, z):
+        self.updates += 1
+        return np.zeros(self.nx), self.Ps[self.k - 1]
+
+    def get_past_mean(self):
+        return np.zeros(self.nx)
+
+
+def _cases():
+    return [
+        ("ledh_linear1d.npz", Linear1DModel(), 1e-8, "linear"),
+        ("ledh_linear1d_resample.npz", Linear1DModel(), 1e-8, "linear"),
+        ("ledh_acoustic1.npz", AcousticCVModel(n_targets=1, grid=(3, 3)), 1e-8, "acoustic"),
+        ("ledh_acoustic2.npz", AcousticCVModel(n_targets=2, grid=(4, 4)), 2e-5, "acoustic"),
+    ]
+
+
+def _measurement_spec(model, kind):
+    from particle_filters_b200 import AcousticMeasurement, LinearMeasurement
+
+    if kind == "linear":
+        return LinearMeasurement(np.array([[1.0]]))
+    return AcousticMeasurement(model.S, model.psi, model.d0, n_targets=model.n_targets)
+
+
+@pytest.mark.parametrize("mode", ["bridge", "device_h"])
+@pytest.mark.parametrize("name,model,tol,kind", _cases())
+def test_ledh_step_tracks_reference(golden, name, model, tol, kind, mode):
+    from particle_filters_b200.ledh_particle_filter import LEDHConfig, LEDHFlowPF, PFState
+
+    g = golden(name)
+    N, L, T = int(g["N"]), int(g["L"]), int(g["T"])
+    rng = np.random.default_rng(int(g["seed"]) + 1)
+    rng.multivariate_normal(np.zeros(model.nx), np.eye(model.nx), size=N)    # init draw of the reference run
+    cfg = LEDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=float(g["ess_ratio"]), rng=rng)
+    tracker = ScriptedTracker(g["Ps"], model.nx)
+    if mode == "bridge":
+        h, jh = (lambda x: model.h(x)), (lambda x: model.jac_h(x))
+    else:
+        spec = _measurement_spec(model, kind)
+        h, jh = spec.h, spec.jacobian_h
+    f = LEDHFlowPF(tracker, model.g, h, jh, model.log_trans_pdf, model.log_like_pdf, model.R, cfg)
+    x, w = g["particles0"], g["weights0"]
+    mean0, cov0 = ledh_weighted_stats(x, w)
+    for k in range(T):
+        st = PFState(particles=x, weights=w, mean=mean0, cov=cov0, diagnostics={})
+        V = g["V"][k]
+        sampler = (lambda n_, d_, V=V: V) if bool(g["with_noise"]) else None
+        out = f.step(st, g["Z"][k], None, sampler)
+        assert out.particles.shape == (N, model.nx) and out.weights.shape == (N,)
+        np.testing.assert_allclose(np.sum(out.weights), 1.0, rtol=1e-10)
+        np.testing.assert_allclose(out.particles, g[f"particles_{k}"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out.weights, g[f"weights_{k}"], rtol=200 * tol, atol=1e-12)
+        np.testing.assert_allclose(out.mean, g[f"mean_{k}"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(out.cov, g[f"cov_{k}"], rtol=20 * tol, atol=20 * tol)
+        np.testing.assert_allclose(out.cov, out.cov.T, rtol=0, atol=0)
+        np.testing.assert_allclose(out.diagnostics["condition_numbers"], g[f"cond_{k}"], rtol=1e-6)
+        assert len(out.diagnostics["condition_numbers"]) == L
+        # continue from the reference's state so one step's round-off cannot compound
+        x, w = g[f"particles_{k}"], g[f"weights_{k}"]
+        mean0, cov0 = g[f"mean_{k}"], g[f"cov_{k}"]
+    assert tracker.updates == T
+
+
+def test_flow_kernel_matches_oracle_flow_fp64_and_fp32():
+    """K4 alone: eta and log-det sum vs the NumPy oracle flow on a 16-D / 25-sensor problem
+    (BASELINE config 5 shape, small N)."""
+    import ctypes as C
+
+    from particle_filters_b200 import AcousticMeasurement, _lib
+    from particle_filters_b200.ledh_particle_filter import _FlowBuffers
+
+    m = AcousticCVModel(n_targets=4, grid=(5, 5), r_var=0.05)
+    rng = np.random.default_rng(4)
+    N, L = 257, 8
+    centre = np.array([10, 12, .5, -.3, 30, 28, -.4, .2, 12, 30, .3, .3, 28, 10, -.2, .4])
+    eta0 = centre + rng.standard_normal((N, 16)) * np.tile([1.5, 1.5, .3, .3], 4)
+    P = np.kron(np.eye(4), np.diag([4.0, 4.0, 0.3, 0.3])) + 0.05
+    P = 0.5 * (P + P.T)
+    z = m.h(centre) + 0.1 * rng.standard_normal(25)
+    eta_ref, theta_ref, cond_ref = ledh_flow(eta0, P, m.R, z, m.h_batch, m.jac_batch, L)
+    spec = AcousticMeasurement(m.S, m.psi, m.d0, n_targets=4)
+    kind, hp = spec.ledh_functor()
+    lib = _lib.load()
+    for dtype, tol in (("f64", 1e-8), ("f32", 5e-3)):
+        buf = _FlowBuffers(N, 16, 25, L, dtype, None)
+        buf.load(eta0)
+        kP, pP = _lib.as_doubles(P)
+        kR, pR = _lib.as_doubles(m.R)
+        kz, pz = _lib.as_doubles(z)
+        kh, ph = _lib.as_doubles(hp)
+        _lib.check(lib.smc_ledh_flow(C.byref(buf.desc), pP, pR, pz, kind, ph, kh.size, buf.stream))
+        eta = buf.eta_host()
+        theta = buf.theta[:N].cpu().numpy().astype(np.float64)
+        scale = np.abs(eta_ref).max()
+        err = np.abs(eta - eta_ref)
+        if dtype == "f64":
+            assert err.max() <= tol * scale, (dtype, err.max())
+            np.testing.assert_allclose(theta, theta_ref, rtol=0, atol=1e-8 * max(1.0, np.abs(theta_ref).max()))
+        else:
+            # fp32 flow: particles that pass close to a sensor see Jacobians ~ psi/d0^2 and a stiff
+            # S; their fp32 trajectories are ill-conditioned, so the bar is on the bulk, not the max
+            assert np.quantile(err, 0.95) <= tol * scale, (dtype, np.quantile(err, 0.95))
+            assert np.median(np.abs(theta - theta_ref)) <= 1e-3 * max(1.0, np.abs(theta_ref).max())
+        if dtype == "f64":
+            cond = [np.linalg.cond(s) for s in buf.s0.cpu().numpy()]
+            np.testing.assert_allclose(cond, cond_ref, rtol=1e-8)
+
+
+def test_init_from_gaussian_and_weighted_stats():
+    from particle_filters_b200.ledh_particle_filter import LEDHConfig, LEDHFlowPF
+
+    m = Linear1DModel()
+
+    def make(seed):
+        cfg = LEDHConfig(n_particles=300, rng=np.random.default_rng(seed))
+        return LEDHFlowPF(ScriptedTracker([np.eye(1)], 1), m.g, m.h, m.jac_h, m.log_trans_pdf, m.log_like_pdf, m.R, cfg)
+
+    a = make(5).init_from_gaussian(np.array([0.5]), np.array([[0.3]]))
+    b = make(5).init_from_gaussian(np.array([0.5]), np.array([[0.3]]))
+    assert a.particles.shape == (300, 1) and a.diagnostics == {}
+    np.testing.assert_array_equal(a.particles, b.particles)
+    np.testing.assert_allclose(a.weights, 1.0 / 300, rtol=0, atol=0)
+    mref, cref = ledh_weighted_stats(a.particles, a.weights)
+    np.testing.assert_allclose(a.mean, mref, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(a.cov, cref, rtol=1e-10)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((77, 5)) + 3.0
+    w = rng.random(77)
+    mean, cov = LEDHFlowPF._weighted_stats(x, w)
+    mref, cref = ledh_weighted_stats(x, w)
+    np.testing.assert_allclose(mean, mref, rtol=1e-12)
+    np.testing.assert_allclose(cov, cref, rtol=1e-10, atol=1e-14)
+
+
+def test_module_level_resample_and_ess(golden):
+    from particle_filters_b200.ledh_particle_filter import effective_sample_size, systematic_resample
+
+    g = golden("resample_cases.npz")
+
+    class U:
+        def __init__(self, u):
+            self.u = u
+
+        def random(self):
+            return self.u
+
+    checked = 0
+    for k in range(0, int(g["n_cases"]), 4):
+        if not bool(g[f"c{k}_ledh_ok"]):
+            continue
+        w, u = g[f"c{k}_w"] * 3.7, float(g[f"c{k}_u"])          # un-normalised on purpose (:27)
+        idx = systematic_resample(w, U(u))
+        assert idx.dtype == np.int64 and idx.shape == w.shape
+        wn = w / np.sum(w)
+        assert_ancestors(idx, g[f"c{k}_ledh"], wn, u, clamp_last=False, msg=f"case {k}")
+        np.testing.assert_allclose(effective_sample_size(w), 1.0 / np.sum(wn ** 2), rtol=1e-10)
+        checked += 1
+    assert checked >= 15
+
+
+@pytest.mark.parametrize("N,nx,nz", [(1, 1, 1), (5, 3, 2), (64, 9, 4)])
+def test_ledh_shapes_small_and_odd_dims(N, nx, nz):
+    """Dimensions the reference tests use (nx in {1,3,9}, nz in {1,2,4}); linear-Gaussian model,
+    bridge vs on-chip measurement functor must agree."""
+    from particle_filters_b200 import LinearMeasurement
+    from particle_filters_b200.ledh_particle_filter import LEDHConfig, LEDHFlowPF
+
+    rng = np.random.default_rng(N + nx)
+    H = rng.standard_normal((nz, nx))
+    F = 0.9 * np.eye(nx)
+    Q, R = 0.05 * np.eye(nx), 0.2 * np.eye(nz)
+    P = np.eye(nx) * 0.5 + 0.05
+
+    def g(x, u, v):
+        return F @ x + (0 if v is None else v)
+
+    def ltp(xk, xp):
+        d = xk - F @ xp
+        return float(-0.5 * d @ np.linalg.solve(Q, d))
+
+    def llp(z, x):
+        d = z - H @ x
+        return float(-0.5 * d @ np.linalg.solve(R, d))
+
+    outs = []
+    for mode in ("bridge", "device"):
+        cfg = LEDHConfig(n_particles=N, n_lambda_steps=4, resample_ess_ratio=0.5, rng=np.random.default_rng(1))
+        spec = LinearMeasurement(H)
+        h, jh = ((lambda x: H @ x), (lambda x: H)) if mode == "bridge" else (spec.h, spec.jacobian_h)
+        f = LEDHFlowPF(ScriptedTracker([P, P], nx), g, h, jh, ltp, llp, R, cfg)
+        st = f.init_from_gaussian(np.zeros(nx), np.eye(nx))
+        z = rng.standard_normal(nz) if mode == "bridge" else z
+        st = f.step(st, z, None, None)
+        assert st.particles.shape == (N, nx) and np.all(np.isfinite(st.particles))
+        np.testing.assert_allclose(np.sum(st.weights), 1.0, rtol=1e-10)
+        assert st.cov.shape == (nx, nx)
+        outs.append(st)
+    np.testing.assert_allclose(outs[0].particles, outs[1].particles, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(outs[0].weights, outs[1].weights, rtol=1e-7, atol=1e-12)
