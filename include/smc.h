@@ -160,6 +160,26 @@ int smc_sir_reduce_partials(const smc_sir_desc *d, double *out_dev, void *stream
 int smc_sir_resample(const smc_sir_desc *d, uint64_t cdf_offset_fix, double *stats_row_dev,
                      void *const *peer_x_dev, int32_t n_shards, void *stream);
 
+/* Sharded form of smc_sir_resample: the CDF offset of this shard is the sum of the lower
+ * ranks' entries of totals_dev (n_shards uint64 values, the all-gathered results of
+ * smc_sir_shard_weight_total), read on the device so that no host synchronisation is needed.
+ * peer_x_dev: device array of 2*n_shards pointers [buffer 0 of every rank][buffer 1 of every
+ * rank] (peer-mapped, see smc_ipc_*); every output is stored straight into the buffer of the
+ * rank that owns its index (NVLink P2P stores) -- the gather and the cross-shard migration are
+ * one kernel. */
+int smc_sir_resample_sharded(const smc_sir_desc *d, const uint64_t *totals_dev, int32_t rank,
+                             int32_t n_shards, void *const *peer_x_dev, void *stream);
+/* Fold this shard's per-tile post-resample moment partials into one record
+ * (nx + nx(nx+1)/2 doubles) at out_dev, to be all-gathered and passed to smc_sir_finish_step. */
+int smc_sir_reduce_moment_partials(const smc_sir_desc *d, double *out_dev, void *stream);
+
+/* Raw device allocations that can be shared between the ranks of one node (CUDA IPC). */
+int smc_dev_alloc(uint64_t bytes, void **ptr_out);
+int smc_dev_free(void *ptr);
+int smc_ipc_export(void *ptr, unsigned char handle_out[64]);
+int smc_ipc_import(const unsigned char handle[64], void **ptr_out);
+int smc_ipc_close(void *ptr);
+
 /* Fixed-point total of this shard's normalised weights (index units * 2^32),
  * written to total_dev (one uint64); input to the cross-shard exclusive scan. */
 int smc_sir_shard_weight_total(const smc_sir_desc *d, uint64_t *total_dev, void *stream);

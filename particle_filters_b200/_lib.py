@@ -68,6 +68,13 @@ _SIG = {
     "smc_sir_reduce_partials": (C.c_int, [C.POINTER(SirDesc), _P, _P]),
     "smc_sir_resample": (C.c_int, [C.POINTER(SirDesc), C.c_uint64, _P, _P, C.c_int32, _P]),
     "smc_sir_shard_weight_total": (C.c_int, [C.POINTER(SirDesc), _P, _P]),
+    "smc_sir_resample_sharded": (C.c_int, [C.POINTER(SirDesc), _P, C.c_int32, C.c_int32, _P, _P]),
+    "smc_sir_reduce_moment_partials": (C.c_int, [C.POINTER(SirDesc), _P, _P]),
+    "smc_dev_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "smc_dev_free": (C.c_int, [_P]),
+    "smc_ipc_export": (C.c_int, [_P, C.c_char_p]),
+    "smc_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "smc_ipc_close": (C.c_int, [_P]),
     "smc_sir_finish_step": (C.c_int, [C.POINTER(SirDesc), _P, _P, C.c_int32, _P]),
     "smc_sir_step": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _D, C.c_int32, _P, _P, C.c_double,
                                C.c_double, C.c_uint64, C.c_int64, _P, _P]),

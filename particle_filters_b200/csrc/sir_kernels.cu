@@ -483,6 +483,8 @@ template <typename real> struct K3Args {
     unsigned int* ticket;
     double* mom_parts;          // nullable
     unsigned long long cdf_offset;
+    const unsigned long long* totals;   // nullable: per-shard weight totals (offset = sum over lower ranks)
+    int32_t rank;
     int64_t n, n_global, offset, ld, shard_n;
     int32_t force;              // ignore ctrl->do_resample (stand-alone use)
 };
@@ -735,8 +737,10 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
         volatile unsigned long long* words = reinterpret_cast<volatile unsigned long long*>(a.state + tile);
         if (tile == 0) {
             if (lane == 0) {
-                words[1] = kValidBit | (a.cdf_offset + tile_agg);
-                s_prefix = a.cdf_offset;
+                unsigned long long off = a.cdf_offset;
+                if (a.totals) for (int r = 0; r < a.rank; ++r) off += a.totals[r];
+                words[1] = kValidBit | (off + tile_agg);
+                s_prefix = off;
             }
         } else {
             if (lane == 0) words[0] = kValidBit | tile_agg;
@@ -920,6 +924,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_shard_total(const Ctrl* ctrl, const real* logw, int64_t n,
                                                           int64_t n_global, unsigned long long* total) {
+    if (!ctrl->do_resample) return;
     // same quantisation as k3_resample: one thread owns IPT consecutive items and quantises
     // its running sum, so the shard total equals the last inclusive prefix K3 will compute
     constexpr int IPT = K3Geom<real>::IPT;
@@ -985,6 +990,19 @@ __global__ void __launch_bounds__(kThreads) k_finish_step(Ctrl* ctrl, double* st
         if (do_res) { ctrl->cur ^= 1; ctrl->uniform = 1; }
         if (stats && !no_moments)
             for (int d = 0; d < nx && d < kMaxNx; ++d) ctrl->shift[d] = stats[SMC_STATS_HEADER + d];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_reduce_moment_partials(const Ctrl* ctrl, const double* mom_parts,
+                                                                     int n_parts, int nm, double* out) {
+    __shared__ double s_tmp[kWarps];
+    const bool live = ctrl->do_resample != 0;
+    for (int k = 0; k < nm; ++k) {
+        double acc = 0;
+        if (live)
+            for (int p = threadIdx.x; p < n_parts; p += kThreads) acc += mom_parts[(int64_t)p * nm + k];
+        const double tot = block_sum_256(acc, s_tmp);
+        if (threadIdx.x == 0) out[k] = tot;
     }
 }
 
@@ -1306,7 +1324,8 @@ int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
 
 template <typename real>
 int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
-              void* const* peer, int n_shards, bool want_moments) {
+              void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
+              int rank = 0) {
     const smc_sir_desc* d = l.d;
     // clear tile state + ticket (contiguous in the layout)
     SMC_CHECK_CUDA(cudaMemsetAsync(l.ws + l.L.tile_agg, 0, l.L.mom_parts - l.L.tile_agg, l.st));
@@ -1326,6 +1345,7 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
     a.state = reinterpret_cast<ulonglong2*>(l.agg()); a.ticket = l.ticket();
     a.mom_parts = want_moments ? l.mom_parts() : nullptr;
     a.cdf_offset = cdf_offset;
+    a.totals = totals; a.rank = rank;
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
     a.shard_n = n_shards > 0 ? d->n_global / n_shards : d->n_global;
     a.force = force;
@@ -1526,6 +1546,61 @@ int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* sta
                                                               d->n, d->ld, d->nx);
         SMC_CHECK_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+int smc_sir_resample_sharded(const smc_sir_desc* d, const uint64_t* totals_dev, int32_t rank, int32_t n_shards,
+                             void* const* peer_x_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(d->nx <= kFusedNxMax, "smc: sharded resampling requires nx <= %d", kFusedNxMax);
+    SMC_REQUIRE(n_shards > 0 && rank >= 0 && rank < n_shards && d->n_global % n_shards == 0 &&
+                    d->n == d->n_global / n_shards && d->offset == (int64_t)rank * d->n,
+                "smc: inconsistent shard geometry (rank %d of %d)", rank, n_shards);
+    SMC_REQUIRE(totals_dev && peer_x_dev, "smc: totals / peer table missing");
+    const bool want_m = inline_moments(d) && !(d->flags & SMC_FLAG_NO_MOMENTS);
+    return d->dtype == SMC_F32
+               ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, peer_x_dev, n_shards, want_m,
+                                  (const unsigned long long*)totals_dev, rank)
+               : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, peer_x_dev, n_shards, want_m,
+                                   (const unsigned long long*)totals_dev, rank);
+}
+
+int smc_sir_reduce_moment_partials(const smc_sir_desc* d, double* out_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(inline_moments(d), "smc: moment partials exist only for nx <= %d", kFusedNxMax);
+    k_reduce_moment_partials<<<1, kThreads, 0, l.st>>>(l.ctrl(), l.mom_parts(), (int)l.L.n_tiles, moment_stride(d->nx),
+                                                      out_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_dev_alloc(uint64_t bytes, void** ptr_out) {
+    SMC_REQUIRE(ptr_out, "smc_dev_alloc: null out pointer");
+    SMC_CHECK_CUDA(cudaMalloc(ptr_out, bytes));
+    SMC_CHECK_CUDA(cudaMemset(*ptr_out, 0, bytes));
+    return 0;
+}
+int smc_dev_free(void* ptr) {
+    SMC_CHECK_CUDA(cudaFree(ptr));
+    return 0;
+}
+int smc_ipc_export(void* ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SMC_CHECK_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int smc_ipc_import(const unsigned char handle[64], void** ptr_out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SMC_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int smc_ipc_close(void* ptr) {
+    SMC_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
     return 0;
 }
 

@@ -38,7 +38,8 @@ class SirEngine:
 
     def __init__(self, n: int, nx: int, nz: int, *, dtype: str = "f32", device=None,
                  n_global: Optional[int] = None, offset: int = 0, write_ancestors: bool = False,
-                 generic_moments: bool = False, post_moments_generic: bool = False, trace_len: int = 1):
+                 generic_moments: bool = False, post_moments_generic: bool = False, trace_len: int = 1,
+                 x_buffers=None):
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
@@ -52,7 +53,11 @@ class SirEngine:
         self.ld = _round4(self.n)
         self.generic_moments = bool(generic_moments) or self.nx > 4
         with torch.cuda.device(self.device):
-            self.x = [torch.zeros((self.nx, self.ld), dtype=self.tdtype, device=self.device) for _ in range(2)]
+            if x_buffers is not None:      # caller-owned (e.g. IPC-shareable) ping-pong buffers
+                self.x = list(x_buffers)
+                assert all(tuple(b.shape) == (self.nx, self.ld) and b.dtype == self.tdtype for b in self.x)
+            else:
+                self.x = [torch.zeros((self.nx, self.ld), dtype=self.tdtype, device=self.device) for _ in range(2)]
             self.logw = torch.zeros((self.ld,), dtype=self.tdtype, device=self.device)
             need_anc = write_ancestors or self.nx > 4
             self.ancestors = (torch.zeros((self.ld,), dtype=torch.int32, device=self.device)

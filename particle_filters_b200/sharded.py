@@ -1,0 +1,281 @@
+"""Sharded SIR filter: one process per GPU, particles split into contiguous shards.
+
+SURVEY.md section 8e.  Per step every rank runs the fused propagate+likelihood kernel on
+its shard (Philox is keyed by the GLOBAL particle id), then
+
+1. all-gather of ONE partial record per rank (max, sum e, sum e^2, weighted moments);
+   every rank reduces the G records in rank order -> identical log normaliser, ESS,
+   resampling decision and systematic uniform everywhere;
+2. all-gather of the shards' fixed-point weight totals (uint64); the exclusive prefix of
+   the lower ranks is this shard's CDF offset (integer arithmetic: the global CDF is
+   bit-identical to the single-GPU one);
+3. the resampling kernel stores every output particle straight into the buffer of the
+   rank that owns its index over NVLink (peer pointers obtained through CUDA IPC), so the
+   gather and the cross-shard ancestor migration are one kernel -- only particles whose
+   ancestor lives on another shard cross the link;
+4. all-gather of the post-resample moment record, which doubles as the barrier that orders
+   the peer stores before the next step.
+
+No host synchronisation happens inside the step loop.  The pure-host helpers at the top
+(`combine_partial_records`, `shard_offsets`, `migration_plan`) restate the device
+arithmetic for the CPU (gloo) tests of the multi-rank logic.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import List
+
+import numpy as np
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side restatement of the cross-rank arithmetic (used by tests under gloo, and for planning)
+# ------------------------------------------------------------------------------------------------
+def combine_partial_records(records: np.ndarray) -> np.ndarray:
+    """Combine (max, sum e, sum e^2, moments...) records exactly like ``combine_partials``
+    in csrc/sir_kernels.cu: common max, sums rescaled by exp(m_r - M) (squared for slot 2),
+    accumulated in rank order."""
+    rec = np.asarray(records, dtype=np.float64)
+    M = np.max(rec[:, 0])
+    Mref = 0.0 if np.isneginf(M) else M
+    out = np.zeros(rec.shape[1])
+    out[0] = M
+    for r in range(rec.shape[0]):
+        sc = np.exp(rec[r, 0] - Mref) if not np.isneginf(rec[r, 0]) else 0.0
+        for k in range(1, rec.shape[1]):
+            out[k] += rec[r, k] * (sc * sc if k == 2 else sc)
+    return out
+
+
+def frac_bits_for(n_global: int) -> int:
+    lg = 0
+    while (1 << lg) < n_global:
+        lg += 1
+    return min(60, max(32, 62 - lg))
+
+
+def shard_offsets(totals: List[int]) -> List[int]:
+    """Exclusive prefix of the shards' fixed-point weight totals (rank order)."""
+    out, acc = [], 0
+    for t in totals:
+        out.append(acc)
+        acc += int(t)
+    return out
+
+
+def outputs_below(C_fix: int, u: float, n_global: int) -> int:
+    """Number of stratified positions (u + i) / N below the fixed-point CDF value C (away from
+    round-off ties this equals the device's closed form)."""
+    F = frac_bits_for(n_global)
+    uq = int(np.floor(np.ldexp(u, F)))
+    e = (C_fix + ((1 << F) - 1 - uq)) >> F
+    return int(min(max(e, 0), n_global))
+
+
+def migration_plan(totals: List[int], u: float, n_global: int) -> np.ndarray:
+    """``plan[src, dst]`` = number of output particles whose ancestor lives on shard ``src``
+    and whose index belongs to shard ``dst`` (what an alltoallv would have to move)."""
+    G = len(totals)
+    shard = n_global // G
+    off = shard_offsets(totals) + [sum(int(t) for t in totals)]
+    plan = np.zeros((G, G), dtype=np.int64)
+    for s in range(G):
+        lo = outputs_below(off[s], u, n_global)
+        hi = n_global if s == G - 1 else outputs_below(off[s + 1], u, n_global)
+        for d in range(G):
+            a, b = max(lo, d * shard), min(hi, (d + 1) * shard)
+            plan[s, d] = max(0, b - a)
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# device side
+# ------------------------------------------------------------------------------------------------
+class _RawCuda:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class ShardedSir:
+    """One rank of a G-way sharded SIR filter (torch.distributed must be initialised, NCCL)."""
+
+    def __init__(self, n_global: int, nx: int, nz: int, *, dtype: str = "f32", trace_len: int = 1):
+        import torch
+        import torch.distributed as dist
+
+        from .engine import SirEngine, _round4
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.G = dist.get_rank(), dist.get_world_size()
+        assert n_global % self.G == 0 and (n_global // self.G) % 4096 == 0, \
+            "shards must be equal and tile aligned (multiple of 4096 particles)"
+        self.n = n_global // self.G
+        self.lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # particle buffers from raw cudaMalloc so that they can be exported through CUDA IPC
+        elt = 4 if dtype == "f32" else 8
+        ld = _round4(self.n)
+        self._raw = []
+        for _ in range(2):
+            p = C.c_void_p()
+            _lib.check(self.lib.smc_dev_alloc(C.c_uint64(nx * ld * elt), C.byref(p)))
+            self._raw.append(p.value)
+        typestr = "<f4" if dtype == "f32" else "<f8"
+        xbufs = [torch.as_tensor(_RawCuda(p, (nx, ld), typestr), device=dev) for p in self._raw]
+        self.eng = SirEngine(self.n, nx, nz, dtype=dtype, n_global=n_global, offset=self.rank * self.n,
+                             trace_len=trace_len, x_buffers=xbufs)
+        # exchange IPC handles; table = [buffer 0 of every rank][buffer 1 of every rank]
+        mine = []
+        for p in self._raw:
+            h = C.create_string_buffer(64)
+            _lib.check(self.lib.smc_ipc_export(C.c_void_p(p), h))
+            mine.append(bytes(h.raw))
+        allh = [None] * self.G
+        dist.all_gather_object(allh, mine)
+        table = np.zeros(2 * self.G, dtype=np.int64)
+        self._opened = []
+        for r in range(self.G):
+            for b in range(2):
+                if r == self.rank:
+                    table[b * self.G + r] = self._raw[b]
+                else:
+                    q = C.c_void_p()
+                    _lib.check(self.lib.smc_ipc_import(allh[r][b], C.byref(q)))
+                    self._opened.append(q.value)
+                    table[b * self.G + r] = q.value
+        self.peer_table = torch.from_numpy(table).to(dev)
+        ps = int(self.lib.smc_partial_stride(nx))
+        nm = nx + nx * (nx + 1) // 2
+        self.rec_local = torch.zeros(ps, dtype=torch.float64, device=dev)
+        self.rec_all = torch.zeros(self.G * ps, dtype=torch.float64, device=dev)
+        self.tot_local = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.tot_all = torch.zeros(self.G, dtype=torch.int64, device=dev)
+        self.mom_local = torch.zeros(nm, dtype=torch.float64, device=dev)
+        self.mom_all = torch.zeros(self.G * nm, dtype=torch.float64, device=dev)
+        dist.barrier()
+
+    def step(self, model_id, params, thresh, z_index, seed, t, row):
+        eng, lib, dist = self.eng, self.lib, self.dist
+        eng.propagate_weight(model_id, params, _lib.SMC_MODE_STEP, z_index=z_index, seed=seed, t=t)
+        _lib.check(lib.smc_sir_reduce_partials(eng._d, C.c_void_p(self.rec_local.data_ptr()), eng.stream))
+        dist.all_gather_into_tensor(self.rec_all, self.rec_local)
+        eng.finalize(thresh, u=-1.0, seed=seed, t=t, row=row, parts=self.rec_all, n_parts=self.G)
+        _lib.check(lib.smc_sir_shard_weight_total(eng._d, C.c_void_p(self.tot_local.data_ptr()), eng.stream))
+        dist.all_gather_into_tensor(self.tot_all, self.tot_local)
+        _lib.check(lib.smc_sir_resample_sharded(eng._d, C.c_void_p(self.tot_all.data_ptr()), self.rank, self.G,
+                                                C.c_void_p(self.peer_table.data_ptr()), eng.stream))
+        _lib.check(lib.smc_sir_reduce_moment_partials(eng._d, C.c_void_p(self.mom_local.data_ptr()), eng.stream))
+        dist.all_gather_into_tensor(self.mom_all, self.mom_local)     # also orders the peer stores
+        eng.finish_step(row=row, mom_parts=self.mom_all, n_mom_parts=self.G)
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+        for q in self._opened:
+            self.lib.smc_ipc_close(C.c_void_p(q))
+        self.dist.barrier()
+        for p in self._raw:
+            self.lib.smc_dev_free(C.c_void_p(p))
+
+
+def init_distributed():
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return dist
+
+
+def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC, UNIT):
+    """bench.py's N > 1 arm: BASELINE config 3 (SV, N = 2^26 total) sharded over the ranks."""
+    import torch
+
+    from .ssm import StochVolSSM
+
+    dist = init_distributed()
+    rank, G = dist.get_rank(), dist.get_world_size()
+    N = 1 << args.log2n
+    K, W = args.steps, max(3, args.warmup)
+    ALPHA, SIGMA, BETA = 0.95, 0.2, 1.0
+    Q, R = np.array([[SIGMA ** 2]]), np.array([[BETA ** 2]])
+    mid, params = StochVolSSM(ALPHA, BETA).device_functor(Q, R)
+    Y = sv_observations(W + K + 2)
+    sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=W + K + 2)
+    sh.eng.init_gaussian(np.zeros(1), np.array([[SIGMA / np.sqrt(1 - ALPHA ** 2)]]), 42)
+    sh.eng.set_observations(Y.reshape(-1, 1))
+    thresh, seed = 2.0, 42
+    for k in range(W):
+        sh.step(mid, params, thresh, k, seed, k, k)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)           # let the sampler take its first reading before the timed region
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + K):
+        sh.step(mid, params, thresh, k, seed, k, k)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / K
+    # end to end: host observation in, host moments out, every step, through the same engine
+    Ke = max(3, min(K, 20))
+    zpin = torch.zeros(1, dtype=torch.float64).pin_memory()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        zpin[0] = float(Y[k])
+        sh.eng.zbuf[0].copy_(zpin, non_blocking=True)
+        sh.step(mid, params, thresh, 0, seed, 1000 + k, 0)
+        _ = sh.eng.read_row(0)[4]
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    rows = sh.eng.trace[: W + K].cpu().numpy()
+    clk = clocks.stop() if rank == 0 else None
+    ok = bool(np.all(np.isfinite(rows[:, :5])) and np.all(rows[W:, 2] == 1.0))
+    peak, peak_src = measured_peak()
+    value = N / (ms_step * 1e-3)
+    if rank == 0:
+        assert ok, "non-finite statistics in the sharded run"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SV SIR bootstrap filter N=2^{args.log2n} total, {G} shards of {N // G}, "
+                                   "systematic resampling every step with cross-shard migration "
+                                   "(BASELINE.json configs[2])",
+                       "n_particles": N, "nx": 1, "nz": 1, "parallelism": f"particle-sharded x{G}",
+                       "l2": "per-step working set 3 x N/G x 4 B; no flush (strong scaling shrinks it)"},
+            "clocks": clk,
+            "e2e": {"value": N / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": 8,
+                    "d2h_bytes_per_step": 8 * int(sh.eng.stride), "ms_per_step": float(e2e_dt.item()) * 1e3},
+            "gpu_launches": 7 * K,
+            "roofline": {"bound": "hbm", "kernel": "whole step (per-kernel split is taken at N=1)",
+                         "achieved": 24.0 * value / 1e9 / G, "peak": peak, "unit": "GB/s",
+                         "frac": 24.0 * value / 1e9 / G / peak, "traffic": None, "peak_source": peak_src},
+            "roofline_step": {"alg_bytes_per_particle_update": 32.0, "achieved": 32.0 * value / 1e9,
+                              "peak": peak * G, "unit": "GB/s", "frac": 32.0 * value / 1e9 / (peak * G)},
+            "cpu_baseline": None,
+            "filter": {"mean_last": float(rows[-1, 4]), "ess_last": float(rows[-1, 1])},
+        }
+        print(json.dumps(line))
+    sh.close()
+    dist.destroy_process_group()
