@@ -239,7 +239,8 @@ def run_gpu_arm(args):
     for k in range(W + K, W + K + 2):   # two extra steps reuse trace rows via modulo
         evs = [ev() for _ in range(5)]
         evs[0].record()
-        _lib.check(eng.lib.smc_sir_propagate_weight(eng._d, mid, pp, kp.size, _lib.SMC_MODE_STEP, eng._zptr(k % (W + K)),
+        # same K1 variant as smc_sir_step uses when every step resamples (mode bit 4)
+        _lib.check(eng.lib.smc_sir_propagate_weight(eng._d, mid, pp, kp.size, _lib.SMC_MODE_STEP | 4, eng._zptr(k % (W + K)),
                                                     None, C.c_uint64(seed), k, eng.stream))
         evs[1].record()
         eng.finalize(thresh, u=-1.0, seed=seed, t=k, row=k)

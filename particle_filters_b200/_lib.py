@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libsmc.so")
+LIB_PATH = os.environ.get("SMC_LIB_PATH", os.path.join(HERE, "_lib", "libsmc.so"))   # override: kernel tuning sweeps
 
 SMC_ABI_VERSION = 1
 SMC_F32, SMC_F64 = 0, 1

@@ -31,9 +31,11 @@ template <typename real> struct StochVolModel {
         x[0] = fma(lq, nrm[0], alpha * x[0]);
     }
     __device__ inline real loglik(const real (&x)[1], const real (&z)[1]) const {
-        real d = (z[0] - beta * fast_exp(real(0.5) * x[0])) * rinv;
+        real d = (z[0] - beta * half_exp(x[0])) * rinv;
         return real(-0.5) * d * d;
     }
+    static __device__ inline float half_exp(float x) { return ex2_approx(x * 0.7213475204444817f); }   // exp(x/2)
+    static __device__ inline double half_exp(double x) { return exp(0.5 * x); }
 };
 
 template <typename real, int NX_, int NZ_> struct LinGaussModel {
@@ -133,8 +135,118 @@ __device__ inline double prev_logweight(double lw_old, double log_norm) {
     return log(exp(lw_old - log_norm) + 1e-300);
 }
 
-template <typename real, class Model>
-__global__ void __launch_bounds__(kThreads) k1_propagate_weight(K1Args<real> a, Model m) {
+// One 4096-particle chunk of K1.  CHECK = the chunk may run past n (last chunk only);
+// MOM = accumulate the weighted moments (not needed when the step is known to resample,
+// because then the post-resample moments come from K3).
+template <typename real, class Model, bool CHECK, bool MOM, int NR>
+__device__ __forceinline__ void k1_chunk(const K1Args<real>& a, const Model& m, real* x, int64_t blk_base, int tid,
+                                         bool uniform, real log_norm_prev, real lw_uniform, bool do_prop, bool do_w,
+                                         const real (&z)[Model::NZ], const real (&shift)[Model::NX], real& tm,
+                                         real (&acc)[NR]) {
+    constexpr int NX = Model::NX;
+    const real NEG_INF = -INFINITY;
+    real xs[kK1Quads][NX][4];
+    real lw[kK1Quads][4];
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q) {
+        const int64_t i0 = blk_base + (int64_t)(q * kThreads + tid) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lw[q][j] = NEG_INF;
+        if (!CHECK || i0 < a.n) {
+#pragma unroll
+            for (int d = 0; d < NX; ++d) load4<real>(x + d * a.ld + i0, xs[q][d]);
+            if (do_prop) {
+                real nrm[NX][4];
+                if (a.noise) {
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
+                } else {
+                    Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    real xv[NX], nv[NX];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) { xv[d] = xs[q][d][j]; nv[d] = nrm[d][j]; }
+                    m.propagate(xv, nv);
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xs[q][d][j] = xv[d];
+                }
+#pragma unroll
+                for (int d = 0; d < NX; ++d) store4<real>(x + d * a.ld + i0, xs[q][d]);
+            }
+            if (do_w) {
+                real prev[4];
+                if (uniform) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prev[j] = lw_uniform;
+                } else {
+                    load4<real>(a.logw + i0, prev);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prev[j] = prev_logweight(prev[j], log_norm_prev);
+                }
+                real out[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    real xv[NX];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xv[d] = xs[q][d][j];
+                    real v = prev[j] + m.loglik(xv, z);
+                    if (CHECK && (i0 + j) >= a.n) v = NEG_INF;
+                    v = fmax(v, NEG_INF);                 // NaN -> -inf (counts as zero weight)
+                    out[j] = v;
+                    lw[q][j] = v;
+                }
+                store4<real>(a.logw + i0, out);
+            }
+        } else if (MOM) {
+#pragma unroll
+            for (int d = 0; d < NX; ++d)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xs[q][d][j] = 0;
+        }
+    }
+    if (!do_w) return;
+    // ---- fold this chunk into the thread's running (max, sums) ------------------------------
+    real cmax = NEG_INF;
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cmax = fmax(cmax, lw[q][j]);
+    if (cmax > tm) {
+        const real sc = fast_exp(tm - cmax);          // tm = -inf -> 0
+        acc[0] *= sc;
+        acc[1] *= sc * sc;
+#pragma unroll
+        for (int k = 2; k < NR; ++k) acc[k] *= sc;
+        tm = cmax;
+    }
+    if (tm == NEG_INF) return;                         // nothing but zero weights so far
+#pragma unroll
+    for (int q = 0; q < kK1Quads; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const real e = fast_exp(lw[q][j] - tm);    // exp(-inf) = 0 for padding / zero weights
+            acc[0] += e;
+            acc[1] = fma(e, e, acc[1]);
+            if (MOM) {
+                real xc[NX];   // padding lanes hold finite values (zero-filled buffers) and e = 0
+#pragma unroll
+                for (int d = 0; d < NX; ++d) xc[d] = xs[q][d][j] - shift[d];
+                int k = 2;
+#pragma unroll
+                for (int d = 0; d < NX; ++d) { acc[k] = fma(e, xc[d], acc[k]); ++k; }
+#pragma unroll
+                for (int d = 0; d < NX; ++d)
+#pragma unroll
+                    for (int d2 = 0; d2 <= d; ++d2) { acc[k] = fma(e * xc[d], xc[d2], acc[k]); ++k; }
+            }
+        }
+}
+
+template <typename real, class Model, bool MOM>
+__global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && Model::NX <= 2) ? 4 : 2)
+k1_propagate_weight(K1Args<real> a, Model m) {
     constexpr int NX = Model::NX, NZ = Model::NZ;
     constexpr int NM = NX + NX * (NX + 1) / 2;   // moment accumulators
     constexpr int NR = 2 + NM;                   // sum e, sum e^2, moments
@@ -165,95 +277,12 @@ __global__ void __launch_bounds__(kThreads) k1_propagate_weight(K1Args<real> a, 
     const int64_t n_chunks = cdiv64(a.n, kK1Block);
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int64_t blk_base = chunk * kK1Block;
-        real xs[kK1Quads][NX][4];
-        real lw[kK1Quads][4];
-#pragma unroll
-        for (int q = 0; q < kK1Quads; ++q) {
-            const int64_t i0 = blk_base + (int64_t)(q * kThreads + tid) * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) lw[q][j] = NEG_INF;
-            if (i0 < a.n) {
-#pragma unroll
-                for (int d = 0; d < NX; ++d) load4<real>(x + d * a.ld + i0, xs[q][d]);
-                if (do_prop) {
-                    real nrm[NX][4];
-                    if (a.noise) {
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
-                    } else {
-                        Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        real xv[NX], nv[NX];
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) { xv[d] = xs[q][d][j]; nv[d] = nrm[d][j]; }
-                        m.propagate(xv, nv);
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) xs[q][d][j] = xv[d];
-                    }
-#pragma unroll
-                    for (int d = 0; d < NX; ++d) store4<real>(x + d * a.ld + i0, xs[q][d]);
-                }
-                if (do_w) {
-                    real prev[4];
-                    if (uniform) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) prev[j] = lw_uniform;
-                    } else {
-                        load4<real>(a.logw + i0, prev);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) prev[j] = prev_logweight(prev[j], log_norm_prev);
-                    }
-                    real out[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        real xv[NX];
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) xv[d] = xs[q][d][j];
-                        real v = prev[j] + m.loglik(xv, z);
-                        const bool valid = (i0 + j) < a.n;
-                        out[j] = valid ? v : NEG_INF;
-                        lw[q][j] = (valid && v == v) ? v : NEG_INF;   // NaN counts as zero weight
-                    }
-                    store4<real>(a.logw + i0, out);
-                }
-            }
-        }
-        if (!do_w) continue;
-        // ---- fold this chunk into the thread's running (max, sums) ------------------------------
-        real cmax = NEG_INF;
-#pragma unroll
-        for (int q = 0; q < kK1Quads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cmax = lw[q][j] > cmax ? lw[q][j] : cmax;
-        if (cmax > tm) {
-            const real sc = fast_exp(tm - cmax);          // tm = -inf -> 0
-            acc[0] *= sc;
-            acc[1] *= sc * sc;
-#pragma unroll
-            for (int k = 2; k < NR; ++k) acc[k] *= sc;
-            tm = cmax;
-        }
-        if (tm == NEG_INF) continue;                       // nothing but zero weights so far
-#pragma unroll
-        for (int q = 0; q < kK1Quads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const real e = fast_exp(lw[q][j] - tm);    // exp(-inf) = 0 for padding / zero weights
-                acc[0] += e;
-                acc[1] = fma(e, e, acc[1]);
-                real xc[NX];
-#pragma unroll
-                for (int d = 0; d < NX; ++d) xc[d] = (lw[q][j] == NEG_INF) ? real(0) : xs[q][d][j] - shift[d];
-                int k = 2;
-#pragma unroll
-                for (int d = 0; d < NX; ++d) { acc[k] = fma(e, xc[d], acc[k]); ++k; }
-#pragma unroll
-                for (int d = 0; d < NX; ++d)
-#pragma unroll
-                    for (int d2 = 0; d2 <= d; ++d2) { acc[k] = fma(e * xc[d], xc[d2], acc[k]); ++k; }
-            }
+        if (blk_base + kK1Block <= a.n)
+            k1_chunk<real, Model, false, MOM, NR>(a, m, x, blk_base, tid, uniform, log_norm_prev, lw_uniform, do_prop,
+                                                  do_w, z, shift, tm, acc);
+        else
+            k1_chunk<real, Model, true, MOM, NR>(a, m, x, blk_base, tid, uniform, log_norm_prev, lw_uniform, do_prop,
+                                                 do_w, z, shift, tm, acc);
     }
     if (!do_w) return;
 
@@ -479,8 +508,7 @@ template <typename real> struct K3Args {
     real* const* peer0;         // nullable: per-shard destination pointers (cur == 1 / cur == 0)
     real* const* peer1;
     int32_t* ancestors;         // nullable
-    ulonglong2* state;          // per-tile {aggregate, inclusive prefix} words
-    unsigned int* ticket;
+    const ulonglong2* state;    // per-tile {total, exclusive prefix} from the pre-pass
     double* mom_parts;          // nullable
     unsigned long long cdf_offset;
     const unsigned long long* totals;   // nullable: per-shard weight totals (offset = sum over lower ranks)
@@ -489,13 +517,17 @@ template <typename real> struct K3Args {
     int32_t force;              // ignore ctrl->do_resample (stand-alone use)
 };
 
+// Tile geometry: THREADS threads own IPT consecutive items each (fp32: 256 x 16 = 4096-particle
+// tiles, fp64: 256 x 8); every shared/global access moves 16-byte units of EPU items.
+// Measured on B200 at N = 2^26 (resampler + pre-pass, ms): 128 x 16 -> 0.347, 256 x 16 -> 0.336,
+// 512 x 16 -> 0.368, 512 x 8 (3 CTAs/SM, spilling) -> 0.423.
 template <typename real> struct K3Geom;
 template <> struct K3Geom<float> {
-    static constexpr int IPT = 16, EPU = 4;
+    static constexpr int THREADS = 256, IPT = 16, EPU = 4;
     using unit = float4;
 };
 template <> struct K3Geom<double> {
-    static constexpr int IPT = 8, EPU = 2;
+    static constexpr int THREADS = 256, IPT = 8, EPU = 2;
     using unit = double2;
 };
 
@@ -503,70 +535,39 @@ __device__ inline void unit_to_array(const float4& u, float* v) { v[0] = u.x; v[
 __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; v[1] = u.y; }
 
 
-// Decoupled look-back over tile state records (integer sums -> order independent).
-// One 16-byte record per tile: .x = aggregate word, .y = inclusive-prefix word, bit 63 = valid.
-// Each lane inspects kLookPerLane predecessors per round with independent 128-bit loads, so one
-// L2 round trip covers a window of 32 * kLookPerLane tiles.
-constexpr int kLookPerLane = 4;
-__device__ inline ulonglong2 ld_tile_state(const ulonglong2* p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
-    return v;
-}
-__device__ inline unsigned long long lookback(const ulonglong2* state, int64_t tile, int lane) {
-    unsigned long long sum = 0;
-    int64_t p0 = tile - 1;                       // nearest predecessor of this round
-    while (true) {
-        // lane l looks at predecessors p0 - (l * kLookPerLane + q), q = 0..kLookPerLane-1 (nearest first)
-        ulonglong2 st[kLookPerLane];
-#pragma unroll
-        for (int q = 0; q < kLookPerLane; ++q) {
-            const int64_t p = p0 - (lane * kLookPerLane + q);
-            st[q] = p >= 0 ? ld_tile_state(state + p) : make_ulonglong2(0ull, kValidBit);   // before tile 0: prefix 0
-        }
-        // per lane: contribution of its run up to (and including) its first inclusive prefix
-        unsigned long long contrib = 0;
-        bool lane_has_incl = false, lane_missing = false;
-#pragma unroll
-        for (int q = 0; q < kLookPerLane; ++q) {
-            if (lane_has_incl || lane_missing) continue;
-            if (st[q].y & kValidBit) { contrib += st[q].y & ~kValidBit; lane_has_incl = true; }
-            else if (st[q].x & kValidBit) contrib += st[q].x & ~kValidBit;
-            else lane_missing = true;
-        }
-        const unsigned mask_i = __ballot_sync(0xffffffffu, lane_has_incl);
-        const unsigned mask_m = __ballot_sync(0xffffffffu, lane_missing);
-        const int first_i = mask_i ? (__ffs(mask_i) - 1) : 32;
-        const int first_m = mask_m ? (__ffs(mask_m) - 1) : 32;
-        // a lane sets at most one of the two flags; an unpublished tile nearer than the first
-        // inclusive prefix means the window is not complete yet: read it again
-        if (first_m < first_i) continue;
-        const unsigned long long take = (lane <= first_i) ? contrib : 0ull;
-        sum += warp_sum(take);
-        if (first_i < 32) break;
-        p0 -= 32 * kLookPerLane;
-    }
-    return sum;
-}
-
 // Per-item quantisation of the weights.
 //  fp32 mode: each weight carries 24 significant bits, so it is converted on its own (one F2I);
 //  fp64 mode (parity): the thread's fp64 running sum is quantised instead, so the round-off of
 //  2^-F index units does not accumulate over a run of tiny weights.
 template <typename real> struct Quant;
 template <> struct Quant<float> {
-    float fscale;
-    __device__ inline void init(int F) { fscale = __uint_as_float((127u + (uint32_t)F) << 23); }   // 2^F
+    float fscale, kshift;
+    __device__ inline void init(int F, double lw_ref) {
+        fscale = __uint_as_float((127u + (uint32_t)F) << 23);                 // 2^F
+        kshift = (float)((double)F - lw_ref * 1.4426950408889634);          // N w 2^F = 2^(lw log2e + kshift)
+    }
     __device__ inline unsigned long long add(unsigned long long run, float v, double&) const {
         return run + __float2ull_rn(v * fscale);
     }
+    // log-weight -> fixed point in one FFMA + FMNMX + MUFU.EX2 + F2I (NaN-free input, see K1)
+    __device__ inline unsigned long long add_logw(unsigned long long run, float lw, double&) const {
+        const float p = ex2_approx(fminf(fmaf(lw, 1.4426950408889634f, kshift), 62.5f));
+        unsigned long long q;
+        asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
+        return run + q;
+    }
 };
 template <> struct Quant<double> {
-    double fscale, nmax;
-    __device__ inline void init(int F) { fscale = ldexp(1.0, F); }
+    double fscale, lw_ref, nmax;
+    __device__ inline void init(int F, double lw_ref_) { fscale = ldexp(1.0, F); lw_ref = lw_ref_; nmax = ldexp(1.0, 62 - F); }
     __device__ inline unsigned long long add(unsigned long long, double v, double& runf) const {
         runf += v;
         return __double2ull_rn(runf * fscale);
+    }
+    __device__ inline unsigned long long add_logw(unsigned long long run, double lw, double& runf) const {
+        double v = exp(lw - lw_ref);
+        v = fmin(fmax(v, 0.0), nmax);                                        // NaN / negative -> 0
+        return add(run, v, runf);
     }
 };
 
@@ -593,35 +594,131 @@ __device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bia
     const uint32_t hi = (uint32_t)(Cb >> 32), lo = (uint32_t)Cb;
     uint32_t e = hi >> fs.sh;
     const uint32_t frac_hi = __funnelshift_r(lo, hi, fs.sh);    // bits [F-32, F) of Cb
-    e = e < fs.n_global ? e : fs.n_global;
     if (frac_hi + fs.m32 <= 2u * fs.m32)                         // near 0 or near 2^32 (wraps)
         e = exact_outputs_below(Cb - fs.bias, e, sp.u, sp.n_global, sp.F);
     return e;
 }
 
-template <typename real, int NXF, bool LINEAR_W>
-__global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 : 2) k3_resample(K3Args<real> a) {
+// ---- K3a: per-tile fixed-point weight totals, then an exclusive scan over the tiles ------------
+// The tile prefixes are produced by a light streaming pre-pass (one extra read of the log-weights)
+// instead of an in-kernel decoupled look-back: the resampling CTAs then have no inter-tile
+// dependency at all, which removes the ticket, the spin on predecessor state and the barrier
+// stalls behind them (profiles/: 40 % of K3's stall samples sat behind the look-back barrier).
+// tile record: .x = tile total, .y = exclusive prefix (both in 2^-F index units).
+template <typename real, bool LINEAR_W>
+__global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_tile_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
+                                                             int64_t n_global, ulonglong2* tiles, int force) {
     using G = K3Geom<real>;
     using unit = typename G::unit;
+    constexpr int kK3Threads = G::THREADS, kK3Warps = kK3Threads / 32;
+    constexpr int IPT = G::IPT, EPU = G::EPU, UPT = IPT / EPU, TILE = kK3Threads * IPT;
+    __shared__ unsigned long long s_tot[kK3Warps];
+    if (!force && !ctrl->do_resample) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile_base = (int64_t)blockIdx.x * TILE;
+    Quant<real> quant;
+    quant.init(ctrl->frac_bits, LINEAR_W ? 0.0 : ctrl->lw_ref);
+    const real n_real = (real)n_global;
+    const int n_in_tile = tile_base + TILE <= n ? TILE : (int)(n - tile_base);
+    const unit* wtile = reinterpret_cast<const unit*>(wsrc + tile_base);
+    unsigned long long run = 0;
+    double runf = 0.0;
+    // fp32: weights are quantised one by one, so any (coalesced) assignment gives the same total;
+    // fp64: the thread's running sum is quantised, so the thread must own the same IPT consecutive
+    //       items as in k3_resample (blocked assignment)
+#pragma unroll
+    for (int r = 0; r < UPT; ++r) {
+        const int f = (sizeof(real) == 4) ? (r * kK3Threads + tid) : (UPT * tid + r);
+        real tmp[EPU];
+        const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+#pragma unroll
+        for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+        if (f * EPU < n_in_tile) {
+            unit_to_array(wtile[f], tmp);
+#pragma unroll
+            for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
+        }
+#pragma unroll
+        for (int j = 0; j < EPU; ++j) {
+            if (LINEAR_W) {
+                real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);
+                run = quant.add(run, v, runf);
+            } else {
+                run = quant.add_logw(run, tmp[j], runf);
+            }
+        }
+    }
+    run = warp_sum(run);
+    if (lane == 0) s_tot[warp] = run;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kK3Warps; ++w) t += s_tot[w];
+        tiles[blockIdx.x].x = t;
+    }
+}
+
+// single-CTA exclusive scan of the tile totals (integer, exact); also emits the shard total
+__global__ void __launch_bounds__(1024) k3a_scan_tiles(const Ctrl* ctrl, ulonglong2* tiles, int64_t n_tiles,
+                                                      unsigned long long offset, unsigned long long* total_out,
+                                                      int force) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    if (!force && !ctrl->do_resample) { if (total_out && threadIdx.x == 0) *total_out = 0ull; return; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = offset;
+    __syncthreads();
+    for (int64_t base = 0; base < n_tiles; base += 1024) {
+        const int64_t i = base + tid;
+        const unsigned long long v = i < n_tiles ? tiles[i].x : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        unsigned long long wex = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long t = s_w[w];
+            if (w < warp) wex += t;
+            tot += t;
+        }
+        const unsigned long long carry = s_carry;
+        if (i < n_tiles) tiles[i].y = carry + wex + inc - v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (total_out && tid == 0) *total_out = s_carry - offset;
+}
+
+template <typename real, int NXF, bool LINEAR_W>
+__global__ void __launch_bounds__(K3Geom<real>::THREADS, (sizeof(real) == 4 && NXF <= 2) ? 4 : 2)
+k3_resample(K3Args<real> a) {
+    using G = K3Geom<real>;
+    using unit = typename G::unit;
+    constexpr int kK3Threads = G::THREADS, kK3Warps = kK3Threads / 32;
     constexpr int IPT = G::IPT, EPU = G::EPU;
-    constexpr int TILE = kThreads * IPT;
+    constexpr int TILE = kK3Threads * IPT;
     constexpr int UPT = IPT / EPU;                    // 16-byte units per thread (= 4)
     constexpr int CH = IPT + 2;                       // fill chunk per thread (even)
-    constexpr int W = kThreads * CH;                  // output window (tile + 12.5 % / 25 % slack)
+    constexpr int W = kK3Threads * CH;                  // output window (tile + 12.5 % / 25 % slack)
     constexpr int NM = NXF + NXF * (NXF + 1) / 2;
-    static_assert(UPT == 4, "layout assumes 4 x 16B units per thread");
+    static_assert(UPT == 2 || UPT == 4, "swizzle assumes 2 or 4 16-byte units per thread");
     static_assert(CH % 2 == 0, "fill chunk must be word aligned");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unit* lw_s = reinterpret_cast<unit*>(smem_raw);                       // TILE reals, swizzled
     unsigned short* out_s = reinterpret_cast<unsigned short*>(smem_raw);  // aliases lw_s (W * 2 B)
     real* x_s = reinterpret_cast<real*>(smem_raw + sizeof(real) * TILE);  // NXF * TILE reals
-    __shared__ unsigned long long s_warp_tot[kWarps];
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_warp_tot[kK3Warps];
     __shared__ uint32_t s_E[2];
-    __shared__ unsigned int s_tile;
-    __shared__ int s_wmax[kWarps];
-    __shared__ double s_mom[kWarps][NM > 0 ? NM : 1];
+    __shared__ int s_wmax[kK3Warps];
+    __shared__ double s_mom[kK3Warps][NM > 0 ? NM : 1];
 
     Ctrl* ctrl = a.ctrl;
     if (!a.force && !ctrl->do_resample) return;
@@ -631,9 +728,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
     real* const* peer = cur ? a.peer0 : a.peer1;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
+    const int64_t tile = blockIdx.x;
     const int64_t tile_base = tile * TILE;
 
     const SearchParams sp = load_search(ctrl, a.n_global);
@@ -643,9 +738,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
     fs.m32 = (uint32_t)(sp.margin >> fs.sh) + 2u;
     fs.n_global = (uint32_t)a.n_global;
     Quant<real> quant;
-    quant.init(sp.F);
-    // weight = exp(lw - log_norm) * N  =  exp(lw - (log_norm - log N))
-    const real lw_ref = LINEAR_W ? real(0) : (real)ctrl->lw_ref;
+    quant.init(sp.F, LINEAR_W ? 0.0 : ctrl->lw_ref);      // weight N w = exp(lw - (log_norm - log N))
     const real n_real = (real)a.n_global;
 
     // ---- phase A: coalesced loads -> shared ------------------------------------------------
@@ -656,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
     if (NXF > 0) {
 #pragma unroll
         for (int r = 0; r < UPT; ++r) {
-            const int f = r * kThreads + tid;
+            const int f = r * kK3Threads + tid;
             if (f * EPU < n_in_tile) {
 #pragma unroll
                 for (int d = 0; d < NXF; ++d) {
@@ -672,17 +765,17 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
         if (interior) {
             unit v[UPT];
 #pragma unroll
-            for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kThreads + tid];
+            for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kK3Threads + tid];
 #pragma unroll
             for (int r = 0; r < UPT; ++r) {
-                const int f = r * kThreads + tid;
-                lw_s[f ^ ((f >> 3) & 3)] = v[r];
+                const int f = r * kK3Threads + tid;
+                lw_s[f ^ ((f >> 3) & (UPT - 1))] = v[r];
             }
         } else {
             const real fill = LINEAR_W ? real(0) : real(-INFINITY);
 #pragma unroll
             for (int r = 0; r < UPT; ++r) {
-                const int f = r * kThreads + tid;
+                const int f = r * kK3Threads + tid;
                 real tmp[EPU];
 #pragma unroll
                 for (int j = 0; j < EPU; ++j) tmp[j] = fill;
@@ -691,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
 #pragma unroll
                     for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
                 }
-                real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & 3)]);
+                real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
 #pragma unroll
                 for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
             }
@@ -708,12 +801,15 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
         for (int k = 0; k < UPT; ++k) {
             const int g = UPT * tid + k;
             real tmp[EPU];
-            unit_to_array(lw_s[g ^ ((g >> 3) & 3)], tmp);
+            unit_to_array(lw_s[g ^ ((g >> 3) & (UPT - 1))], tmp);
 #pragma unroll
             for (int j = 0; j < EPU; ++j) {
-                real v = LINEAR_W ? tmp[j] * n_real : fast_exp(tmp[j] - lw_ref);
-                v = fmin(fmax(v, real(0)), n_real);          // NaN / negative -> 0, cap at N
-                run = quant.add(run, v, runf);
+                if (LINEAR_W) {
+                    real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);   // NaN / negative -> 0, cap at N
+                    run = quant.add(run, v, runf);
+                } else {
+                    run = quant.add_logw(run, tmp[j], runf);
+                }
                 c[k * EPU + j] = run;                        // inclusive within thread
             }
         }
@@ -728,36 +824,22 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
     __syncthreads();   // also: everyone is done reading lw_s
     unsigned long long warp_excl = 0, tile_agg = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
+    for (int w = 0; w < kK3Warps; ++w) {
         unsigned long long t = s_warp_tot[w];
         if (w < warp) warp_excl += t;
         tile_agg += t;
     }
-    if (warp == 0) {
-        volatile unsigned long long* words = reinterpret_cast<volatile unsigned long long*>(a.state + tile);
-        if (tile == 0) {
-            if (lane == 0) {
-                unsigned long long off = a.cdf_offset;
-                if (a.totals) for (int r = 0; r < a.rank; ++r) off += a.totals[r];
-                words[1] = kValidBit | (off + tile_agg);
-                s_prefix = off;
-            }
-        } else {
-            if (lane == 0) words[0] = kValidBit | tile_agg;
-            unsigned long long pre = lookback(a.state, tile, lane);
-            if (lane == 0) {
-                words[1] = kValidBit | (pre + tile_agg);
-                s_prefix = pre;
-            }
-        }
-    }
+    // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded)
+    unsigned long long tile_prefix = a.state[tile].y + a.cdf_offset;
+    if (a.totals) for (int r = 0; r < a.rank; ++r) tile_prefix += a.totals[r];
+    (void)tile_agg;
     if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
 
     // ---- phase C: output boundaries (32-bit) -------------------------------------------------
     // e[k] = number of outputs whose stratified position lies below the CDF value after item k
-    const unsigned long long base_b = s_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
-    const uint32_t e_start = fast_outputs_below(base_b, fs, sp);
+    const unsigned long long base_b = tile_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
+    uint32_t e_start = fast_outputs_below(base_b, fs, sp);
     uint32_t e[IPT];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) e[k] = fast_outputs_below(base_b + c[k], fs, sp);
@@ -767,10 +849,17 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
 #pragma unroll
             for (int k = 0; k < IPT; ++k) if (j0 + k >= a.n_global - 1) e[k] = fs.n_global;
         }
+        // the quantised total may exceed N 2^F by round-off: no boundary may pass N
+        // (boundaries are monotone, so one test per thread suffices)
+        if (e[IPT - 1] > fs.n_global) {
+            e_start = e_start < fs.n_global ? e_start : fs.n_global;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) e[k] = e[k] < fs.n_global ? e[k] : fs.n_global;
+        }
     }
     // (padding items beyond the shard carry zero weight, hence no outputs of their own)
     if (tid == 0) s_E[0] = e_start;
-    if (tid == kThreads - 1) s_E[1] = e[IPT - 1];
+    if (tid == kK3Threads - 1) s_E[1] = e[IPT - 1];
     __syncthreads();
     const uint32_t E0 = s_E[0], E1 = s_E[1];
     const uint32_t count = E1 - E0;
@@ -786,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
         // 1. clear the window
         {
             uint4* o4 = reinterpret_cast<uint4*>(out_s);
-            for (int p = tid; p < W * 2 / 16; p += kThreads) o4[p] = make_uint4(0, 0, 0, 0);
+            for (int p = tid; p < W * 2 / 16; p += kK3Threads) o4[p] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
         // 2. head markers (local index + 1) at the first output of every item with offspring
@@ -834,7 +923,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
             __syncthreads();
             int carry = excl;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
+            for (int w = 0; w < kK3Warps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
 #pragma unroll
             for (int k = 0; k < CH / 2; ++k) {
                 int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
@@ -850,21 +939,22 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
             const int cnt = rem < (uint32_t)W ? (int)rem : W;
             const int64_t g0 = (int64_t)E0 + wbase;                  // global index of window slot 0
             if (!peer) {
-                real* dwin = xdst + (g0 - a.offset);                 // local destination of slot 0
-                int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) : nullptr;
-                const int32_t abase = (int32_t)(a.offset + tile_base);
+                real* dwin = xdst + (g0 - a.offset) + tid;           // this thread's first output slot
+                int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) + tid : nullptr;
+                const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // markers are index + 1
+                const unsigned short* mk = out_s + tid;
+                const real* xg = x_s - 1;                            // ditto
 #pragma unroll
                 for (int it = 0; it < CH; ++it) {
-                    const int p = it * kThreads + tid;
-                    if (p < cnt) {
-                        const int li = (int)out_s[p] - 1;            // local ancestor
-                        if (awin) awin[p] = abase + li;
+                    if (it * kK3Threads + tid < cnt) {
+                        const int li1 = (int)mk[it * kK3Threads];       // local ancestor + 1
+                        if (awin) awin[it * kK3Threads] = abase + li1;
                         if (NXF > 0) {
                             real xv[NXF > 0 ? NXF : 1];
 #pragma unroll
                             for (int d = 0; d < NXF; ++d) {
-                                xv[d] = x_s[d * TILE + li];
-                                dwin[d * a.ld + p] = xv[d];
+                                xv[d] = xg[d * TILE + li1];
+                                dwin[d * a.ld + it * kK3Threads] = xv[d];
                             }
                             int k = 0;
 #pragma unroll
@@ -877,7 +967,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
                     }
                 }
             } else {
-                for (int p = tid; p < cnt; p += kThreads) {          // cross-shard migration path
+                for (int p = tid; p < cnt; p += kK3Threads) {          // cross-shard migration path
                     const int li = (int)out_s[p] - 1;
                     const int64_t gi = g0 + p;
                     const int64_t r = gi / a.shard_n;
@@ -914,41 +1004,10 @@ __global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && NXF <= 2) ? 4 
         if (tid < NM) {
             double s = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += s_mom[w][tid];
+            for (int w = 0; w < kK3Warps; ++w) s += s_mom[w][tid];
             a.mom_parts[tile * NM + tid] = s;
         }
     }
-}
-
-// shard total of the fixed-point weights (integer atomics: order independent)
-template <typename real>
-__global__ void __launch_bounds__(kThreads) k_shard_total(const Ctrl* ctrl, const real* logw, int64_t n,
-                                                          int64_t n_global, unsigned long long* total) {
-    if (!ctrl->do_resample) return;
-    // same quantisation as k3_resample: one thread owns IPT consecutive items and quantises
-    // its running sum, so the shard total equals the last inclusive prefix K3 will compute
-    constexpr int IPT = K3Geom<real>::IPT;
-    const real lw_ref = (real)ctrl->lw_ref;
-    const real n_real = (real)n_global;
-    Quant<real> quant;
-    quant.init(ctrl->frac_bits);
-    unsigned long long acc = 0;
-    const int64_t n_groups = cdiv64(n, IPT);
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * kThreads) {
-        double runf = 0.0;
-        unsigned long long run = 0;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const int64_t i = g * IPT + k;
-            real v = i < n ? fast_exp(logw[i] - lw_ref) : real(0);
-            v = (v > real(0)) ? v : real(0);
-            v = v < n_real ? v : n_real;
-            run = quant.add(run, v, runf);
-        }
-        acc += run;
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
 }
 
 // ==============================================================================================
@@ -1267,8 +1326,12 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
     a.z = z_dev;
     a.parts = l.k1_parts();
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
-    a.seed = seed; a.t = (uint32_t)t; a.mode = mode;
-    k1_propagate_weight<real, Model><<<(unsigned)l.L.n_k1_blocks, kThreads, 0, l.st>>>(a, m);
+    a.seed = seed; a.t = (uint32_t)t; a.mode = mode & 3;
+    // mode bit 4 (internal): the caller knows the step resamples -> skip the pre-resample moments
+    if (mode & 4)
+        k1_propagate_weight<real, Model, false><<<(unsigned)l.L.n_k1_blocks, kThreads, 0, l.st>>>(a, m);
+    else
+        k1_propagate_weight<real, Model, true><<<(unsigned)l.L.n_k1_blocks, kThreads, 0, l.st>>>(a, m);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1308,7 +1371,7 @@ template <typename real> int dispatch_k1(const Launch& l, int model_id, const do
 template <typename real, int NXF, bool LIN>
 int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
     using G = K3Geom<real>;
-    const size_t smem = sizeof(real) * kThreads * G::IPT * (1 + NXF);
+    const size_t smem = sizeof(real) * G::THREADS * G::IPT * (1 + NXF);
     auto kern = k3_resample<real, NXF, LIN>;
     static bool attr_set = false;   // one flag per template instantiation
     if (!attr_set) {
@@ -1317,7 +1380,24 @@ int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
                                             cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    kern<<<(unsigned)n_tiles, kThreads, smem, l.st>>>(a);
+    kern<<<(unsigned)n_tiles, G::THREADS, smem, l.st>>>(a);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename real>
+int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int force, unsigned long long* total_out) {
+    const smc_sir_desc* d = l.d;
+    ulonglong2* tiles = reinterpret_cast<ulonglong2*>(l.agg());
+    const unsigned nt = (unsigned)l.L.n_tiles;
+    if (linear_w)
+        k3a_tile_totals<real, true><<<nt, K3Geom<real>::THREADS, 0, l.st>>>(l.ctrl(), static_cast<const real*>(wsrc), d->n,
+                                                               d->n_global, tiles, force);
+    else
+        k3a_tile_totals<real, false><<<nt, K3Geom<real>::THREADS, 0, l.st>>>(l.ctrl(), static_cast<const real*>(wsrc), d->n,
+                                                                d->n_global, tiles, force);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    k3a_scan_tiles<<<1, 1024, 0, l.st>>>(l.ctrl(), tiles, l.L.n_tiles, 0ull, total_out, force);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1325,10 +1405,12 @@ int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
 template <typename real>
 int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
               void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
-              int rank = 0) {
+              int rank = 0, bool run_prepass = true) {
     const smc_sir_desc* d = l.d;
-    // clear tile state + ticket (contiguous in the layout)
-    SMC_CHECK_CUDA(cudaMemsetAsync(l.ws + l.L.tile_agg, 0, l.L.mom_parts - l.L.tile_agg, l.st));
+    ulonglong2* tiles = reinterpret_cast<ulonglong2*>(l.agg());
+    if (run_prepass) {
+        if (int rc = launch_prepass<real>(l, linear_w, wsrc, force, nullptr)) return rc;
+    }
     K3Args<real> a;
     a.ctrl = l.ctrl();
     a.wsrc = static_cast<const real*>(wsrc);
@@ -1342,7 +1424,7 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
         a.peer1 = reinterpret_cast<real* const*>(peer) + n_shards;
     }
     a.ancestors = ((d->flags & SMC_FLAG_WRITE_ANCESTORS) || nxf == 0) ? d->ancestors_dev : nullptr;
-    a.state = reinterpret_cast<ulonglong2*>(l.agg()); a.ticket = l.ticket();
+    a.state = tiles;
     a.mom_parts = want_moments ? l.mom_parts() : nullptr;
     a.cdf_offset = cdf_offset;
     a.totals = totals; a.rank = rank;
@@ -1414,7 +1496,7 @@ int smc_sir_propagate_weight(const smc_sir_desc* d, int32_t model_id, const doub
                              void* stream) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
-    SMC_REQUIRE(mode >= 1 && mode <= 3, "smc: bad mode %d", mode);
+    SMC_REQUIRE((mode & 3) >= 1 && mode <= 7, "smc: bad mode %d", mode);
     SMC_REQUIRE(!(mode & SMC_MODE_WEIGHT) || z_dev, "smc: z_dev required when weighting");
     SMC_REQUIRE(params_host != nullptr, "smc: params missing");
     SMC_REQUIRE(!(d->flags & SMC_FLAG_GENERIC_MOMENTS), "smc: fused K1 carries inline moments; clear GENERIC_MOMENTS");
@@ -1505,18 +1587,11 @@ int smc_sir_set_uniform(const smc_sir_desc* d, double u, void* stream) {
 int smc_sir_shard_weight_total(const smc_sir_desc* d, uint64_t* total_dev, void* stream) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
-    SMC_CHECK_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint64_t), l.st));
-    int64_t g = cdiv64(d->n, kThreads * 16);
-    if (g > 148 * 8) g = 148 * 8;
-    const unsigned grid = (unsigned)g;
-    if (d->dtype == SMC_F32)
-        k_shard_total<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const float*)d->logw_dev, d->n, d->n_global,
-                                                         (unsigned long long*)total_dev);
-    else
-        k_shard_total<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (const double*)d->logw_dev, d->n, d->n_global,
-                                                          (unsigned long long*)total_dev);
-    SMC_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    SMC_REQUIRE(total_dev, "smc: total_dev missing");
+    // the tile pre-pass of the resampler: leaves the tile prefixes in the workspace for
+    // smc_sir_resample_sharded and the shard total (0 when the step does not resample) in total_dev
+    return d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, 0, (unsigned long long*)total_dev)
+                               : launch_prepass<double>(l, false, d->logw_dev, 0, (unsigned long long*)total_dev);
 }
 
 int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* stats_row_dev, void* const* peer_x_dev,
@@ -1561,9 +1636,9 @@ int smc_sir_resample_sharded(const smc_sir_desc* d, const uint64_t* totals_dev, 
     const bool want_m = inline_moments(d) && !(d->flags & SMC_FLAG_NO_MOMENTS);
     return d->dtype == SMC_F32
                ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, peer_x_dev, n_shards, want_m,
-                                  (const unsigned long long*)totals_dev, rank)
+                                  (const unsigned long long*)totals_dev, rank, /*run_prepass=*/false)
                : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, peer_x_dev, n_shards, want_m,
-                                   (const unsigned long long*)totals_dev, rank);
+                                   (const unsigned long long*)totals_dev, rank, /*run_prepass=*/false);
 }
 
 int smc_sir_reduce_moment_partials(const smc_sir_desc* d, double* out_dev, void* stream) {
@@ -1639,8 +1714,10 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
 int smc_sir_step(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
                  const double* z_dev, const void* noise_dev, double resample_thresh, double u_host, uint64_t seed,
                  int64_t t, double* stats_row_dev, void* stream) {
-    if (int rc = smc_sir_propagate_weight(d, model_id, params_host, n_params, SMC_MODE_STEP, z_dev, noise_dev, seed, t,
-                                          stream))
+    // resample_thresh > 1 means ESS <= N < thresh N: the step certainly resamples, so the weighted
+    // (pre-resample) moments would be overwritten by the post-resample ones and are not accumulated
+    const int mode = SMC_MODE_STEP | (resample_thresh > 1.0 ? 4 : 0);
+    if (int rc = smc_sir_propagate_weight(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream))
         return rc;
     if (int rc = smc_sir_finalize(d, resample_thresh, u_host, seed, t, stats_row_dev, nullptr, 0, stream)) return rc;
     if (resample_thresh > 0.0)

@@ -88,6 +88,7 @@ __host__ __device__ inline int moment_stride(int nx) {
     return nx <= kFusedNxMax ? nx + nx * (nx + 1) / 2 : 1;
 }
 
+// particles per resampling tile (must match K3Geom in sir_kernels.cu: 256 x 16 fp32, 256 x 8 fp64)
 __host__ __device__ inline int k3_tile_items(int dtype) { return dtype == SMC_F64 ? 2048 : 4096; }
 
 inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
@@ -142,6 +143,11 @@ __device__ inline void philox_quad(uint64_t seed, uint64_t quad, uint32_t t, uin
     philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
+// single-MUFU approximations (flush-to-zero: no denormal fix-up code around them)
+__device__ inline float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ inline float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ inline float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // four standard normals (fp32 Box-Muller on 32-bit uniforms, curand-style open interval)
 __device__ inline void normals4_f32(const uint32_t (&r)[4], float (&z)[4]) {
     const float k2pow32inv = 2.3283064365386963e-10f;
@@ -150,7 +156,8 @@ __device__ inline void normals4_f32(const uint32_t (&r)[4], float (&z)[4]) {
     for (int p = 0; p < 2; ++p) {
         float u1 = fmaf((float)r[2 * p], k2pow32inv, 0.5f * k2pow32inv);
         float u2 = fmaf((float)r[2 * p + 1], k2pow32inv * k2pi, 0.5f * k2pow32inv * k2pi);
-        float rad = sqrtf(-2.0f * __logf(u1));
+        // sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1): two MUFU ops
+        float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
         float s, c;
         __sincosf(u2, &s, &c);
         z[2 * p] = rad * c;
@@ -243,7 +250,7 @@ template <> __device__ inline void store4<double>(double* p, const double (&v)[4
     *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
 }
 
-__device__ inline float fast_exp(float x) { return __expf(x); }
+__device__ inline float fast_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
 __device__ inline double fast_exp(double x) { return exp(x); }
 
 }  // namespace smc
