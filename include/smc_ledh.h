@@ -54,6 +54,22 @@ int smc_ledh_flow_step_supplied(const smc_ledh_desc *d, const double *P_host, co
                                 const double *z_host, const double *H_dev, const double *h_dev,
                                 double lam, double dlam, int32_t step_index, void *stream);
 
+/* Device-resident pieces for linear-Gaussian dynamics (spec model LedhGaussianSSM): the
+ * reference evaluates these through N Python callbacks per step (:113-115, :187-189).
+ *  propagate: eta0 = F x + v, v = Lq n with n ~ Philox(seed, t) when v_dev is NULL, else the
+ *             caller's coloured noise (SoA, desc dtype); eta is initialised to eta0, theta_log to 0;
+ *  terms    : log N(eta; F x, Q) + log N(z; h(eta), R) - log N(eta0; F x, Q) per particle
+ *             (the additive constants of the two transition densities cancel, the likelihood
+ *             constant is common to all particles and drops out in the normalisation).
+ * x_dev: previous particles, SoA like eta (nx rows of ld).  Qinv/Rinv: inverse covariances. */
+int smc_ledh_propagate_linear(const smc_ledh_desc *d, const void *x_dev, const double *F_host,
+                              const double *Lq_host, const void *v_dev, uint64_t seed, int64_t t,
+                              void *stream);
+int smc_ledh_gauss_terms(const smc_ledh_desc *d, const void *x_dev, const double *F_host,
+                         const double *Qinv_host, const double *Rinv_host, const double *z_host,
+                         int32_t h_kind, const double *h_params_host, int32_t n_h_params,
+                         double *terms_dev, void *stream);
+
 /* Weight update of LEDHFlowPF.step (:186-190):
  *   logw = log(w_prev + 1e-300) + theta_log + terms,
  * terms = log p(x_k|x_{k-1}) + log p(z|x_k) - log p(eta_0|x_{k-1}) per particle (fp64, device).

@@ -89,6 +89,8 @@ _LEDH_SIG = {
     "smc_ledh_flow": (C.c_int, [C.POINTER(LedhDesc), _D, _D, _D, C.c_int32, _D, C.c_int32, _P]),
     "smc_ledh_flow_step_supplied": (C.c_int, [C.POINTER(LedhDesc), _D, _D, _D, _P, _P, C.c_double,
                                               C.c_double, C.c_int32, _P]),
+    "smc_ledh_propagate_linear": (C.c_int, [C.POINTER(LedhDesc), _P, _D, _D, _P, C.c_uint64, C.c_int64, _P]),
+    "smc_ledh_gauss_terms": (C.c_int, [C.POINTER(LedhDesc), _P, _D, _D, _D, _D, C.c_int32, _D, C.c_int32, _P, _P]),
     "smc_ledh_weights": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P, _P]),
     "smc_weighted_moments": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P]),
 }

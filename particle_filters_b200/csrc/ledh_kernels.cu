@@ -298,6 +298,132 @@ __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a
     if (lane == 0) a.theta[i] = theta;
 }
 
+
+// ---- device-resident linear-Gaussian pieces (thread per particle, constants in shared memory) ----
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_ledh_propagate_linear(const real* x, real* eta0, real* eta, real* theta,
+                                                                    const real* v, const double* F, const double* Lq,
+                                                                    int64_t n, int64_t ld, int nx, uint64_t seed,
+                                                                    uint32_t t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sF = reinterpret_cast<double*>(smem_raw);
+    double* sL = sF + nx * nx;
+    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) { sF[i] = F[i]; sL[i] = Lq[i]; }
+    __syncthreads();
+    const int64_t quad = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t i0 = quad * 4;
+    if (i0 >= n) return;
+    // one thread handles 4 consecutive particles so that one Philox block serves them (per dimension)
+    double xs[kLedhMaxDim][4];
+    for (int d = 0; d < nx; ++d) {
+        real tmp[4];
+        load4<real>(x + d * ld + i0, tmp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xs[d][j] = (double)tmp[j];
+    }
+    double nz[kLedhMaxDim][4];
+    if (!v) {
+        for (int d = 0; d < nx; ++d) {
+            uint32_t r[4];
+            double z2[2];
+            philox_quad(seed, (uint64_t)i0 >> 2, t, kStreamProcess | (uint32_t(d) << 8), r);
+            normals2_f64(r, z2); nz[d][0] = z2[0]; nz[d][1] = z2[1];
+            philox_quad(seed, (uint64_t)i0 >> 2, t, kStreamProcess | (uint32_t(d) << 8) | (1u << 16), r);
+            normals2_f64(r, z2); nz[d][2] = z2[0]; nz[d][3] = z2[1];
+        }
+    }
+    for (int d = 0; d < nx; ++d) {
+        double acc[4] = {0, 0, 0, 0};
+        for (int k = 0; k < nx; ++k) {
+            const double f = sF[d * nx + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fma(f, xs[k][j], acc[j]);
+        }
+        if (v) {
+            real tmp[4];
+            load4<real>(v + d * ld + i0, tmp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += (double)tmp[j];
+        } else {
+            for (int k = 0; k <= d; ++k) {
+                const double l = sL[d * nx + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fma(l, nz[k][j], acc[j]);
+            }
+        }
+        real out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = (real)acc[j];
+        store4<real>(eta0 + d * ld + i0, out);
+        store4<real>(eta + d * ld + i0, out);
+    }
+    real zero[4] = {0, 0, 0, 0};
+    store4<real>(theta + i0, zero);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(128) k_ledh_gauss_terms(const real* x, const real* eta0, const real* eta,
+                                                          const double* F, const double* Qinv, const double* Rinv,
+                                                          const double* z, const double* hp, int n_hp, int kind,
+                                                          int64_t n, int64_t ld, int nx, int nz, double* terms) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sF = reinterpret_cast<double*>(smem_raw);
+    double* sQi = sF + nx * nx;
+    double* sRi = sQi + nx * nx;
+    double* sz = sRi + nz * nz;
+    double* shp = sz + nz;
+    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) { sF[i] = F[i]; sQi[i] = Qinv[i]; }
+    for (int i = threadIdx.x; i < nz * nz; i += blockDim.x) sRi[i] = Rinv[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) sz[i] = z[i];
+    for (int i = threadIdx.x; i < n_hp; i += blockDim.x) shp[i] = hp[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xv[kLedhMaxDim], e1[kLedhMaxDim], e0[kLedhMaxDim], et[kLedhMaxDim];
+    for (int d = 0; d < nx; ++d) { xv[d] = (double)x[d * ld + i]; et[d] = (double)eta[d * ld + i]; }
+    for (int d = 0; d < nx; ++d) {
+        double fx = 0;
+        for (int k = 0; k < nx; ++k) fx = fma(sF[d * nx + k], xv[k], fx);
+        e1[d] = et[d] - fx;
+        e0[d] = (double)eta0[d * ld + i] - fx;
+    }
+    double q1 = 0, q0 = 0;
+    for (int d = 0; d < nx; ++d) {
+        double a1 = 0, a0 = 0;
+        for (int k = 0; k < nx; ++k) { a1 = fma(sQi[d * nx + k], e1[k], a1); a0 = fma(sQi[d * nx + k], e0[k], a0); }
+        q1 = fma(e1[d], a1, q1);
+        q0 = fma(e0[d], a0, q0);
+    }
+    // innovation z - h(eta)
+    double dz[kLedhMaxDim];
+    if (kind == SMC_LEDH_H_LINEAR) {
+        for (int s = 0; s < nz; ++s) {
+            double acc = sz[s];
+            for (int k = 0; k < nx; ++k) acc = fma(-shp[s * nx + k], et[k], acc);
+            dz[s] = acc;
+        }
+    } else if (kind == SMC_LEDH_H_ACOUSTIC) {
+        const double psi = shp[0], d0 = shp[1];
+        for (int s = 0; s < nz; ++s) {
+            double acc = 0;
+            for (int c = 0; c < nx / 4; ++c) {
+                const double dx = et[4 * c] - shp[2 + 2 * s], dy = et[4 * c + 1] - shp[3 + 2 * s];
+                acc += psi / (dx * dx + dy * dy + d0);
+            }
+            dz[s] = sz[s] - acc;
+        }
+    } else {
+        for (int s = 0; s < nz; ++s) dz[s] = sz[s] - shp[0] * exp(0.5 * et[s]);
+    }
+    double qz = 0;
+    for (int s = 0; s < nz; ++s) {
+        double acc = 0;
+        for (int k = 0; k < nz; ++k) acc = fma(sRi[s * nz + k], dz[k], acc);
+        qz = fma(dz[s], acc, qz);
+    }
+    terms[i] = -0.5 * (q1 - q0) - 0.5 * qz;
+}
+
 // logw = log(w_prev + 1e-300) + theta_log + (log-density terms) (:186-190), with block partials
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_ledh_weights(real* logw, const double* wprev, const real* theta,
@@ -478,6 +604,70 @@ int smc_ledh_flow_step_supplied(const smc_ledh_desc* d, const double* P_host, co
     return d->dtype == SMC_F32
                ? launch_flow<float>(d, P_host, R_host, z_host, 0, nullptr, 0, H_dev, h_dev, lam, dlam, step_index, 1, st)
                : launch_flow<double>(d, P_host, R_host, z_host, 0, nullptr, 0, H_dev, h_dev, lam, dlam, step_index, 1, st);
+}
+
+int smc_ledh_propagate_linear(const smc_ledh_desc* d, const void* x_dev, const double* F_host, const double* Lq_host,
+                              const void* v_dev, uint64_t seed, int64_t t, void* stream) {
+    if (int rc = check_ledh(d)) return rc;
+    SMC_REQUIRE(x_dev && F_host && Lq_host, "smc_ledh_propagate_linear: null argument");
+    SMC_REQUIRE(d->ld % 4 == 0, "smc_ledh_propagate_linear: ld must be a multiple of 4");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nx = d->nx;
+    std::vector<double> host(2 * (size_t)nx * nx);
+    memcpy(host.data(), F_host, sizeof(double) * nx * nx);
+    memcpy(host.data() + nx * nx, Lq_host, sizeof(double) * nx * nx);
+    double* dev = nullptr;
+    SMC_CHECK_CUDA(cudaMallocAsync(&dev, host.size() * sizeof(double), st));
+    SMC_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)cdiv64((d->n + 3) / 4, kThreads);
+    const size_t smem = 2 * (size_t)nx * nx * sizeof(double);
+    if (d->dtype == SMC_F32)
+        k_ledh_propagate_linear<float><<<grid, kThreads, smem, st>>>((const float*)x_dev, (float*)d->eta0_dev, (float*)d->eta_dev,
+                                                                    (float*)d->theta_log_dev, (const float*)v_dev, dev,
+                                                                    dev + nx * nx, d->n, d->ld, nx, seed, (uint32_t)t);
+    else
+        k_ledh_propagate_linear<double><<<grid, kThreads, smem, st>>>((const double*)x_dev, (double*)d->eta0_dev,
+                                                                     (double*)d->eta_dev, (double*)d->theta_log_dev,
+                                                                     (const double*)v_dev, dev, dev + nx * nx, d->n, d->ld, nx,
+                                                                     seed, (uint32_t)t);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    SMC_CHECK_CUDA(cudaFreeAsync(dev, st));
+    return 0;
+}
+
+int smc_ledh_gauss_terms(const smc_ledh_desc* d, const void* x_dev, const double* F_host, const double* Qinv_host,
+                         const double* Rinv_host, const double* z_host, int32_t h_kind, const double* h_params_host,
+                         int32_t n_h_params, double* terms_dev, void* stream) {
+    if (int rc = check_ledh(d)) return rc;
+    SMC_REQUIRE(x_dev && F_host && Qinv_host && Rinv_host && z_host && terms_dev && h_params_host && n_h_params > 0,
+                "smc_ledh_gauss_terms: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nx = d->nx, nz = d->nz;
+    const size_t cnt = 2 * (size_t)nx * nx + (size_t)nz * nz + nz + n_h_params;
+    std::vector<double> host(cnt);
+    double* q = host.data();
+    memcpy(q, F_host, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, Qinv_host, sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, Rinv_host, sizeof(double) * nz * nz); q += nz * nz;
+    memcpy(q, z_host, sizeof(double) * nz); q += nz;
+    memcpy(q, h_params_host, sizeof(double) * n_h_params);
+    double* dev = nullptr;
+    SMC_CHECK_CUDA(cudaMallocAsync(&dev, cnt * sizeof(double), st));
+    SMC_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *dF = dev, *dQ = dF + nx * nx, *dR = dQ + nx * nx, *dz = dR + nz * nz, *dh = dz + nz;
+    const unsigned grid = (unsigned)cdiv64(d->n, 128);
+    const size_t smem = cnt * sizeof(double);
+    if (d->dtype == SMC_F32)
+        k_ledh_gauss_terms<float><<<grid, 128, smem, st>>>((const float*)x_dev, (const float*)d->eta0_dev,
+                                                          (const float*)d->eta_dev, dF, dQ, dR, dz, dh, n_h_params, h_kind,
+                                                          d->n, d->ld, nx, nz, terms_dev);
+    else
+        k_ledh_gauss_terms<double><<<grid, 128, smem, st>>>((const double*)x_dev, (const double*)d->eta0_dev,
+                                                           (const double*)d->eta_dev, dF, dQ, dR, dz, dh, n_h_params,
+                                                           h_kind, d->n, d->ld, nx, nz, terms_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    SMC_CHECK_CUDA(cudaFreeAsync(dev, st));
+    return 0;
 }
 
 int smc_ledh_weights(const smc_sir_desc* d, const double* wprev_dev, const void* theta_log_dev, const double* terms_dev,

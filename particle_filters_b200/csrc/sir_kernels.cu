@@ -245,7 +245,7 @@ __device__ __forceinline__ void k1_chunk(const K1Args<real>& a, const Model& m, 
 }
 
 template <typename real, class Model, bool MOM>
-__global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && Model::NX <= 2) ? 4 : 2)
+__global__ void __launch_bounds__(kThreads, (sizeof(real) == 4 && Model::NX <= 2) ? (MOM ? 4 : 5) : 2)
 k1_propagate_weight(K1Args<real> a, Model m) {
     constexpr int NX = Model::NX, NZ = Model::NZ;
     constexpr int NM = NX + NX * (NX + 1) / 2;   // moment accumulators
@@ -343,16 +343,22 @@ __device__ inline void combine_partials(const double* parts, int n_parts, int ps
     }
     const double M = block_max_256(m, s_tmp);
     const double Mref = (M == -INFINITY) ? 0.0 : M;
-    for (int k = 1; k < ps; ++k) {
-        double acc = 0;
-        for (int p = tid; p < n_parts; p += kThreads) {
-            const double* r = parts + (int64_t)p * ps;
-            double sc = exp(r[0] - Mref);           // r[0] = -inf -> 0
-            if (k == 2) sc *= sc;                    // sum e^2 scales with the square
-            acc = fma(r[k], sc, acc);
+    double acc[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) acc[k] = 0;
+    for (int p = tid; p < n_parts; p += kThreads) {     // fixed record -> thread assignment
+        const double* r = parts + (int64_t)p * ps;
+        const double sc = exp(r[0] - Mref);             // r[0] = -inf -> 0
+#pragma unroll
+        for (int k = 1; k < 20; ++k)
+            if (k < ps) acc[k] = fma(r[k], k == 2 ? sc * sc : sc, acc[k]);   // sum e^2 scales with the square
+    }
+#pragma unroll
+    for (int k = 1; k < 20; ++k) {
+        if (k < ps) {
+            const double tot = block_sum_256(acc[k], s_tmp);
+            if (tid == 0) s_out[k] = tot;
         }
-        double tot = block_sum_256(acc, s_tmp);
-        if (tid == 0) s_out[k] = tot;
     }
     if (tid == 0) s_out[0] = M;
     __syncthreads();
@@ -730,6 +736,10 @@ k3_resample(K3Args<real> a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
     const int64_t tile_base = tile * TILE;
+    // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded);
+    // loaded first so that its latency hides behind the tile loads
+    unsigned long long tile_prefix = a.state[tile].y + a.cdf_offset;
+    if (a.totals) for (int r = 0; r < a.rank; ++r) tile_prefix += a.totals[r];
 
     const SearchParams sp = load_search(ctrl, a.n_global);
     FastSearch fs;
@@ -829,9 +839,6 @@ k3_resample(K3Args<real> a) {
         if (w < warp) warp_excl += t;
         tile_agg += t;
     }
-    // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded)
-    unsigned long long tile_prefix = a.state[tile].y + a.cdf_offset;
-    if (a.totals) for (int r = 0; r < a.rank; ++r) tile_prefix += a.totals[r];
     (void)tile_agg;
     if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
@@ -1013,20 +1020,38 @@ k3_resample(K3Args<real> a) {
 // ==============================================================================================
 // finish step: post-resample moments, buffer flip, shift refresh
 // ==============================================================================================
-__global__ void __launch_bounds__(kThreads) k_finish_step(Ctrl* ctrl, double* stats, const double* mom_parts,
-                                                          int n_mom_parts, int nx, int inline_moments,
-                                                          int64_t n_global, int no_moments) {
-    __shared__ double s_tmp[kWarps];
+constexpr int kFinishThreads = 1024;
+__global__ void __launch_bounds__(kFinishThreads) k_finish_step(Ctrl* ctrl, double* stats, const double* mom_parts,
+                                                               int n_mom_parts, int nx, int inline_moments,
+                                                               int64_t n_global, int no_moments) {
+    __shared__ double s_w[kFinishThreads / 32][16];
     __shared__ double s_m[16];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int do_res = ctrl->do_resample;
     if (do_res && inline_moments && !no_moments && stats) {
         const int nm = moment_stride(nx);
-        for (int k = 0; k < nm; ++k) {
-            double acc = 0;
-            for (int p = tid; p < n_mom_parts; p += kThreads) acc += mom_parts[(int64_t)p * nm + k];
-            double tot = block_sum_256(acc, s_tmp);
-            if (tid == 0) s_m[k] = tot;
+        // fixed assignment record -> thread, independent loads issued back to back
+        double acc[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) acc[k] = 0;
+#pragma unroll 4
+        for (int p = tid; p < n_mom_parts; p += kFinishThreads) {
+            const double* r = mom_parts + (int64_t)p * nm;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) if (k < nm) acc[k] += r[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+            if (k < nm) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) s_w[warp][k] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nm) {
+            double t = 0;
+            for (int w = 0; w < kFinishThreads / 32; ++w) t += s_w[w][tid];
+            s_m[tid] = t;
         }
         __syncthreads();
         if (tid == 0) {
@@ -1704,7 +1729,7 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
         k_moments_generic_fix<<<1, 32, 0, l.st>>>(l.ctrl(), nx, stats_row_dev);
         SMC_CHECK_CUDA(cudaGetLastError());
     }
-    k_finish_step<<<1, kThreads, 0, l.st>>>(l.ctrl(), stats_row_dev, mom_parts_dev ? mom_parts_dev : l.mom_parts(),
+    k_finish_step<<<1, kFinishThreads, 0, l.st>>>(l.ctrl(), stats_row_dev, mom_parts_dev ? mom_parts_dev : l.mom_parts(),
                                            n_mom_parts > 0 ? n_mom_parts : (int)l.L.n_tiles, d->nx, inl ? 1 : 0,
                                            d->n_global, no_m);
     SMC_CHECK_CUDA(cudaGetLastError());

@@ -23,7 +23,7 @@ from typing import Callable, Optional, Protocol, Tuple
 import numpy as np
 
 from . import _lib
-from .ssm import measurement_spec_of
+from .ssm import ledh_spec_of, measurement_spec_of
 
 Array = np.ndarray
 
@@ -101,6 +101,27 @@ class PFState:
     diagnostics: dict = None
 
 
+class DeviceLedhState(PFState):
+    """``PFState`` of a device-resident LEDH run: particles / weights are fetched on access."""
+
+    def __init__(self, owner, mean, cov, diagnostics):
+        self._owner = owner
+        self._particles = self._weights = None
+        self.mean, self.cov, self.diagnostics = mean, cov, diagnostics
+
+    @property
+    def particles(self):
+        if self._particles is None:
+            self._particles = self._owner._dev_eng.get_particles()
+        return self._particles
+
+    @property
+    def weights(self):
+        if self._weights is None:
+            self._weights = self._owner._dev_eng.weights()
+        return self._weights
+
+
 class _FlowBuffers:
     """Device arrays of one (N, nx, nz) flow problem."""
 
@@ -165,7 +186,13 @@ class LEDHFlowPF:
         self.cfg = config or LEDHConfig()
         self._dtype, self._device = dtype, device
         self._meas = measurement_spec_of(h, jacobian_h)
+        self._spec = ledh_spec_of(g, h, jacobian_h, log_trans_pdf, log_like_pdf)
+        if self._spec is not None:
+            self._meas = self._spec.meas
         self._flow = {}
+        self._dev_eng = None
+        self._seed = 0
+        self._t = 0
 
     # ------------------------------------------------------------------ API
     def init_from_gaussian(self, mean0: Array, cov0: Array) -> PFState:
@@ -191,6 +218,8 @@ class LEDHFlowPF:
         process_noise_sampler: Optional[Callable[[int, int], Array]] = None,
     ) -> PFState:
         """One LEDH step (reference :93-214)."""
+        if self._spec is not None:
+            return self._step_device(state, z_k, process_noise_sampler)
         particles = np.asarray(state.particles, float)
         N, nx = particles.shape
         z_k = np.asarray(z_k, float).reshape(-1)
@@ -280,6 +309,87 @@ class LEDHFlowPF:
         cov = 0.5 * (cov + cov.T)
         return PFState(particles=xk, weights=w, mean=mean, cov=cov,
                        diagnostics={"condition_numbers": cond_numbers})
+
+    # ------------------------------------------------------------------ device-resident step
+    def _step_device(self, state, z_k, process_noise_sampler, philox_seed=None):
+        """Whole step on the GPU for a ``LedhGaussianSSM`` spec: propagate, flow, log-density
+        terms, weights, ESS-triggered systematic resampling, moments.  The particle set only
+        crosses PCIe when the caller reads ``state.particles``.  With
+        ``process_noise_sampler=None`` the reference uses v = 0 (:109-110); pass
+        ``"philox"`` to draw v ~ N(0, Q) on chip instead."""
+        from .engine import SirEngine
+
+        sp = self._spec
+        lib = _lib.load()
+        nx, nz = sp.nx, sp.nz
+        z_k = np.asarray(z_k, float).reshape(-1)
+        resident = isinstance(state, DeviceLedhState) and state._owner is self and state._particles is None \
+            and state._weights is None
+        N = self.cfg.n_particles if resident else np.asarray(state.particles).shape[0]
+        if self._dev_eng is None or self._dev_eng.n != N:
+            self._dev_eng = SirEngine(N, nx, nz, dtype=self._dtype, device=self._device, write_ancestors=True,
+                                      generic_moments=True)
+        eng = self._dev_eng
+        torch = eng.torch
+        if not resident:
+            eng.set_particles(np.asarray(state.particles, float), shift=np.asarray(state.mean, float).reshape(-1)[:nx])
+            wprev = torch.from_numpy(np.asarray(state.weights, float).reshape(-1).copy()).to(eng.device)
+        else:
+            wprev = torch.empty((N,), dtype=torch.float64, device=eng.device)
+            _lib.check(lib.smc_sir_export_weights(eng._d, C.c_void_p(wprev.data_ptr()), eng.stream))
+        cur = eng.current_buffer()
+        xprev = eng.x[cur]
+
+        m_pred, P = self.tracker.predict()
+        P = 0.5 * (P + P.T)
+        n_steps = max(1, int(self.cfg.n_lambda_steps))
+        buf = self._buffers(N, nx, nz, n_steps)
+        kF, pF = _lib.as_doubles(sp.F)
+        kL, pL = _lib.as_doubles(sp.Lq)
+        v_dev = None
+        if process_noise_sampler is None:
+            v_dev = torch.zeros((nx, buf.ld), dtype=buf.tdtype, device=buf.device)
+        elif process_noise_sampler != "philox":
+            v = np.asarray(process_noise_sampler(N, nx), float)
+            v_dev = torch.zeros((nx, buf.ld), dtype=buf.tdtype, device=buf.device)
+            v_dev[:, :N].copy_(torch.from_numpy(np.ascontiguousarray(v.T).astype(buf.npdtype, copy=False)))
+        _lib.check(lib.smc_ledh_propagate_linear(
+            C.byref(buf.desc), C.c_void_p(xprev.data_ptr()), pF, pL,
+            C.c_void_p(v_dev.data_ptr()) if v_dev is not None else None, C.c_uint64(self._seed), self._t, buf.stream))
+        self._t += 1
+        kP, pP = _lib.as_doubles(P)
+        kR, pR = _lib.as_doubles(self.R)
+        kz, pz = _lib.as_doubles(z_k)
+        kind, hp = self._meas.ledh_functor()
+        kh, ph = _lib.as_doubles(hp)
+        _lib.check(lib.smc_ledh_flow(C.byref(buf.desc), pP, pR, pz, kind, ph, kh.size, buf.stream))
+        terms = torch.empty((N,), dtype=torch.float64, device=buf.device)
+        kQi, pQi = _lib.as_doubles(sp.Qinv)
+        kRi, pRi = _lib.as_doubles(sp.Rinv)
+        _lib.check(lib.smc_ledh_gauss_terms(C.byref(buf.desc), C.c_void_p(xprev.data_ptr()), pF, pQi, pRi, pz, kind,
+                                            ph, kh.size, C.c_void_p(terms.data_ptr()), buf.stream))
+        # weights on the SIR kernels: the flowed particles become the engine's current buffer
+        eng.x[cur][:, :N].copy_(buf.eta[:, :N])
+        _lib.check(lib.smc_ledh_weights(eng._d, C.c_void_p(wprev.data_ptr()), C.c_void_p(buf.theta.data_ptr()),
+                                        C.c_void_p(terms.data_ptr()), eng.stream))
+        ratio = float(self.cfg.resample_ess_ratio)
+        eng.finalize(ratio if ratio > 0.0 else 0.0, u=0.0)
+        row = eng.read_row()
+        self.tracker.update(z_k)
+        if bool(row[2]):
+            eng.set_uniform(float(self.cfg.rng.random()))
+            eng.resample()
+        eng.finish_step()
+        row = eng.read_row()
+        H0 = _lib.SMC_STATS_HEADER
+        mean = row[H0:H0 + nx].copy()
+        cov = row[H0 + nx:].reshape(nx, nx).copy()
+        cov = 0.5 * (cov + cov.T)
+        s0 = buf.s0.cpu().numpy()
+        cond = [float(np.linalg.cond(s0[j])) for j in range(n_steps)]
+        self.last_ess = float(row[1])
+        self.last_resampled = bool(row[2])
+        return DeviceLedhState(self, mean, cov, {"condition_numbers": cond})
 
     # ------------------------------------------------------------------ helpers
     @staticmethod

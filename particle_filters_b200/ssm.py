@@ -166,3 +166,55 @@ def measurement_spec_of(h, jacobian_h):
             and getattr(jacobian_h, "__func__", None) is type(sh).jacobian_h:
         return sh
     return None
+
+
+class LedhGaussianSSM:
+    """Linear-Gaussian dynamics ``x_k = F x_{k-1} + v, v ~ N(0, Q)`` with a measurement spec and
+    Gaussian observation noise ``R``: supplies all five LEDH callbacks in the reference's
+    signatures (``g(x,u,v)``, ``h``, ``jacobian_h``, ``log_trans_pdf``, ``log_like_pdf``,
+    LEDH_particle_filter.py:18-22).  When all five callables handed to ``LEDHFlowPF`` are the
+    bound methods of one such object the whole step runs on the GPU."""
+
+    def __init__(self, F, Q, measurement: _MeasurementSpec, R):
+        self.F = np.atleast_2d(np.asarray(F, float))
+        self.Q = np.atleast_2d(np.asarray(Q, float))
+        self.R = np.atleast_2d(np.asarray(R, float))
+        self.meas = measurement
+        self.nx, self.nz = self.F.shape[0], self.R.shape[0]
+        self.Lq = np.linalg.cholesky(self.Q)
+        self.Qinv = np.linalg.inv(self.Q)
+        self.Rinv = np.linalg.inv(self.R)
+        self._cq = np.linalg.slogdet(2 * np.pi * self.Q)[1]
+        self._cr = np.linalg.slogdet(2 * np.pi * self.R)[1]
+
+    def g(self, x, u=None, v=None):
+        return self.F @ x + (0.0 if v is None else v)
+
+    def h(self, x):
+        return self.meas.h(x)
+
+    def jacobian_h(self, x):
+        return self.meas.jacobian_h(x)
+
+    def log_trans_pdf(self, xk, xkm1):
+        d = xk - self.F @ xkm1
+        return float(-0.5 * (d @ self.Qinv @ d + self._cq))
+
+    def log_like_pdf(self, z, x):
+        d = z - self.meas.h(x)
+        return float(-0.5 * (d @ self.Rinv @ d + self._cr))
+
+    def sampler(self, rng):
+        """A ``process_noise_sampler(N, nx)`` drawing N(0, Q) from ``rng`` (host)."""
+        return lambda n, nx: rng.standard_normal((n, nx)) @ self.Lq.T
+
+
+def ledh_spec_of(g, h, jacobian_h, log_trans_pdf, log_like_pdf):
+    owners = [getattr(f, "__self__", None) for f in (g, h, jacobian_h, log_trans_pdf, log_like_pdf)]
+    s = owners[0]
+    if isinstance(s, LedhGaussianSSM) and all(o is s for o in owners):
+        names = ("g", "h", "jacobian_h", "log_trans_pdf", "log_like_pdf")
+        fns = (g, h, jacobian_h, log_trans_pdf, log_like_pdf)
+        if all(getattr(f, "__func__", None) is getattr(type(s), n) for f, n in zip(fns, names)):
+            return s
+    return None

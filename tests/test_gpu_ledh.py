@@ -50,7 +50,7 @@ def _measurement_spec(model, kind):
     return AcousticMeasurement(model.S, model.psi, model.d0, n_targets=model.n_targets)
 
 
-@pytest.mark.parametrize("mode", ["bridge", "device_h"])
+@pytest.mark.parametrize("mode", ["bridge", "device_h", "device_full"])
 @pytest.mark.parametrize("name,model,tol,kind", _cases())
 def test_ledh_step_tracks_reference(golden, name, model, tol, kind, mode):
     from particle_filters_b200.ledh_particle_filter import LEDHConfig, LEDHFlowPF, PFState
@@ -63,10 +63,16 @@ def test_ledh_step_tracks_reference(golden, name, model, tol, kind, mode):
     tracker = ScriptedTracker(g["Ps"], model.nx)
     if mode == "bridge":
         h, jh = (lambda x: model.h(x)), (lambda x: model.jac_h(x))
-    else:
+        f = LEDHFlowPF(tracker, model.g, h, jh, model.log_trans_pdf, model.log_like_pdf, model.R, cfg)
+    elif mode == "device_h":
         spec = _measurement_spec(model, kind)
-        h, jh = spec.h, spec.jacobian_h
-    f = LEDHFlowPF(tracker, model.g, h, jh, model.log_trans_pdf, model.log_like_pdf, model.R, cfg)
+        f = LEDHFlowPF(tracker, model.g, spec.h, spec.jacobian_h, model.log_trans_pdf, model.log_like_pdf, model.R, cfg)
+    else:   # every callback from one LedhGaussianSSM spec: the whole step stays on the GPU
+        from particle_filters_b200.ssm import LedhGaussianSSM
+
+        F = np.array([[model.alpha]]) if kind == "linear" else model.F
+        full = LedhGaussianSSM(F, model.Q, _measurement_spec(model, kind), model.R)
+        f = LEDHFlowPF(tracker, full.g, full.h, full.jacobian_h, full.log_trans_pdf, full.log_like_pdf, model.R, cfg)
     x, w = g["particles0"], g["weights0"]
     mean0, cov0 = ledh_weighted_stats(x, w)
     for k in range(T):
