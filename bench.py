@@ -230,35 +230,30 @@ def run_gpu_arm(args):
     ms_total = e0.elapsed_time(e1)
     ms_step = ms_total / K
 
-    # ---- per-kernel breakdown (same steps again, events between the phases) -----------------
-    phases = ("k1_propagate_weight", "k2_finalize", "k3_resample", "finish_step")
+    # ---- per-kernel breakdown (same fused step, split at its three launch groups) --------------
+    phases = ("k1_propagate_weight+finalize", "k3a_tile_prepass+scan", "k3_resample+finish")
     acc = {p: 0.0 for p in phases}
-    kp, pp = _lib.as_doubles(params)
-    import ctypes as C
-
-    for k in range(W + K, W + K + 2):   # two extra steps reuse trace rows via modulo
-        evs = [ev() for _ in range(5)]
+    NB = 4
+    for k in range(W + K, W + K + NB):   # extra steps reuse trace rows / observations via modulo
+        evs = [ev() for _ in range(4)]
+        kk = k % (W + K)
         evs[0].record()
-        # same K1 variant as smc_sir_step uses when every step resamples (mode bit 4)
-        _lib.check(eng.lib.smc_sir_propagate_weight(eng._d, mid, pp, kp.size, _lib.SMC_MODE_STEP | 4, eng._zptr(k % (W + K)),
-                                                    None, C.c_uint64(seed), k, eng.stream))
+        eng.step_weight(mid, params, thresh, z_index=kk, seed=seed, t=k, row=kk)
         evs[1].record()
-        eng.finalize(thresh, u=-1.0, seed=seed, t=k, row=k)
+        eng.step_resample(1, row=kk)
         evs[2].record()
-        eng.resample(row=k)
+        eng.step_resample(2, row=kk)
         evs[3].record()
-        eng.finish_step(row=k)
-        evs[4].record()
         torch.cuda.synchronize()
         for i, p in enumerate(phases):
-            acc[p] += evs[i].elapsed_time(evs[i + 1]) / 2.0
+            acc[p] += evs[i].elapsed_time(evs[i + 1]) / NB
     clk = clocks.stop()
     rows = eng.trace[: W + K].cpu().numpy()
     assert np.all(np.isfinite(rows[:, :5])), "non-finite filter statistics"
     assert np.all(rows[W:, 2] == 1.0), "bootstrap filter must resample every step"
 
     peak, peak_src = measured_peak()
-    dom = max(("k1_propagate_weight", "k3_resample"), key=lambda p: acc[p])
+    dom = max((phases[0], phases[2]), key=lambda p: acc[p])
     alg_bytes = 12.0 * N          # K1: R x, W x, W logw ; K3: R logw, R x, W x   (fp32, nx = 1)
     achieved = alg_bytes / (acc[dom] * 1e-3) / 1e9
     value = N / (ms_step * 1e-3)
@@ -299,14 +294,14 @@ def run_gpu_arm(args):
                                "(BASELINE.json configs[2] / SURVEY 8d C3)",
                    "n_particles": N, "nx": 1, "nz": 1, "resample": "every step", "noise": "philox4x32-10 on chip",
                    "l2": "inputs (2 x 256 MiB per step) exceed the 126 MB L2; no flush needed"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": 4 * K,
+        "clocks": clk, "e2e": e2e, "gpu_launches": 4 * K,   # K1(+finalize), tile pre-pass, tile scan, K3(+finish)
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": acc[dom]},
         "roofline_step": {"alg_bytes_per_particle_update": step_alg,
                           "achieved": step_alg * value / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": step_alg * value / 1e9 / peak,
-                          "note": "SURVEY 8d closed form 16 nx + 16 B; the fused pipeline moves 24 B"},
+                          "note": "SURVEY 8d closed form 16 nx + 16 B; the pipeline actually moves 28 B (12 K1 + 4 pre-pass + 12 K3)"},
         "kernel_ms": acc, "cpu_baseline": cpu,
         "filter": {"mean_last": float(rows[-1, 4]), "ess_last": float(rows[-1, 1])},
     }

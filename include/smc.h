@@ -197,6 +197,16 @@ int smc_sir_step(const smc_sir_desc *d, int32_t model_id, const double *params_h
                  double resample_thresh, double u_host, uint64_t seed, int64_t t,
                  double *stats_row_dev, void *stream);
 
+/* The two halves of smc_sir_step, for callers that want to time or interleave them:
+ *  _weight  : K1 with the K2 finalize folded into its last CTA (one launch);
+ *  _resample: phases bit 1 = tile pre-pass + tile scan, bit 2 = K3 with the finish step folded
+ *             into its last CTA; a no-op on the data when the control block says "do not resample". */
+int smc_sir_step_weight(const smc_sir_desc *d, int32_t model_id, const double *params_host,
+                        int32_t n_params, const double *z_dev, const void *noise_dev,
+                        double resample_thresh, double u_host, uint64_t seed, int64_t t,
+                        double *stats_row_dev, void *stream);
+int smc_sir_step_resample(const smc_sir_desc *d, int32_t phases, double *stats_row_dev, void *stream);
+
 /* Stand-alone pieces used by the drop-in classes' private helpers. */
 
 /* ParticleFilter._systematic_resample(weights) (particle_filter.py:146-171):

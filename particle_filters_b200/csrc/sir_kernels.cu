@@ -79,6 +79,19 @@ template <typename real, int NX_, int NZ_> struct LinGaussModel {
 // ==============================================================================================
 // K1: fused propagate + log-likelihood + block partials
 // ==============================================================================================
+struct K2Args {
+    Ctrl* ctrl;
+    const double* parts;
+    double* stats;     // nullable
+    int64_t n_global;
+    int32_t n_parts, nx, inline_moments;
+    double thresh, u_host;
+    uint64_t seed;
+    uint32_t t;
+};
+
+__device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp);   // defined with K2
+
 template <typename real> struct K1Args {
     Ctrl* ctrl;
     real* x0;
@@ -91,28 +104,32 @@ template <typename real> struct K1Args {
     uint64_t seed;
     uint32_t t;
     int32_t mode;
+    PhiloxKeys keys;            // the ten round keys of `seed`, expanded once on the host
+    int32_t fuse_finalize;      // the last CTA to finish also runs the K2 finalize (fin)
+    unsigned int* ticket;       // arrival counter for fuse_finalize (zero between launches)
+    K2Args fin;
 };
 
 template <typename real, int NX>
 __device__ inline void draw_normals(uint64_t seed, uint64_t gquad, uint32_t t, real (&nrm)[NX][4]);
 
-template <int NX> __device__ inline void draw_normals_f32(uint64_t seed, uint64_t gquad, uint32_t t,
+template <int NX> __device__ inline void draw_normals_f32(const PhiloxKeys& keys, uint64_t gquad, uint32_t t,
                                                           float (&nrm)[NX][4]) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
         uint32_t r[4];
-        philox_quad(seed, gquad, t, kStreamProcess | (uint32_t(d) << 8), r);
+        philox_quad_keys(keys, gquad, t, kStreamProcess | (uint32_t(d) << 8), r);
         normals4_f32(r, nrm[d]);
     }
 }
-template <int NX> __device__ inline void draw_normals_f64(uint64_t seed, uint64_t gquad, uint32_t t,
+template <int NX> __device__ inline void draw_normals_f64(const PhiloxKeys& keys, uint64_t gquad, uint32_t t,
                                                           double (&nrm)[NX][4]) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t r[4];
-            philox_quad(seed, gquad, t, kStreamProcess | (uint32_t(d) << 8) | (uint32_t(h) << 16), r);
+            philox_quad_keys(keys, gquad, t, kStreamProcess | (uint32_t(d) << 8) | (uint32_t(h) << 16), r);
             double z2[2];
             normals2_f64(r, z2);
             nrm[d][2 * h] = z2[0];
@@ -121,10 +138,10 @@ template <int NX> __device__ inline void draw_normals_f64(uint64_t seed, uint64_
     }
 }
 template <int NX> struct Draw {
-    static __device__ inline void run(uint64_t s, uint64_t q, uint32_t t, float (&n)[NX][4]) {
+    static __device__ inline void run(const PhiloxKeys& s, uint64_t q, uint32_t t, float (&n)[NX][4]) {
         draw_normals_f32<NX>(s, q, t, n);
     }
-    static __device__ inline void run(uint64_t s, uint64_t q, uint32_t t, double (&n)[NX][4]) {
+    static __device__ inline void run(const PhiloxKeys& s, uint64_t q, uint32_t t, double (&n)[NX][4]) {
         draw_normals_f64<NX>(s, q, t, n);
     }
 };
@@ -161,7 +178,7 @@ __device__ __forceinline__ void k1_chunk(const K1Args<real>& a, const Model& m, 
 #pragma unroll
                     for (int d = 0; d < NX; ++d) load4<real>(a.noise + d * a.ld + i0, nrm[d]);
                 } else {
-                    Draw<NX>::run(a.seed, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
+                    Draw<NX>::run(a.keys, (uint64_t)(a.offset + i0) >> 2, a.t, nrm);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -313,6 +330,21 @@ k1_propagate_weight(K1Args<real> a, Model m) {
             out[tid] = s;
         }
     }
+    if (a.fuse_finalize) {
+        // the last CTA to arrive reduces all block partials (fixed order) and finalises the step
+        __shared__ int s_last;
+        __shared__ double s_out[32];
+        __shared__ double s_tmp[kWarps];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finalize_body(a.fin, s_out, s_tmp);
+            if (tid == 0) *a.ticket = 0u;
+        }
+    }
 }
 
 // ==============================================================================================
@@ -320,16 +352,6 @@ k1_propagate_weight(K1Args<real> a, Model m) {
 // ==============================================================================================
 __device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global);   // defined with the resampler
 
-struct K2Args {
-    Ctrl* ctrl;
-    const double* parts;
-    double* stats;     // nullable
-    int64_t n_global;
-    int32_t n_parts, nx, inline_moments;
-    double thresh, u_host;
-    uint64_t seed;
-    uint32_t t;
-};
 
 // Combine partial records (max-shifted sums) into one record `out` of the same layout
 // (out[0] = global max, sums relative to it).  All threads of the CTA return the record in smem.
@@ -338,7 +360,7 @@ __device__ inline void combine_partials(const double* parts, int n_parts, int ps
     const int tid = threadIdx.x;
     double m = -INFINITY;
     for (int p = tid; p < n_parts; p += kThreads) {
-        double v = parts[(int64_t)p * ps];
+        double v = __ldcg(parts + (int64_t)p * ps);
         m = v > m ? v : m;
     }
     const double M = block_max_256(m, s_tmp);
@@ -348,10 +370,10 @@ __device__ inline void combine_partials(const double* parts, int n_parts, int ps
     for (int k = 0; k < 20; ++k) acc[k] = 0;
     for (int p = tid; p < n_parts; p += kThreads) {     // fixed record -> thread assignment
         const double* r = parts + (int64_t)p * ps;
-        const double sc = exp(r[0] - Mref);             // r[0] = -inf -> 0
+        const double sc = exp(__ldcg(r) - Mref);        // r[0] = -inf -> 0
 #pragma unroll
         for (int k = 1; k < 20; ++k)
-            if (k < ps) acc[k] = fma(r[k], k == 2 ? sc * sc : sc, acc[k]);   // sum e^2 scales with the square
+            if (k < ps) acc[k] = fma(__ldcg(r + k), k == 2 ? sc * sc : sc, acc[k]);   // sum e^2 scales with the square
     }
 #pragma unroll
     for (int k = 1; k < 20; ++k) {
@@ -372,9 +394,9 @@ __global__ void __launch_bounds__(kThreads) k2_reduce_partials(const double* par
     if (threadIdx.x < ps) out[threadIdx.x] = s_out[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
-    __shared__ double s_out[32];
-    __shared__ double s_tmp[kWarps];
+// K2 body: combine the partial records, publish normaliser / ESS / decision / u (+ weighted moments).
+// Runs in one 256-thread CTA: the stand-alone kernel below, or the last CTA of K1 to finish.
+__device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp) {
     const int ps = a.inline_moments ? partial_stride(a.nx) : 3;
     combine_partials(a.parts, a.n_parts, ps, s_out, s_tmp);
     if (threadIdx.x != 0) return;
@@ -418,6 +440,12 @@ __global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
                 }
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
+    __shared__ double s_out[32];
+    __shared__ double s_tmp[kWarps];
+    finalize_body(a, s_out, s_tmp);
 }
 
 // ==============================================================================================
@@ -504,6 +532,13 @@ __device__ inline int64_t outputs_below(unsigned long long C, const SearchParams
     return e;
 }
 
+struct FinishArgs {
+    double* stats;              // stats row (nullable)
+    const double* mom_parts;    // n_mom_parts records of moment_stride(nx) doubles
+    int32_t n_mom_parts, nx, inline_moments, no_moments;
+    int64_t n_global;
+};
+
 template <typename real> struct K3Args {
     Ctrl* ctrl;
     const real* wsrc;           // log-weights (or linear normalised weights)
@@ -521,6 +556,10 @@ template <typename real> struct K3Args {
     int32_t rank;
     int64_t n, n_global, offset, ld, shard_n;
     int32_t force;              // ignore ctrl->do_resample (stand-alone use)
+    int64_t n_tiles;
+    int32_t fuse_finish;        // the last CTA to finish also runs finish_body(fin)
+    unsigned int* ticket;       // arrival counter for fuse_finish (zero between launches)
+    FinishArgs fin;
 };
 
 // Tile geometry: THREADS threads own IPT consecutive items each (fp32: 256 x 16 = 4096-particle
@@ -665,20 +704,28 @@ __global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_tile_totals(const C
     }
 }
 
-// single-CTA exclusive scan of the tile totals (integer, exact); also emits the shard total
+// single-CTA exclusive scan of the tile totals (integer, exact); also emits the shard total.
+// 1024 threads x 16 consecutive tiles per pass: all loads of a pass are in flight together, one
+// CTA-wide scan per 16 K tiles.
 __global__ void __launch_bounds__(1024) k3a_scan_tiles(const Ctrl* ctrl, ulonglong2* tiles, int64_t n_tiles,
                                                       unsigned long long offset, unsigned long long* total_out,
                                                       int force) {
+    constexpr int PER = 16;
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_carry;
     if (!force && !ctrl->do_resample) { if (total_out && threadIdx.x == 0) *total_out = 0ull; return; }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = offset;
     __syncthreads();
-    for (int64_t base = 0; base < n_tiles; base += 1024) {
-        const int64_t i = base + tid;
-        const unsigned long long v = i < n_tiles ? tiles[i].x : 0ull;
-        unsigned long long inc = v;
+    for (int64_t base = 0; base < n_tiles; base += 1024 * PER) {
+        const int64_t i0 = base + (int64_t)tid * PER;
+        unsigned long long v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) v[k] = (i0 + k < n_tiles) ? tiles[i0 + k].x : 0ull;
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { const unsigned long long t = v[k]; v[k] = sum; sum += t; }   // local exclusive
+        unsigned long long inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -694,7 +741,9 @@ __global__ void __launch_bounds__(1024) k3a_scan_tiles(const Ctrl* ctrl, ulonglo
             tot += t;
         }
         const unsigned long long carry = s_carry;
-        if (i < n_tiles) tiles[i].y = carry + wex + inc - v;
+        const unsigned long long ex = carry + wex + inc - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) if (i0 + k < n_tiles) tiles[i0 + k].y = ex + v[k];
         __syncthreads();
         if (tid == 0) s_carry = carry + tot;
         __syncthreads();
@@ -702,8 +751,79 @@ __global__ void __launch_bounds__(1024) k3a_scan_tiles(const Ctrl* ctrl, ulonglo
     if (total_out && tid == 0) *total_out = s_carry - offset;
 }
 
+// ---- fused "finish step" (also a stand-alone kernel below): post-resample moments from the
+// per-CTA partial records, buffer flip, moment-shift refresh.  Runs in ONE CTA (any size that is
+// a multiple of 32, <= 1024).
+
+__device__ inline void finish_body(Ctrl* ctrl, const FinishArgs& f, double (*s_w)[16], double* s_m) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int do_res = ctrl->do_resample;
+    if (do_res && f.inline_moments && !f.no_moments && f.stats) {
+        const int nm = moment_stride(f.nx);
+        double acc[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) acc[k] = 0;
+#pragma unroll 2
+        for (int p = tid; p < f.n_mom_parts; p += nthreads) {    // fixed record -> thread assignment
+            const double* r = f.mom_parts + (int64_t)p * nm;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) if (k < nm) acc[k] += __ldcg(r + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 14; ++k) {
+            if (k < nm) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) s_w[warp][k] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nm) {
+            double t = 0;
+            for (int w = 0; w < nwarps; ++w) t += s_w[w][tid];
+            s_m[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double* mean = f.stats + SMC_STATS_HEADER;
+            double* cov = mean + f.nx;
+            const double inv = 1.0 / (double)f.n_global;
+            double m1[kFusedNxMax];
+            for (int d = 0; d < f.nx; ++d) { m1[d] = s_m[d] * inv; mean[d] = ctrl->shift[d] + m1[d]; }
+            int k = f.nx;
+            for (int d = 0; d < f.nx; ++d)
+                for (int d2 = 0; d2 <= d; ++d2) {
+                    double v = s_m[k++] * inv - m1[d] * m1[d2];
+                    cov[d * f.nx + d2] = v;
+                    cov[d2 * f.nx + d] = v;
+                }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (do_res) { ctrl->cur ^= 1; ctrl->uniform = 1; }
+        if (f.stats && !f.no_moments)
+            for (int d = 0; d < f.nx && d < kMaxNx; ++d) ctrl->shift[d] = f.stats[SMC_STATS_HEADER + d];
+    }
+}
+
+// Resident CTAs per SM of the resampler (shared memory: (1 + NXF) tiles + the id window)
+template <typename real, int NXF> struct K3Occ {
+    static constexpr int value = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
+};
+
+// K3 proper.  Persistent grid: CTA b handles tiles b, b + grid, ... (static assignment, so the
+// per-CTA moment partials are reproducible).  Per tile:
+//   A  coalesced load of the tile's log-weights -> shared (16-byte swizzle)            | S1
+//      cp.async of the tile's particles -> shared (waited for at S3)
+//   B  blocked read-back, fixed-point quantisation, thread/warp/CTA inclusive scan      | S2
+//   C  output boundaries e[k] = #{positions below the CDF value after item k} (32-bit, branch-free;
+//      the exact fp64 predicate only when a position lies within round-off of a CDF value)
+//   D  expansion: every item stores its local id into the u16 window slots of its offspring   | S3, S4
+//      (direct stores, bank-swizzled; tiles with a very heavy item or more than W outputs take the
+//      marker + max-scan route, which costs O(window) whatever the skew)
+//   E  copy-out: window slot -> particle payload from shared -> coalesced global stores, moments
 template <typename real, int NXF, bool LINEAR_W>
-__global__ void __launch_bounds__(K3Geom<real>::THREADS, (sizeof(real) == 4 && NXF <= 2) ? 4 : 2)
+__global__ void __launch_bounds__(K3Geom<real>::THREADS, K3Occ<real, NXF>::value)
 k3_resample(K3Args<real> a) {
     using G = K3Geom<real>;
     using unit = typename G::unit;
@@ -711,35 +831,37 @@ k3_resample(K3Args<real> a) {
     constexpr int IPT = G::IPT, EPU = G::EPU;
     constexpr int TILE = kK3Threads * IPT;
     constexpr int UPT = IPT / EPU;                    // 16-byte units per thread (= 4)
-    constexpr int CH = IPT + 2;                       // fill chunk per thread (even)
-    constexpr int W = kK3Threads * CH;                  // output window (tile + 12.5 % / 25 % slack)
+    constexpr int CH = IPT + 2;                       // window slots per thread (even)
+    constexpr int W = kK3Threads * CH;                // output window (tile + 12.5 % / 25 % slack)
     constexpr int NM = NXF + NXF * (NXF + 1) / 2;
+    constexpr int NMS = NM > 0 ? NM : 1;
+    constexpr uint32_t MAXD = 8;                      // direct expansion up to this many offspring per item
     static_assert(UPT == 2 || UPT == 4, "swizzle assumes 2 or 4 16-byte units per thread");
     static_assert(CH % 2 == 0, "fill chunk must be word aligned");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unit* lw_s = reinterpret_cast<unit*>(smem_raw);                       // TILE reals, swizzled
-    unsigned short* out_s = reinterpret_cast<unsigned short*>(smem_raw);  // aliases lw_s (W * 2 B)
     real* x_s = reinterpret_cast<real*>(smem_raw + sizeof(real) * TILE);  // NXF * TILE reals
+    unsigned short* ids = reinterpret_cast<unsigned short*>(smem_raw + sizeof(real) * TILE * (1 + NXF));
     __shared__ unsigned long long s_warp_tot[kK3Warps];
     __shared__ uint32_t s_E[2];
     __shared__ int s_wmax[kK3Warps];
-    __shared__ double s_mom[kK3Warps][NM > 0 ? NM : 1];
+    __shared__ double s_mom[kK3Warps][16];
+    __shared__ double s_m[16];
+    __shared__ int s_last;
 
     Ctrl* ctrl = a.ctrl;
-    if (!a.force && !ctrl->do_resample) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!a.force && !ctrl->do_resample) {
+        // nothing to resample: only the moment-shift refresh of the fused finish remains
+        if (a.fuse_finish && blockIdx.x == 0 && tid == 0 && a.fin.stats && !a.fin.no_moments)
+            for (int d = 0; d < a.fin.nx && d < kMaxNx; ++d) ctrl->shift[d] = a.fin.stats[SMC_STATS_HEADER + d];
+        return;
+    }
     const int cur = ctrl->cur;
     const real* xsrc = cur ? a.x1 : a.x0;
     real* xdst = cur ? a.dst0 : a.dst1;
     real* const* peer = cur ? a.peer0 : a.peer1;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int64_t tile_base = tile * TILE;
-    // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded);
-    // loaded first so that its latency hides behind the tile loads
-    unsigned long long tile_prefix = a.state[tile].y + a.cdf_offset;
-    if (a.totals) for (int r = 0; r < a.rank; ++r) tile_prefix += a.totals[r];
 
     const SearchParams sp = load_search(ctrl, a.n_global);
     FastSearch fs;
@@ -750,211 +872,194 @@ k3_resample(K3Args<real> a) {
     Quant<real> quant;
     quant.init(sp.F, LINEAR_W ? 0.0 : ctrl->lw_ref);      // weight N w = exp(lw - (log_norm - log N))
     const real n_real = (real)a.n_global;
+    unsigned long long shard_prefix = a.cdf_offset;
+    if (a.totals) for (int r = 0; r < a.rank; ++r) shard_prefix += a.totals[r];
 
-    // ---- phase A: coalesced loads -> shared ------------------------------------------------
-    // particle payload: asynchronous global->shared copies (LDGSTS, no register staging); they are
-    // only awaited after the look-back, so their HBM latency overlaps the scan
-    const bool interior = tile_base + TILE <= a.n;          // no per-element bounds checks needed
-    const int n_in_tile = interior ? TILE : (int)(a.n - tile_base);
-    if (NXF > 0) {
-#pragma unroll
-        for (int r = 0; r < UPT; ++r) {
-            const int f = r * kK3Threads + tid;
-            if (f * EPU < n_in_tile) {
-#pragma unroll
-                for (int d = 0; d < NXF; ++d) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + f * EPU);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst),
-                                 "l"(xsrc + d * a.ld + tile_base + f * EPU) : "memory");
-                }
-            }
-        }
-    }
-    {
-        const unit* wtile = reinterpret_cast<const unit*>(a.wsrc + tile_base);
-        if (interior) {
-            unit v[UPT];
-#pragma unroll
-            for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kK3Threads + tid];
-#pragma unroll
-            for (int r = 0; r < UPT; ++r) {
-                const int f = r * kK3Threads + tid;
-                lw_s[f ^ ((f >> 3) & (UPT - 1))] = v[r];
-            }
-        } else {
-            const real fill = LINEAR_W ? real(0) : real(-INFINITY);
-#pragma unroll
-            for (int r = 0; r < UPT; ++r) {
-                const int f = r * kK3Threads + tid;
-                real tmp[EPU];
-#pragma unroll
-                for (int j = 0; j < EPU; ++j) tmp[j] = fill;
-                if (f * EPU < n_in_tile) {
-                    unit_to_array(wtile[f], tmp);
-#pragma unroll
-                    for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
-                }
-                real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
-#pragma unroll
-                for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: fixed-point weights, block scan, look-back ---------------------------------
-    unsigned long long c[IPT];
-    unsigned long long run = 0;
-    {
-        double runf = 0.0;
-#pragma unroll
-        for (int k = 0; k < UPT; ++k) {
-            const int g = UPT * tid + k;
-            real tmp[EPU];
-            unit_to_array(lw_s[g ^ ((g >> 3) & (UPT - 1))], tmp);
-#pragma unroll
-            for (int j = 0; j < EPU; ++j) {
-                if (LINEAR_W) {
-                    real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);   // NaN / negative -> 0, cap at N
-                    run = quant.add(run, v, runf);
-                } else {
-                    run = quant.add_logw(run, tmp[j], runf);
-                }
-                c[k * EPU + j] = run;                        // inclusive within thread
-            }
-        }
-    }
-    unsigned long long incl_w = run;                         // warp inclusive scan of thread totals
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
-        if (lane >= o) incl_w += t;
-    }
-    if (lane == 31) s_warp_tot[warp] = incl_w;
-    __syncthreads();   // also: everyone is done reading lw_s
-    unsigned long long warp_excl = 0, tile_agg = 0;
-#pragma unroll
-    for (int w = 0; w < kK3Warps; ++w) {
-        unsigned long long t = s_warp_tot[w];
-        if (w < warp) warp_excl += t;
-        tile_agg += t;
-    }
-    (void)tile_agg;
-    if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();
-
-    // ---- phase C: output boundaries (32-bit) -------------------------------------------------
-    // e[k] = number of outputs whose stratified position lies below the CDF value after item k
-    const unsigned long long base_b = tile_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
-    uint32_t e_start = fast_outputs_below(base_b, fs, sp);
-    uint32_t e[IPT];
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) e[k] = fast_outputs_below(base_b + c[k], fs, sp);
-    {   // cumsum[-1] = 1.0 clamp (particle_filter.py:163): the globally last particle owns the tail
-        const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;
-        if (j0 + IPT >= a.n_global) {
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) if (j0 + k >= a.n_global - 1) e[k] = fs.n_global;
-        }
-        // the quantised total may exceed N 2^F by round-off: no boundary may pass N
-        // (boundaries are monotone, so one test per thread suffices)
-        if (e[IPT - 1] > fs.n_global) {
-            e_start = e_start < fs.n_global ? e_start : fs.n_global;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) e[k] = e[k] < fs.n_global ? e[k] : fs.n_global;
-        }
-    }
-    // (padding items beyond the shard carry zero weight, hence no outputs of their own)
-    if (tid == 0) s_E[0] = e_start;
-    if (tid == kK3Threads - 1) s_E[1] = e[IPT - 1];
-    __syncthreads();
-    const uint32_t E0 = s_E[0], E1 = s_E[1];
-    const uint32_t count = E1 - E0;
-
-    real macc[NM > 0 ? NM : 1];
-#pragma unroll
-    for (int k = 0; k < (NM > 0 ? NM : 1); ++k) macc[k] = 0;
     real shift[NXF > 0 ? NXF : 1];
 #pragma unroll
     for (int d = 0; d < NXF; ++d) shift[d] = (real)ctrl->shift[d];
+    double macc_d[NMS];
+#pragma unroll
+    for (int k = 0; k < NMS; ++k) macc_d[k] = 0.0;
 
-    for (uint32_t wbase = 0; wbase < count; wbase += W) {
-        // 1. clear the window
+    // window slot of output position s: two pad slots per IPT positions, so that the CTA-wide
+    // stores of phase D (lane stride = IPT positions) fall into distinct banks
+    auto slot = [](uint32_t s) -> uint32_t { return s + ((s / (uint32_t)IPT) << 1); };
+
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int64_t tile_base = tile * TILE;
+        // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded);
+        // loaded first so that its latency hides behind the tile loads
+        const unsigned long long tile_prefix = a.state[tile].y + shard_prefix;
+        const bool interior = tile_base + TILE <= a.n;          // no per-element bounds checks needed
+        const int n_in_tile = interior ? TILE : (int)(a.n - tile_base);
+
+        // ---- phase A: coalesced log-weight loads -> shared --------------------------------------
         {
-            uint4* o4 = reinterpret_cast<uint4*>(out_s);
-            for (int p = tid; p < W * 2 / 16; p += kK3Threads) o4[p] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        // 2. head markers (local index + 1) at the first output of every item with offspring
-        if (count <= (uint32_t)W) {            // common case: the whole tile fits one window
-            uint32_t r0 = e_start - E0;
+            const unit* wtile = reinterpret_cast<const unit*>(a.wsrc + tile_base);
+            if (interior) {
+                unit v[UPT];
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                const uint32_t r1 = e[k] - E0;
-                if (r1 > r0) out_s[r0] = (unsigned short)(tid * IPT + k + 1);
-                r0 = r1;
-            }
-        } else {
-            uint32_t r0 = e_start - E0;
+                for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kK3Threads + tid];
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                const uint32_t r1 = e[k] - E0;
-                if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
-                    const uint32_t pos = (r0 > wbase ? r0 : wbase) - wbase;
-                    out_s[pos] = (unsigned short)(tid * IPT + k + 1);
+                for (int r = 0; r < UPT; ++r) {
+                    const int f = r * kK3Threads + tid;
+                    lw_s[f ^ ((f >> 3) & (UPT - 1))] = v[r];
                 }
-                r0 = r1;
+            } else {
+                const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+#pragma unroll
+                for (int r = 0; r < UPT; ++r) {
+                    const int f = r * kK3Threads + tid;
+                    real tmp[EPU];
+#pragma unroll
+                    for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+                    if (f * EPU < n_in_tile) {
+                        unit_to_array(wtile[f], tmp);
+#pragma unroll
+                        for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
+                    }
+                    real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
+#pragma unroll
+                    for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
+                }
             }
         }
-        __syncthreads();
-        // 3. forward fill = inclusive max-scan (markers increase with position)
-        {
-            uint32_t* o32 = reinterpret_cast<uint32_t*>(out_s) + tid * (CH / 2);
-            uint32_t wv[CH / 2];
-            int tmax = 0;
+        __syncthreads();   // S1: lw_s complete; every thread has finished the previous tile's copy-out
+        // particle payload: asynchronous global->shared copies (LDGSTS, no register staging), issued
+        // only now because x_s was still being gathered from until S1; awaited at S3
+        if (NXF > 0) {
 #pragma unroll
-            for (int k = 0; k < CH / 2; ++k) {
-                wv[k] = o32[k];
-                int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
-                tmax = max(tmax, max(lo, hi));
-            }
-            int inc = tmax;
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * kK3Threads + tid;
+                if (f * EPU < n_in_tile) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc = max(inc, t);
-            }
-            int excl = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane == 0) excl = 0;
-            if (lane == 31) s_wmax[warp] = inc;
-            __syncthreads();
-            int carry = excl;
-#pragma unroll
-            for (int w = 0; w < kK3Warps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
-#pragma unroll
-            for (int k = 0; k < CH / 2; ++k) {
-                int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
-                lo = max(lo, carry); carry = lo;
-                hi = max(hi, carry); carry = hi;
-                o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+                    for (int d = 0; d < NXF; ++d) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + f * EPU);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst),
+                                     "l"(xsrc + d * a.ld + tile_base + f * EPU) : "memory");
+                    }
+                }
             }
         }
-        __syncthreads();
-        // 4. coalesced copy-out with the shared-memory-staged gather
+
+        // ---- phase B: fixed-point weights, thread / warp / CTA scan -------------------------------
+        unsigned long long c[IPT];
+        unsigned long long run = 0;
         {
-            const uint32_t rem = count - wbase;
-            const int cnt = rem < (uint32_t)W ? (int)rem : W;
-            const int64_t g0 = (int64_t)E0 + wbase;                  // global index of window slot 0
+            double runf = 0.0;
+#pragma unroll
+            for (int k = 0; k < UPT; ++k) {
+                const int g = UPT * tid + k;
+                real tmp[EPU];
+                unit_to_array(lw_s[g ^ ((g >> 3) & (UPT - 1))], tmp);
+#pragma unroll
+                for (int j = 0; j < EPU; ++j) {
+                    if (LINEAR_W) {
+                        real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);   // NaN / negative -> 0, cap at N
+                        run = quant.add(run, v, runf);
+                    } else {
+                        run = quant.add_logw(run, tmp[j], runf);
+                    }
+                    c[k * EPU + j] = run;                        // inclusive within thread
+                }
+            }
+        }
+        unsigned long long incl_w = run;                         // warp inclusive scan of thread totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
+            if (lane >= o) incl_w += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl_w;
+        __syncthreads();   // S2
+        unsigned long long warp_excl = 0;
+#pragma unroll
+        for (int w = 0; w < kK3Warps; ++w) {
+            unsigned long long t = s_warp_tot[w];
+            if (w < warp) warp_excl += t;
+        }
+
+        // ---- phase C: output boundaries (32-bit) -------------------------------------------------
+        // e[k] = number of outputs whose stratified position lies below the CDF value after item k
+        const unsigned long long base_b = tile_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
+        uint32_t e_start, e[IPT];
+        {
+            uint32_t near = 0;
+            auto fast_e = [&](unsigned long long Cb) -> uint32_t {
+                const uint32_t hi = (uint32_t)(Cb >> 32), lo = (uint32_t)Cb;
+                const uint32_t frac_hi = __funnelshift_r(lo, hi, fs.sh);    // bits [F-32, F) of Cb
+                near |= (frac_hi + fs.m32 <= 2u * fs.m32) ? 1u : 0u;        // near 0 or near 2^32 (wraps)
+                return hi >> fs.sh;
+            };
+            e_start = fast_e(base_b);
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) e[k] = fast_e(base_b + c[k]);
+            if (near) {   // rare (~1e-6 per thread): redo with the exact predicate where needed; the
+                          // running CDF is recomputed from shared memory so that c[] need not stay live
+                e_start = fast_outputs_below(base_b, fs, sp);
+                unsigned long long run2 = 0;
+                double runf2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < UPT; ++k) {
+                    const int g = UPT * tid + k;
+                    real tmp[EPU];
+                    unit_to_array(lw_s[g ^ ((g >> 3) & (UPT - 1))], tmp);
+#pragma unroll
+                    for (int j = 0; j < EPU; ++j) {
+                        if (LINEAR_W) {
+                            real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);
+                            run2 = quant.add(run2, v, runf2);
+                        } else {
+                            run2 = quant.add_logw(run2, tmp[j], runf2);
+                        }
+                        e[k * EPU + j] = fast_outputs_below(base_b + run2, fs, sp);
+                    }
+                }
+            }
+        }
+        {   // cumsum[-1] = 1.0 clamp (particle_filter.py:163): the globally last particle owns the tail
+            const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;
+            if (j0 + IPT >= a.n_global) {
+#pragma unroll
+                for (int k = 0; k < IPT; ++k) if (j0 + k >= a.n_global - 1) e[k] = fs.n_global;
+            }
+            // the quantised total may exceed N 2^F by round-off: no boundary may pass N
+            // (boundaries are monotone, so one test per thread suffices)
+            if (e[IPT - 1] > fs.n_global) {
+                e_start = e_start < fs.n_global ? e_start : fs.n_global;
+#pragma unroll
+                for (int k = 0; k < IPT; ++k) e[k] = e[k] < fs.n_global ? e[k] : fs.n_global;
+            }
+        }
+        // (padding items beyond the shard carry zero weight, hence no outputs of their own)
+        uint32_t nmax = e[0] - e_start;
+#pragma unroll
+        for (int k = 1; k < IPT; ++k) nmax = max(nmax, e[k] - e[k - 1]);
+        if (tid == 0) s_E[0] = e_start;
+        if (tid == kK3Threads - 1) s_E[1] = e[IPT - 1];
+        if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
+        const int heavy = __syncthreads_or(nmax > MAXD);   // S3: also publishes s_E and x_s
+        const uint32_t E0 = s_E[0], E1 = s_E[1];
+        const uint32_t count = E1 - E0;
+        const bool direct = !heavy && count <= (uint32_t)W;
+
+        real macc[NMS];
+#pragma unroll
+        for (int k = 0; k < NMS; ++k) macc[k] = 0;
+
+        // copy-out of `cnt` window slots starting at global output index g0 (SWZ: slots are swizzled)
+        auto copy_out = [&](const int64_t g0, const int cnt, const bool swz) {
             if (!peer) {
                 real* dwin = xdst + (g0 - a.offset) + tid;           // this thread's first output slot
                 int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) + tid : nullptr;
-                const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // markers are index + 1
-                const unsigned short* mk = out_s + tid;
+                const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // ids are index + 1
                 const real* xg = x_s - 1;                            // ditto
 #pragma unroll
                 for (int it = 0; it < CH; ++it) {
-                    if (it * kK3Threads + tid < cnt) {
-                        const int li1 = (int)mk[it * kK3Threads];       // local ancestor + 1
+                    const uint32_t p = it * kK3Threads + tid;
+                    if ((int)p < cnt) {
+                        const int li1 = (int)ids[swz ? slot(p) : p];    // local ancestor + 1
                         if (awin) awin[it * kK3Threads] = abase + li1;
                         if (NXF > 0) {
                             real xv[NXF > 0 ? NXF : 1];
@@ -975,7 +1080,7 @@ k3_resample(K3Args<real> a) {
                 }
             } else {
                 for (int p = tid; p < cnt; p += kK3Threads) {          // cross-shard migration path
-                    const int li = (int)out_s[p] - 1;
+                    const int li = (int)ids[swz ? slot((uint32_t)p) : (uint32_t)p] - 1;
                     const int64_t gi = g0 + p;
                     const int64_t r = gi / a.shard_n;
                     real* dbase = peer[r];
@@ -997,14 +1102,96 @@ k3_resample(K3Args<real> a) {
                     }
                 }
             }
+        };
+
+        if (direct) {
+            // ---- phase D (common case): every item writes its id straight into its offspring's slots
+            uint32_t r0 = e_start - E0;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const uint32_t r1 = e[k] - E0;
+                const unsigned short v = (unsigned short)(tid * IPT + k + 1);
+                if (r0 < r1) {
+                    ids[slot(r0)] = v;
+                    if (r0 + 1 < r1) {
+                        ids[slot(r0 + 1)] = v;
+                        for (uint32_t r = r0 + 2; r < r1; ++r) ids[slot(r)] = v;
+                    }
+                }
+                r0 = r1;
+            }
+            __syncthreads();   // S4
+            copy_out((int64_t)E0, (int)count, true);
+        } else {
+            // ---- phase D (skewed tile): head markers + max-scan fill, window by window ----------
+            for (uint32_t wbase = 0; wbase < count; wbase += W) {
+                {
+                    uint4* o4 = reinterpret_cast<uint4*>(ids);
+                    for (int p = tid; p < W * 2 / 16; p += kK3Threads) o4[p] = make_uint4(0, 0, 0, 0);
+                }
+                __syncthreads();
+                {   // head markers (local index + 1) at the first output of every item with offspring
+                    uint32_t r0 = e_start - E0;
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        const uint32_t r1 = e[k] - E0;
+                        if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
+                            const uint32_t pos = (r0 > wbase ? r0 : wbase) - wbase;
+                            ids[pos] = (unsigned short)(tid * IPT + k + 1);
+                        }
+                        r0 = r1;
+                    }
+                }
+                __syncthreads();
+                {   // forward fill = inclusive max-scan (markers increase with position)
+                    uint32_t* o32 = reinterpret_cast<uint32_t*>(ids) + tid * (CH / 2);
+                    uint32_t wv[CH / 2];
+                    int tmax = 0;
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) {
+                        wv[k] = o32[k];
+                        int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                        tmax = max(tmax, max(lo, hi));
+                    }
+                    int inc = tmax;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc = max(inc, t);
+                    }
+                    int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+                    if (lane == 0) excl = 0;
+                    if (lane == 31) s_wmax[warp] = inc;
+                    __syncthreads();
+                    int carry = excl;
+#pragma unroll
+                    for (int w = 0; w < kK3Warps; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) {
+                        int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                        lo = max(lo, carry); carry = lo;
+                        hi = max(hi, carry); carry = hi;
+                        o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+                    }
+                }
+                __syncthreads();
+                const uint32_t rem = count - wbase;
+                copy_out((int64_t)E0 + wbase, rem < (uint32_t)W ? (int)rem : W, false);
+                __syncthreads();
+            }
         }
-        __syncthreads();
+        if (NM > 0) {
+#pragma unroll
+            for (int k = 0; k < NMS; ++k) macc_d[k] += (double)macc[k];
+        }
     }
-    // ---- per-tile post-resample moment partials -------------------------------------------
+
+    // ---- per-CTA post-resample moment partials (+ the fused finish in the last CTA to arrive) ----
     if (NM > 0 && a.mom_parts) {
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < NM; ++k) {
-            double v = warp_sum((double)macc[k]);
+            double v = warp_sum(macc_d[k]);
             if (lane == 0) s_mom[warp][k] = v;
         }
         __syncthreads();
@@ -1012,7 +1199,18 @@ k3_resample(K3Args<real> a) {
             double s = 0;
 #pragma unroll
             for (int w = 0; w < kK3Warps; ++w) s += s_mom[w][tid];
-            a.mom_parts[tile * NM + tid] = s;
+            a.mom_parts[(int64_t)blockIdx.x * NM + tid] = s;
+        }
+    }
+    if (a.fuse_finish) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finish_body(ctrl, a.fin, s_mom, s_m);
+            if (tid == 0) *a.ticket = 0u;
         }
     }
 }
@@ -1021,60 +1219,10 @@ k3_resample(K3Args<real> a) {
 // finish step: post-resample moments, buffer flip, shift refresh
 // ==============================================================================================
 constexpr int kFinishThreads = 1024;
-__global__ void __launch_bounds__(kFinishThreads) k_finish_step(Ctrl* ctrl, double* stats, const double* mom_parts,
-                                                               int n_mom_parts, int nx, int inline_moments,
-                                                               int64_t n_global, int no_moments) {
+__global__ void __launch_bounds__(kFinishThreads) k_finish_step(Ctrl* ctrl, FinishArgs f) {
     __shared__ double s_w[kFinishThreads / 32][16];
     __shared__ double s_m[16];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int do_res = ctrl->do_resample;
-    if (do_res && inline_moments && !no_moments && stats) {
-        const int nm = moment_stride(nx);
-        // fixed assignment record -> thread, independent loads issued back to back
-        double acc[14];
-#pragma unroll
-        for (int k = 0; k < 14; ++k) acc[k] = 0;
-#pragma unroll 4
-        for (int p = tid; p < n_mom_parts; p += kFinishThreads) {
-            const double* r = mom_parts + (int64_t)p * nm;
-#pragma unroll
-            for (int k = 0; k < 14; ++k) if (k < nm) acc[k] += r[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 14; ++k) {
-            if (k < nm) {
-                const double v = warp_sum(acc[k]);
-                if (lane == 0) s_w[warp][k] = v;
-            }
-        }
-        __syncthreads();
-        if (tid < nm) {
-            double t = 0;
-            for (int w = 0; w < kFinishThreads / 32; ++w) t += s_w[w][tid];
-            s_m[tid] = t;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double* mean = stats + SMC_STATS_HEADER;
-            double* cov = mean + nx;
-            const double inv = 1.0 / (double)n_global;
-            double m1[kFusedNxMax];
-            for (int d = 0; d < nx; ++d) { m1[d] = s_m[d] * inv; mean[d] = ctrl->shift[d] + m1[d]; }
-            int k = nx;
-            for (int d = 0; d < nx; ++d)
-                for (int d2 = 0; d2 <= d; ++d2) {
-                    double v = s_m[k++] * inv - m1[d] * m1[d2];
-                    cov[d * nx + d2] = v;
-                    cov[d2 * nx + d] = v;
-                }
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (do_res) { ctrl->cur ^= 1; ctrl->uniform = 1; }
-        if (stats && !no_moments)
-            for (int d = 0; d < nx && d < kMaxNx; ++d) ctrl->shift[d] = stats[SMC_STATS_HEADER + d];
-    }
+    finish_body(ctrl, f, s_w, s_m);
 }
 
 __global__ void __launch_bounds__(kThreads) k_reduce_moment_partials(const Ctrl* ctrl, const double* mom_parts,
@@ -1340,7 +1488,7 @@ int stage(const Launch& l, int slot, const double* host, int count, double** dev
 
 template <typename real, class Model>
 int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, const void* noise_dev, uint64_t seed,
-              int64_t t) {
+              int64_t t, const K2Args* fin) {
     const smc_sir_desc* d = l.d;
     K1Args<real> a;
     a.ctrl = l.ctrl();
@@ -1352,6 +1500,14 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
     a.parts = l.k1_parts();
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
     a.seed = seed; a.t = (uint32_t)t; a.mode = mode & 3;
+    a.keys = philox_expand(seed);
+    a.fuse_finalize = 0; a.ticket = l.ticket();
+    memset(&a.fin, 0, sizeof(a.fin));
+    if (fin && (mode & SMC_MODE_WEIGHT)) {
+        a.fuse_finalize = 1;
+        a.fin = *fin;
+        a.fin.ctrl = l.ctrl(); a.fin.parts = l.k1_parts(); a.fin.n_parts = (int)l.L.n_k1_blocks;
+    }
     // mode bit 4 (internal): the caller knows the step resamples -> skip the pre-resample moments
     if (mode & 4)
         k1_propagate_weight<real, Model, false><<<(unsigned)l.L.n_k1_blocks, kThreads, 0, l.st>>>(a, m);
@@ -1362,14 +1518,15 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
 }
 
 template <typename real> int dispatch_k1(const Launch& l, int model_id, const double* p, int np, int mode,
-                                         const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t) {
+                                         const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t,
+                                         const K2Args* fin) {
     const smc_sir_desc* d = l.d;
     if (model_id == SMC_MODEL_STOCH_VOL) {
         // params: alpha, lq (= chol(Q)), beta, lr (= chol(R + 1e-12))
         SMC_REQUIRE(np == 4 && d->nx == 1 && d->nz == 1, "smc: STOCH_VOL needs 4 params and nx = nz = 1");
         StochVolModel<real> m;
         m.alpha = (real)p[0]; m.lq = (real)p[1]; m.beta = (real)p[2]; m.rinv = (real)(1.0 / p[3]);
-        return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t);
+        return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin);
     }
     if (model_id == SMC_MODEL_LINEAR_GAUSSIAN) {
         // params: A (nx*nx), Lq (nx*nx lower), H (nz*nx), LRinv (nz*nz lower), all row-major
@@ -1383,7 +1540,7 @@ template <typename real> int dispatch_k1(const Launch& l, int model_id, const do
             for (int i = 0; i < NX_ * NX_; ++i) m.Lq[i] = (real)*q++;                             \
             for (int i = 0; i < NZ_ * NX_; ++i) m.H[i] = (real)*q++;                              \
             for (int i = 0; i < NZ_ * NZ_; ++i) m.LRinv[i] = (real)*q++;                          \
-            return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t);                        \
+            return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin);                     \
         }
         SMC_LG_CASE(1, 1) SMC_LG_CASE(2, 1) SMC_LG_CASE(2, 2) SMC_LG_CASE(4, 1) SMC_LG_CASE(4, 2) SMC_LG_CASE(4, 4)
 #undef SMC_LG_CASE
@@ -1393,10 +1550,34 @@ template <typename real> int dispatch_k1(const Launch& l, int model_id, const do
     SMC_REQUIRE(false, "smc: unknown model id %d", model_id);
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// persistent resampler grid (also the number of post-resample moment records it writes)
+inline int k3_occupancy(int dtype, int nxf) {
+    if (dtype == SMC_F32) return nxf <= 1 ? 4 : (nxf == 2 ? 3 : 2);
+    return nxf <= 1 ? 3 : 2;
+}
+inline int64_t k3_grid(int64_t n_tiles, int dtype, int nxf) {
+    const int64_t g = (int64_t)sm_count() * k3_occupancy(dtype, nxf);
+    return n_tiles < g ? n_tiles : g;
+}
+
 template <typename real, int NXF, bool LIN>
-int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
+int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
     using G = K3Geom<real>;
-    const size_t smem = sizeof(real) * G::THREADS * G::IPT * (1 + NXF);
+    static_assert(K3Occ<real, NXF>::value >= 1, "occupancy table");
+    constexpr int W = G::THREADS * (G::IPT + 2);
+    constexpr size_t ids_bytes = ((size_t)(W + 2 * (W / G::IPT) + 8) * 2 + 15) & ~size_t(15);
+    const size_t smem = sizeof(real) * G::THREADS * G::IPT * (1 + NXF) + ids_bytes;
     auto kern = k3_resample<real, NXF, LIN>;
     static bool attr_set = false;   // one flag per template instantiation
     if (!attr_set) {
@@ -1405,7 +1586,10 @@ int launch_k3_t(const Launch& l, const K3Args<real>& a, int64_t n_tiles) {
                                             cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    kern<<<(unsigned)n_tiles, G::THREADS, smem, l.st>>>(a);
+    a.n_tiles = n_tiles;
+    const int64_t grid = k3_grid(n_tiles, sizeof(real) == 4 ? SMC_F32 : SMC_F64, NXF);
+    if (a.fuse_finish) a.fin.n_mom_parts = (int)grid;
+    kern<<<(unsigned)grid, G::THREADS, smem, l.st>>>(a);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1430,7 +1614,7 @@ int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int force, 
 template <typename real>
 int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
               void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
-              int rank = 0, bool run_prepass = true) {
+              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr) {
     const smc_sir_desc* d = l.d;
     ulonglong2* tiles = reinterpret_cast<ulonglong2*>(l.agg());
     if (run_prepass) {
@@ -1456,6 +1640,13 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
     a.shard_n = n_shards > 0 ? d->n_global / n_shards : d->n_global;
     a.force = force;
+    a.fuse_finish = 0; a.ticket = l.ticket() + 1;
+    memset(&a.fin, 0, sizeof(a.fin));
+    if (fin) {
+        a.fuse_finish = 1;
+        a.fin = *fin;
+        a.fin.mom_parts = l.mom_parts();
+    }
     const int64_t nt = l.L.n_tiles;
     if (linear_w) {
         SMC_REQUIRE(nxf == 0, "smc: linear-weight resampling is ancestors-only");
@@ -1516,17 +1707,25 @@ int smc_sir_init_gaussian(const smc_sir_desc* d, const double* mean_host, const 
     return 0;
 }
 
-int smc_sir_propagate_weight(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
-                             int32_t mode, const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t,
-                             void* stream) {
+static int sir_propagate_weight_impl(const smc_sir_desc* d, int32_t model_id, const double* params_host,
+                                    int32_t n_params, int32_t mode, const double* z_dev, const void* noise_dev,
+                                    uint64_t seed, int64_t t, void* stream, const K2Args* fin) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     SMC_REQUIRE((mode & 3) >= 1 && mode <= 7, "smc: bad mode %d", mode);
     SMC_REQUIRE(!(mode & SMC_MODE_WEIGHT) || z_dev, "smc: z_dev required when weighting");
     SMC_REQUIRE(params_host != nullptr, "smc: params missing");
     SMC_REQUIRE(!(d->flags & SMC_FLAG_GENERIC_MOMENTS), "smc: fused K1 carries inline moments; clear GENERIC_MOMENTS");
-    return d->dtype == SMC_F32 ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t)
-                               : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t);
+    return d->dtype == SMC_F32
+               ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, fin)
+               : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, fin);
+}
+
+int smc_sir_propagate_weight(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
+                             int32_t mode, const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t,
+                             void* stream) {
+    return sir_propagate_weight_impl(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream,
+                                     nullptr);
 }
 
 int smc_bridge_predict(const smc_sir_desc* d, const void* gx_dev, const void* noise_dev, const double* Lq_host,
@@ -1619,20 +1818,22 @@ int smc_sir_shard_weight_total(const smc_sir_desc* d, uint64_t* total_dev, void*
                                : launch_prepass<double>(l, false, d->logw_dev, 0, (unsigned long long*)total_dev);
 }
 
-int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* stats_row_dev, void* const* peer_x_dev,
-                     int32_t n_shards, void* stream) {
+static int sir_resample_impl(const smc_sir_desc* d, uint64_t cdf_offset_fix, void* const* peer_x_dev,
+                            int32_t n_shards, void* stream, const FinishArgs* fin) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
-    (void)stats_row_dev;
     const bool fused = d->nx <= kFusedNxMax;
     const int nxf = fused ? d->nx : 0;
     SMC_REQUIRE(fused || d->ancestors_dev, "smc: nx > %d needs an ancestors buffer for the two-pass gather", kFusedNxMax);
     SMC_REQUIRE(!peer_x_dev || fused, "smc: cross-shard migration requires nx <= %d", kFusedNxMax);
     SMC_REQUIRE(!peer_x_dev || (n_shards > 0 && d->n_global % n_shards == 0), "smc: bad shard count");
     const bool want_m = inline_moments(d) && !(d->flags & SMC_FLAG_NO_MOMENTS);
+    SMC_REQUIRE(!fin || fused, "smc: fused finish needs nx <= %d", kFusedNxMax);
     int rc = d->dtype == SMC_F32
-                 ? launch_k3<float>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m)
-                 : launch_k3<double>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m);
+                 ? launch_k3<float>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m, nullptr, 0,
+                                    true, fin)
+                 : launch_k3<double>(l, false, d->logw_dev, nxf, cdf_offset_fix, 0, peer_x_dev, n_shards, want_m, nullptr,
+                                     0, true, fin);
     if (rc) return rc;
     if (!fused) {
         const unsigned grid = (unsigned)cdiv64(d->n, kThreads);
@@ -1647,6 +1848,12 @@ int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* sta
         SMC_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+int smc_sir_resample(const smc_sir_desc* d, uint64_t cdf_offset_fix, double* stats_row_dev, void* const* peer_x_dev,
+                     int32_t n_shards, void* stream) {
+    (void)stats_row_dev;
+    return sir_resample_impl(d, cdf_offset_fix, peer_x_dev, n_shards, stream, nullptr);
 }
 
 int smc_sir_resample_sharded(const smc_sir_desc* d, const uint64_t* totals_dev, int32_t rank, int32_t n_shards,
@@ -1670,7 +1877,8 @@ int smc_sir_reduce_moment_partials(const smc_sir_desc* d, double* out_dev, void*
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     SMC_REQUIRE(inline_moments(d), "smc: moment partials exist only for nx <= %d", kFusedNxMax);
-    k_reduce_moment_partials<<<1, kThreads, 0, l.st>>>(l.ctrl(), l.mom_parts(), (int)l.L.n_tiles, moment_stride(d->nx),
+    k_reduce_moment_partials<<<1, kThreads, 0, l.st>>>(l.ctrl(), l.mom_parts(),
+                                                      (int)k3_grid(l.L.n_tiles, d->dtype, d->nx), moment_stride(d->nx),
                                                       out_dev);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -1729,24 +1937,68 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
         k_moments_generic_fix<<<1, 32, 0, l.st>>>(l.ctrl(), nx, stats_row_dev);
         SMC_CHECK_CUDA(cudaGetLastError());
     }
-    k_finish_step<<<1, kFinishThreads, 0, l.st>>>(l.ctrl(), stats_row_dev, mom_parts_dev ? mom_parts_dev : l.mom_parts(),
-                                           n_mom_parts > 0 ? n_mom_parts : (int)l.L.n_tiles, d->nx, inl ? 1 : 0,
-                                           d->n_global, no_m);
+    FinishArgs f;
+    f.stats = stats_row_dev;
+    f.mom_parts = mom_parts_dev ? mom_parts_dev : l.mom_parts();
+    f.n_mom_parts = n_mom_parts > 0 ? n_mom_parts : (inl ? (int)k3_grid(l.L.n_tiles, d->dtype, d->nx) : 0);
+    f.nx = d->nx; f.inline_moments = inl ? 1 : 0; f.no_moments = no_m; f.n_global = d->n_global;
+    k_finish_step<<<1, kFinishThreads, 0, l.st>>>(l.ctrl(), f);
     SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int smc_sir_step_weight(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
+                        const double* z_dev, const void* noise_dev, double resample_thresh, double u_host, uint64_t seed,
+                        int64_t t, double* stats_row_dev, void* stream) {
+    SMC_REQUIRE(d != nullptr, "smc: null descriptor");
+    // resample_thresh > 1 means ESS <= N < thresh N: the step certainly resamples, so the weighted
+    // (pre-resample) moments would be overwritten by the post-resample ones and are not accumulated
+    const int mode = SMC_MODE_STEP | (resample_thresh > 1.0 ? 4 : 0);
+    K2Args fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.stats = stats_row_dev; fin.n_global = d->n_global; fin.nx = d->nx;
+    fin.inline_moments = inline_moments(d) ? 1 : 0;
+    fin.thresh = resample_thresh; fin.u_host = u_host; fin.seed = seed; fin.t = (uint32_t)t;
+    return sir_propagate_weight_impl(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream, &fin);
+}
+
+int smc_sir_step_resample(const smc_sir_desc* d, int32_t phases, double* stats_row_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(phases >= 1 && phases <= 3, "smc: phases must be 1 (pre-pass), 2 (resample + finish) or 3");
+    const bool fuse_finish = d->nx <= kFusedNxMax && inline_moments(d) && !(d->flags & SMC_FLAG_POST_MOMENTS_GENERIC);
+    if (!fuse_finish) {
+        SMC_REQUIRE(phases == 3, "smc: the split form needs the fused resampler (nx <= %d)", kFusedNxMax);
+        if (int rc = smc_sir_resample(d, 0, stats_row_dev, nullptr, 0, stream)) return rc;
+        return smc_sir_finish_step(d, stats_row_dev, nullptr, 0, stream);
+    }
+    if (phases & 1) {
+        int rc = d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, 0, nullptr)
+                                     : launch_prepass<double>(l, false, d->logw_dev, 0, nullptr);
+        if (rc) return rc;
+    }
+    if (phases & 2) {
+        FinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.stats = stats_row_dev; f.nx = d->nx; f.inline_moments = 1;
+        f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+        const bool want_m = !(d->flags & SMC_FLAG_NO_MOMENTS);
+        return d->dtype == SMC_F32
+                   ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f)
+                   : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f);
+    }
     return 0;
 }
 
 int smc_sir_step(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
                  const double* z_dev, const void* noise_dev, double resample_thresh, double u_host, uint64_t seed,
                  int64_t t, double* stats_row_dev, void* stream) {
-    // resample_thresh > 1 means ESS <= N < thresh N: the step certainly resamples, so the weighted
-    // (pre-resample) moments would be overwritten by the post-resample ones and are not accumulated
-    const int mode = SMC_MODE_STEP | (resample_thresh > 1.0 ? 4 : 0);
-    if (int rc = smc_sir_propagate_weight(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream))
+    // Four launches per step: K1 (+ finalize in its last CTA), tile pre-pass, tile scan, K3 (+ finish
+    // in its last CTA).
+    if (int rc = smc_sir_step_weight(d, model_id, params_host, n_params, z_dev, noise_dev, resample_thresh, u_host, seed,
+                                     t, stats_row_dev, stream))
         return rc;
-    if (int rc = smc_sir_finalize(d, resample_thresh, u_host, seed, t, stats_row_dev, nullptr, 0, stream)) return rc;
-    if (resample_thresh > 0.0)
-        if (int rc = smc_sir_resample(d, 0, stats_row_dev, nullptr, 0, stream)) return rc;
+    if (resample_thresh > 0.0) return smc_sir_step_resample(d, 3, stats_row_dev, stream);
     return smc_sir_finish_step(d, stats_row_dev, nullptr, 0, stream);
 }
 

@@ -143,6 +143,25 @@ __device__ inline void philox_quad(uint64_t seed, uint64_t quad, uint32_t t, uin
     philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
+// The ten round keys, expanded once on the host and passed by value in the kernel arguments:
+// inside the kernel they are constant-bank operands, so the key schedule costs no instructions.
+struct PhiloxKeys { uint32_t k[20]; };
+inline PhiloxKeys philox_expand(uint64_t seed) {
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0; K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return K;
+}
+__device__ inline void philox_quad_keys(const PhiloxKeys& K, uint64_t quad, uint32_t t, uint32_t stream,
+                                        uint32_t (&out)[4]) {
+    out[0] = (uint32_t)quad; out[1] = (uint32_t)(quad >> 32); out[2] = t; out[3] = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(out, K.k[2 * r], K.k[2 * r + 1]);
+}
+
 // single-MUFU approximations (flush-to-zero: no denormal fix-up code around them)
 __device__ inline float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ inline float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -188,6 +188,19 @@ class SirEngine:
             C.c_void_p(noise.data_ptr()) if noise is not None else None,
             float(thresh), float(u), C.c_uint64(seed), t, self._row(row), self.stream))
 
+    def step_weight(self, model_id: int, params, thresh: float, z_index: int = 0, noise=None, u: float = -1.0,
+                    seed: int = 0, t: int = 0, row: int = 0):
+        """First half of ``step``: K1 with the finalize folded into its last CTA (one launch)."""
+        kp, pp = _lib.as_doubles(params)
+        check(self.lib.smc_sir_step_weight(
+            self._d, model_id, pp, kp.size, self._zptr(z_index),
+            C.c_void_p(noise.data_ptr()) if noise is not None else None,
+            float(thresh), float(u), C.c_uint64(seed), t, self._row(row), self.stream))
+
+    def step_resample(self, phases: int = 3, row: int = 0):
+        """Second half of ``step``: 1 = tile pre-pass + scan, 2 = K3 with the fused finish, 3 = both."""
+        check(self.lib.smc_sir_step_resample(self._d, int(phases), self._row(row), self.stream))
+
     def read_row(self, row: int = 0) -> np.ndarray:
         return self.trace[row % self.trace.shape[0]].cpu().numpy()
 
