@@ -231,7 +231,7 @@ def run_gpu_arm(args):
     ms_step = ms_total / K
 
     # ---- per-kernel breakdown (same fused step, split at its three launch groups) --------------
-    phases = ("k1_propagate_weight+finalize", "k3a_tile_prepass+scan", "k3_resample+finish")
+    phases = ("k1_propagate_weight+finalize", "k3a_range_totals", "k3_resample+finish")
     acc = {p: 0.0 for p in phases}
     NB = 4
     for k in range(W + K, W + K + NB):   # extra steps reuse trace rows / observations via modulo
@@ -294,7 +294,7 @@ def run_gpu_arm(args):
                                "(BASELINE.json configs[2] / SURVEY 8d C3)",
                    "n_particles": N, "nx": 1, "nz": 1, "resample": "every step", "noise": "philox4x32-10 on chip",
                    "l2": "inputs (2 x 256 MiB per step) exceed the 126 MB L2; no flush needed"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": 4 * K,   # K1(+finalize), tile pre-pass, tile scan, K3(+finish)
+        "clocks": clk, "e2e": e2e, "gpu_launches": 3 * K,   # K1(+finalize), range pre-pass, K3(+finish)
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": acc[dom]},

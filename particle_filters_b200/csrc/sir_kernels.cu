@@ -84,7 +84,7 @@ struct K2Args {
     const double* parts;
     double* stats;     // nullable
     int64_t n_global;
-    int32_t n_parts, nx, inline_moments;
+    int32_t n_parts, nx, inline_moments, f32;
     double thresh, u_host;
     uint64_t seed;
     uint32_t t;
@@ -350,7 +350,7 @@ k1_propagate_weight(K1Args<real> a, Model m) {
 // ==============================================================================================
 // K2: finalize.  One CTA reduces the partial records in a fixed order.
 // ==============================================================================================
-__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global);   // defined with the resampler
+__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global, bool f32);   // defined with the resampler
 
 
 // Combine partial records (max-shifted sums) into one record `out` of the same layout
@@ -416,7 +416,7 @@ __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_t
     c->u = u;
     c->do_resample = do_res;
     c->uniform = 0;
-    ctrl_prepare_search(c, a.n_global);
+    ctrl_prepare_search(c, a.n_global, a.f32 != 0);
     if (a.stats) {
         a.stats[0] = log_norm;
         a.stats[1] = ess;
@@ -478,16 +478,20 @@ struct SearchParams {
 };
 
 // Fractional bits of the fixed-point CDF ("index units" N*w): as many as fit below the status bit.
-__host__ __device__ inline int frac_bits_for(int64_t n_global) {
+// fp32 populations use F = 32 throughout: the output count below a CDF value is then simply the
+// high word of the biased value, and -- fp32 weights being what they are -- positions within fp64
+// round-off of a CDF value need no special treatment (the exact predicate serves the fp64 parity mode).
+__host__ __device__ inline int frac_bits_for(int64_t n_global, bool f32 = false) {
+    if (f32) return 32;
     int lg = 0;
     while ((1ll << lg) < n_global) ++lg;
     int F = 62 - lg;
     return F < 32 ? 32 : (F > 60 ? 60 : F);
 }
 
-__device__ inline SearchParams make_search(double u, int64_t n_global) {
+__device__ inline SearchParams make_search(double u, int64_t n_global, bool f32) {
     SearchParams sp;
-    sp.F = frac_bits_for(n_global);
+    sp.F = frac_bits_for(n_global, f32);
     sp.u = u;
     sp.uq = __double2ull_rd(ldexp(u, sp.F));
     sp.fmask = (1ull << sp.F) - 1ull;
@@ -500,8 +504,8 @@ __device__ inline SearchParams make_search(double u, int64_t n_global) {
 
 // Once per step (finalize / set_uniform): cache the resampler constants in the control block so
 // that the 16 K resampling CTAs do not each redo the fp64 log / ldexp work.
-__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global) {
-    const SearchParams sp = make_search(c->u, n_global);
+__device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global, bool f32) {
+    const SearchParams sp = make_search(c->u, n_global, f32);
     c->frac_bits = sp.F;
     c->uq = sp.uq;
     c->margin = sp.margin;
@@ -549,7 +553,7 @@ template <typename real> struct K3Args {
     real* const* peer0;         // nullable: per-shard destination pointers (cur == 1 / cur == 0)
     real* const* peer1;
     int32_t* ancestors;         // nullable
-    const ulonglong2* state;    // per-tile {total, exclusive prefix} from the pre-pass
+    const unsigned long long* rtot;   // per-range weight totals from the pre-pass (one per resampler CTA)
     double* mom_parts;          // nullable
     unsigned long long cdf_offset;
     const unsigned long long* totals;   // nullable: per-shard weight totals (offset = sum over lower ranks)
@@ -644,15 +648,24 @@ __device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bia
     return e;
 }
 
-// ---- K3a: per-tile fixed-point weight totals, then an exclusive scan over the tiles ------------
-// The tile prefixes are produced by a light streaming pre-pass (one extra read of the log-weights)
-// instead of an in-kernel decoupled look-back: the resampling CTAs then have no inter-tile
-// dependency at all, which removes the ticket, the spin on predecessor state and the barrier
-// stalls behind them (profiles/: 40 % of K3's stall samples sat behind the look-back barrier).
-// tile record: .x = tile total, .y = exclusive prefix (both in 2^-F index units).
+// ---- K3a: fixed-point weight totals of the resampler's tile ranges --------------------------------
+// The resampler is a persistent kernel: CTA b owns the contiguous tiles [b T / G, (b + 1) T / G).  It
+// needs the exclusive CDF prefix of its first tile only; the prefixes inside its range follow from
+// its own tile totals.  So the pre-pass is a pure streaming reduction over the same ranges (one extra
+// read of the log-weights), with no inter-CTA dependency, no per-tile records and no scan kernel:
+// CTA b of the resampler sums the totals of the ranges below it (<= G values) in its prologue.
+// The quantisation is the one k3_resample applies item by item, so both kernels agree to the bit.
+__host__ __device__ inline int64_t k3_range_begin(int64_t b, int64_t n_tiles, int64_t grid) {
+    return (b * n_tiles) / grid;
+}
+// The pre-pass cuts every resampler range into kPreSplit sub-ranges (more CTAs in flight for a pure
+// streaming kernel): range b of the resampler starts where sub-range kPreSplit * b starts.
+constexpr int kPreSplit = 4;
+
 template <typename real, bool LINEAR_W>
-__global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_tile_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
-                                                             int64_t n_global, ulonglong2* tiles, int force) {
+__global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_range_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
+                                                                         int64_t n_global, int64_t n_tiles,
+                                                                         unsigned long long* rtot, int force) {
     using G = K3Geom<real>;
     using unit = typename G::unit;
     constexpr int kK3Threads = G::THREADS, kK3Warps = kK3Threads / 32;
@@ -660,95 +673,75 @@ __global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_tile_totals(const C
     __shared__ unsigned long long s_tot[kK3Warps];
     if (!force && !ctrl->do_resample) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile_base = (int64_t)blockIdx.x * TILE;
     Quant<real> quant;
     quant.init(ctrl->frac_bits, LINEAR_W ? 0.0 : ctrl->lw_ref);
     const real n_real = (real)n_global;
-    const int n_in_tile = tile_base + TILE <= n ? TILE : (int)(n - tile_base);
-    const unit* wtile = reinterpret_cast<const unit*>(wsrc + tile_base);
-    unsigned long long run = 0;
-    double runf = 0.0;
-    // fp32: weights are quantised one by one, so any (coalesced) assignment gives the same total;
-    // fp64: the thread's running sum is quantised, so the thread must own the same IPT consecutive
-    //       items as in k3_resample (blocked assignment)
+    const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+    const int64_t t0 = k3_range_begin(blockIdx.x, n_tiles, gridDim.x), t1 = k3_range_begin(blockIdx.x + 1, n_tiles, gridDim.x);
+    unsigned long long total = 0;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t tile_base = tile * TILE;
+        const int n_in_tile = tile_base + TILE <= n ? TILE : (int)(n - tile_base);
+        const unit* wtile = reinterpret_cast<const unit*>(wsrc + tile_base);
+        // fp32: weights are quantised one by one, so any (coalesced) assignment gives the same total;
+        // fp64: the thread's running sum is quantised, so the thread must own the same IPT consecutive
+        //       items as in k3_resample (blocked assignment)
+        real tmp[UPT][EPU];
 #pragma unroll
-    for (int r = 0; r < UPT; ++r) {
-        const int f = (sizeof(real) == 4) ? (r * kK3Threads + tid) : (UPT * tid + r);
-        real tmp[EPU];
-        const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+        for (int r = 0; r < UPT; ++r) {
+            const int f = (sizeof(real) == 4) ? (r * kK3Threads + tid) : (UPT * tid + r);
 #pragma unroll
-        for (int j = 0; j < EPU; ++j) tmp[j] = fill;
-        if (f * EPU < n_in_tile) {
-            unit_to_array(wtile[f], tmp);
+            for (int j = 0; j < EPU; ++j) tmp[r][j] = fill;
+            if (f * EPU < n_in_tile) {
+                unit_to_array(wtile[f], tmp[r]);
+                if (f * EPU + EPU > n_in_tile) {
 #pragma unroll
-            for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
-        }
-#pragma unroll
-        for (int j = 0; j < EPU; ++j) {
-            if (LINEAR_W) {
-                real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);
-                run = quant.add(run, v, runf);
-            } else {
-                run = quant.add_logw(run, tmp[j], runf);
+                    for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[r][j] = fill;
+                }
             }
         }
+        unsigned long long run = 0;
+        double runf = 0.0;
+#pragma unroll
+        for (int r = 0; r < UPT; ++r)
+#pragma unroll
+            for (int j = 0; j < EPU; ++j) {
+                if (LINEAR_W) {
+                    real v = fmin(fmax(tmp[r][j] * n_real, real(0)), n_real);
+                    run = quant.add(run, v, runf);
+                } else {
+                    run = quant.add_logw(run, tmp[r][j], runf);
+                }
+            }
+        total += run;
     }
-    run = warp_sum(run);
-    if (lane == 0) s_tot[warp] = run;
+    total = warp_sum(total);
+    if (lane == 0) s_tot[warp] = total;
     __syncthreads();
     if (tid == 0) {
         unsigned long long t = 0;
 #pragma unroll
         for (int w = 0; w < kK3Warps; ++w) t += s_tot[w];
-        tiles[blockIdx.x].x = t;
+        rtot[blockIdx.x] = t;
     }
 }
 
-// single-CTA exclusive scan of the tile totals (integer, exact); also emits the shard total.
-// 1024 threads x 16 consecutive tiles per pass: all loads of a pass are in flight together, one
-// CTA-wide scan per 16 K tiles.
-__global__ void __launch_bounds__(1024) k3a_scan_tiles(const Ctrl* ctrl, ulonglong2* tiles, int64_t n_tiles,
-                                                      unsigned long long offset, unsigned long long* total_out,
-                                                      int force) {
-    constexpr int PER = 16;
-    __shared__ unsigned long long s_w[32];
-    __shared__ unsigned long long s_carry;
-    if (!force && !ctrl->do_resample) { if (total_out && threadIdx.x == 0) *total_out = 0ull; return; }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = offset;
+// shard total = sum of the range totals (multi-GPU: input of the cross-shard exclusive scan)
+__global__ void __launch_bounds__(kThreads) k3a_sum_ranges(const Ctrl* ctrl, const unsigned long long* rtot, int n_ranges,
+                                                          unsigned long long* total_out, int force) {
+    __shared__ unsigned long long s_tot[kWarps];
+    unsigned long long t = 0;
+    if (force || ctrl->do_resample)
+        for (int i = threadIdx.x; i < n_ranges; i += kThreads) t += rtot[i];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = t;
     __syncthreads();
-    for (int64_t base = 0; base < n_tiles; base += 1024 * PER) {
-        const int64_t i0 = base + (int64_t)tid * PER;
-        unsigned long long v[PER];
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) v[k] = (i0 + k < n_tiles) ? tiles[i0 + k].x : 0ull;
-        unsigned long long sum = 0;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) { const unsigned long long t = v[k]; v[k] = sum; sum += t; }   // local exclusive
-        unsigned long long inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        unsigned long long wex = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < 32; ++w) {
-            const unsigned long long t = s_w[w];
-            if (w < warp) wex += t;
-            tot += t;
-        }
-        const unsigned long long carry = s_carry;
-        const unsigned long long ex = carry + wex + inc - sum;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) if (i0 + k < n_tiles) tiles[i0 + k].y = ex + v[k];
-        __syncthreads();
-        if (tid == 0) s_carry = carry + tot;
-        __syncthreads();
+        for (int w = 0; w < kWarps; ++w) tot += s_tot[w];
+        *total_out = tot;
     }
-    if (total_out && tid == 0) *total_out = s_carry - offset;
 }
 
 // ---- fused "finish step" (also a stand-alone kernel below): post-resample moments from the
@@ -811,17 +804,23 @@ template <typename real, int NXF> struct K3Occ {
     static constexpr int value = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
 };
 
-// K3 proper.  Persistent grid: CTA b handles tiles b, b + grid, ... (static assignment, so the
-// per-CTA moment partials are reproducible).  Per tile:
-//   A  coalesced load of the tile's log-weights -> shared (16-byte swizzle)            | S1
-//      cp.async of the tile's particles -> shared (waited for at S3)
-//   B  blocked read-back, fixed-point quantisation, thread/warp/CTA inclusive scan      | S2
+// K3 proper.  Persistent grid: CTA b owns the contiguous tiles [b T / G, (b + 1) T / G) (static
+// assignment, so the per-CTA moment partials are reproducible) and carries the CDF prefix from tile
+// to tile.  Per tile:
+//   A  the tile's log-weights arrive in shared memory by cp.async (16-byte swizzle), issued while the
+//      previous tile was still being expanded                                                  | S1
+//      cp.async of the tile's particles -> shared (awaited at S3); the id window is cleared
+//   B  blocked read-back, fixed-point quantisation, thread / warp / CTA inclusive scan          | S2
+//      (then the cp.async of the NEXT tile's log-weights is issued)
 //   C  output boundaries e[k] = #{positions below the CDF value after item k} (32-bit, branch-free;
-//      the exact fp64 predicate only when a position lies within round-off of a CDF value)
-//   D  expansion: every item stores its local id into the u16 window slots of its offspring   | S3, S4
-//      (direct stores, bank-swizzled; tiles with a very heavy item or more than W outputs take the
-//      marker + max-scan route, which costs O(window) whatever the skew)
-//   E  copy-out: window slot -> particle payload from shared -> coalesced global stores, moments
+//      the exact fp64 predicate only when a position lies within round-off of a CDF value)      | S3
+//   D  every item with offspring stores (local id + 1) as a u16 marker at its first output slot
+//      (bank-swizzled window)                                                                   | S4
+//   E  copy-out: slot p holds its ancestor's marker, or 0 = "same ancestor as slot p - 1" (probed
+//      backwards; one step covers two offspring, a short loop the rest) -> particle payload from
+//      shared -> coalesced global stores, moments.
+//   Tiles with a very heavy item or more than W outputs take the marker + max-scan route instead,
+//   which costs O(window) whatever the skew.
 template <typename real, int NXF, bool LINEAR_W>
 __global__ void __launch_bounds__(K3Geom<real>::THREADS, K3Occ<real, NXF>::value)
 k3_resample(K3Args<real> a) {
@@ -835,16 +834,19 @@ k3_resample(K3Args<real> a) {
     constexpr int W = kK3Threads * CH;                // output window (tile + 12.5 % / 25 % slack)
     constexpr int NM = NXF + NXF * (NXF + 1) / 2;
     constexpr int NMS = NM > 0 ? NM : 1;
-    constexpr uint32_t MAXD = 8;                      // direct expansion up to this many offspring per item
+    constexpr uint32_t MAXD = 4 * IPT;                // marker + back-probe while no thread has more outputs than this
+    constexpr int PADROW = kK3Threads + 2 * (kK3Threads / IPT);   // swizzled slots per row of kK3Threads positions
+    constexpr int GUARD = 8;                          // zeroed slots in front of the window
     static_assert(UPT == 2 || UPT == 4, "swizzle assumes 2 or 4 16-byte units per thread");
     static_assert(CH % 2 == 0, "fill chunk must be word aligned");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unit* lw_s = reinterpret_cast<unit*>(smem_raw);                       // TILE reals, swizzled
     real* x_s = reinterpret_cast<real*>(smem_raw + sizeof(real) * TILE);  // NXF * TILE reals
-    unsigned short* ids = reinterpret_cast<unsigned short*>(smem_raw + sizeof(real) * TILE * (1 + NXF));
+    unsigned short* ids_raw = reinterpret_cast<unsigned short*>(smem_raw + sizeof(real) * TILE * (1 + NXF));
+    unsigned short* ids = ids_raw + GUARD;
     __shared__ unsigned long long s_warp_tot[kK3Warps];
-    __shared__ uint32_t s_E[2];
+    __shared__ uint32_t s_E[3];
     __shared__ int s_wmax[kK3Warps];
     __shared__ double s_mom[kK3Warps][16];
     __shared__ double s_m[16];
@@ -872,8 +874,60 @@ k3_resample(K3Args<real> a) {
     Quant<real> quant;
     quant.init(sp.F, LINEAR_W ? 0.0 : ctrl->lw_ref);      // weight N w = exp(lw - (log_norm - log N))
     const real n_real = (real)a.n_global;
-    unsigned long long shard_prefix = a.cdf_offset;
-    if (a.totals) for (int r = 0; r < a.rank; ++r) shard_prefix += a.totals[r];
+    const real fill = LINEAR_W ? real(0) : real(-INFINITY);
+
+    const int64_t t_begin = k3_range_begin(blockIdx.x, a.n_tiles, gridDim.x);
+    const int64_t t_end = k3_range_begin(blockIdx.x + 1, a.n_tiles, gridDim.x);
+
+    // log-weights of one tile -> lw_s: cp.async for interior tiles, a guarded copy for the ragged last one
+    auto fetch_lw = [&](int64_t tile) {
+        const int64_t tile_base = tile * TILE;
+        if (tile_base + TILE <= a.n) {
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * kK3Threads + tid;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst),
+                             "l"(a.wsrc + tile_base + (int64_t)f * EPU) : "memory");
+            }
+        } else {
+            const int n_in_tile = (int)(a.n - tile_base);
+            const unit* wtile = reinterpret_cast<const unit*>(a.wsrc + tile_base);
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * kK3Threads + tid;
+                real tmp[EPU];
+#pragma unroll
+                for (int j = 0; j < EPU; ++j) tmp[j] = fill;
+                if (f * EPU < n_in_tile) {
+                    unit_to_array(wtile[f], tmp);
+#pragma unroll
+                    for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
+                }
+                real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
+#pragma unroll
+                for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (t_begin < t_end) fetch_lw(t_begin);
+
+    // exclusive CDF prefix of the first tile: the lower shards' totals (multi-GPU) and the totals of
+    // the ranges below this CTA's
+    unsigned long long prefix;
+    {
+        unsigned long long part = 0;
+        for (int i = tid; i < (int)blockIdx.x * kPreSplit; i += kK3Threads) part += a.rtot[i];
+        if (a.totals) for (int r = tid; r < a.rank; r += kK3Threads) part += a.totals[r];
+        part = warp_sum(part);
+        if (lane == 0) s_warp_tot[warp] = part;
+        __syncthreads();
+        prefix = a.cdf_offset;
+#pragma unroll
+        for (int w = 0; w < kK3Warps; ++w) prefix += s_warp_tot[w];
+        __syncthreads();
+    }
 
     real shift[NXF > 0 ? NXF : 1];
 #pragma unroll
@@ -882,49 +936,19 @@ k3_resample(K3Args<real> a) {
 #pragma unroll
     for (int k = 0; k < NMS; ++k) macc_d[k] = 0.0;
 
-    // window slot of output position s: two pad slots per IPT positions, so that the CTA-wide
-    // stores of phase D (lane stride = IPT positions) fall into distinct banks
+    // window slot of output position s: two pad slots per IPT positions, so that the CTA-wide marker
+    // stores of phase D (lane stride ~ IPT positions) spread over the banks
     auto slot = [](uint32_t s) -> uint32_t { return s + ((s / (uint32_t)IPT) << 1); };
+    const int slot_t = tid + 2 * (tid / IPT);                 // slot(it * kK3Threads + tid) = it * PADROW + slot_t
+    const int slot_b = slot_t - ((tid % IPT) ? 1 : 3);        // slot of the position before (tid >= 1 or it >= 1)
 
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
         const int64_t tile_base = tile * TILE;
-        // exclusive prefix of this tile from the pre-pass (+ the lower shards' totals when sharded);
-        // loaded first so that its latency hides behind the tile loads
-        const unsigned long long tile_prefix = a.state[tile].y + shard_prefix;
-        const bool interior = tile_base + TILE <= a.n;          // no per-element bounds checks needed
-        const int n_in_tile = interior ? TILE : (int)(a.n - tile_base);
+        const unsigned long long tile_prefix = prefix;
+        const int n_in_tile = tile_base + TILE <= a.n ? TILE : (int)(a.n - tile_base);
 
-        // ---- phase A: coalesced log-weight loads -> shared --------------------------------------
-        {
-            const unit* wtile = reinterpret_cast<const unit*>(a.wsrc + tile_base);
-            if (interior) {
-                unit v[UPT];
-#pragma unroll
-                for (int r = 0; r < UPT; ++r) v[r] = wtile[r * kK3Threads + tid];
-#pragma unroll
-                for (int r = 0; r < UPT; ++r) {
-                    const int f = r * kK3Threads + tid;
-                    lw_s[f ^ ((f >> 3) & (UPT - 1))] = v[r];
-                }
-            } else {
-                const real fill = LINEAR_W ? real(0) : real(-INFINITY);
-#pragma unroll
-                for (int r = 0; r < UPT; ++r) {
-                    const int f = r * kK3Threads + tid;
-                    real tmp[EPU];
-#pragma unroll
-                    for (int j = 0; j < EPU; ++j) tmp[j] = fill;
-                    if (f * EPU < n_in_tile) {
-                        unit_to_array(wtile[f], tmp);
-#pragma unroll
-                        for (int j = 0; j < EPU; ++j) if (f * EPU + j >= n_in_tile) tmp[j] = fill;
-                    }
-                    real* dstp = reinterpret_cast<real*>(&lw_s[f ^ ((f >> 3) & (UPT - 1))]);
-#pragma unroll
-                    for (int j = 0; j < EPU; ++j) dstp[j] = tmp[j];
-                }
-            }
-        }
+        // ---- phase A ---------------------------------------------------------------------------
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
         __syncthreads();   // S1: lw_s complete; every thread has finished the previous tile's copy-out
         // particle payload: asynchronous global->shared copies (LDGSTS, no register staging), issued
         // only now because x_s was still being gathered from until S1; awaited at S3
@@ -941,6 +965,12 @@ k3_resample(K3Args<real> a) {
                     }
                 }
             }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        {   // clear the marker window (guard slots included)
+            uint4* o4 = reinterpret_cast<uint4*>(ids_raw);
+            constexpr int N16 = (GUARD + CH * PADROW + 8) * 2 / 16;
+            for (int p = tid; p < N16; p += kK3Threads) o4[p] = make_uint4(0, 0, 0, 0);
         }
 
         // ---- phase B: fixed-point weights, thread / warp / CTA scan -------------------------------
@@ -972,18 +1002,26 @@ k3_resample(K3Args<real> a) {
             if (lane >= o) incl_w += t;
         }
         if (lane == 31) s_warp_tot[warp] = incl_w;
-        __syncthreads();   // S2
-        unsigned long long warp_excl = 0;
+        __syncthreads();   // S2 (lw_s is dead from here on, except for the rare exact path below)
+        unsigned long long warp_excl = 0, tile_total = 0;
 #pragma unroll
         for (int w = 0; w < kK3Warps; ++w) {
             unsigned long long t = s_warp_tot[w];
             if (w < warp) warp_excl += t;
+            tile_total += t;
         }
+        prefix = tile_prefix + tile_total;
 
         // ---- phase C: output boundaries (32-bit) -------------------------------------------------
         // e[k] = number of outputs whose stratified position lies below the CDF value after item k
         const unsigned long long base_b = tile_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
         uint32_t e_start, e[IPT];
+        if constexpr (sizeof(real) == 4) {
+            // F = 32: the count is the high word of the biased CDF value
+            e_start = (uint32_t)(base_b >> 32);
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) e[k] = (uint32_t)((base_b + c[k]) >> 32);
+        } else
         {
             uint32_t near = 0;
             auto fast_e = [&](unsigned long long Cb) -> uint32_t {
@@ -995,8 +1033,9 @@ k3_resample(K3Args<real> a) {
             e_start = fast_e(base_b);
 #pragma unroll
             for (int k = 0; k < IPT; ++k) e[k] = fast_e(base_b + c[k]);
-            if (near) {   // rare (~1e-6 per thread): redo with the exact predicate where needed; the
-                          // running CDF is recomputed from shared memory so that c[] need not stay live
+            if (near) {
+                // rare (~1e-6 per thread): redo with the exact predicate where needed; the running CDF is
+                // recomputed from shared memory so that c[] need not stay live
                 e_start = fast_outputs_below(base_b, fs, sp);
                 unsigned long long run2 = 0;
                 double runf2 = 0.0;
@@ -1033,13 +1072,15 @@ k3_resample(K3Args<real> a) {
             }
         }
         // (padding items beyond the shard carry zero weight, hence no outputs of their own)
-        uint32_t nmax = e[0] - e_start;
-#pragma unroll
-        for (int k = 1; k < IPT; ++k) nmax = max(nmax, e[k] - e[k - 1]);
-        if (tid == 0) s_E[0] = e_start;
+        if (tid == 0) {
+            s_E[0] = e_start;
+            if (peer) s_E[2] = (uint32_t)((int64_t)e_start / a.shard_n);   // shard that owns the first output
+        }
         if (tid == kK3Threads - 1) s_E[1] = e[IPT - 1];
         if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
-        const int heavy = __syncthreads_or(nmax > MAXD);   // S3: also publishes s_E and x_s
+        const int heavy = __syncthreads_or(e[IPT - 1] - e_start > MAXD);   // S3: publishes s_E, x_s and the cleared window;
+                                                           //     nobody reads lw_s any more
+        if (tile + 1 < t_end) fetch_lw(tile + 1);          // next tile's log-weights travel during D / E
         const uint32_t E0 = s_E[0], E1 = s_E[1];
         const uint32_t count = E1 - E0;
         const bool direct = !heavy && count <= (uint32_t)W;
@@ -1048,88 +1089,108 @@ k3_resample(K3Args<real> a) {
 #pragma unroll
         for (int k = 0; k < NMS; ++k) macc[k] = 0;
 
-        // copy-out of `cnt` window slots starting at global output index g0 (SWZ: slots are swizzled)
-        auto copy_out = [&](const int64_t g0, const int cnt, const bool swz) {
-            if (!peer) {
-                real* dwin = xdst + (g0 - a.offset) + tid;           // this thread's first output slot
-                int32_t* awin = a.ancestors ? a.ancestors + (g0 - a.offset) + tid : nullptr;
-                const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // ids are index + 1
-                const real* xg = x_s - 1;                            // ditto
+        // payload of local ancestor (li1 - 1) -> output slot `o` of this thread's column; moments
+        auto emit = [&](real* dcol, int32_t* acol, const int li1, const int32_t abase) {
+            if (acol) *acol = abase + li1;
+            if (NXF > 0) {
+                real xv[NXF > 0 ? NXF : 1];
 #pragma unroll
-                for (int it = 0; it < CH; ++it) {
-                    const uint32_t p = it * kK3Threads + tid;
-                    if ((int)p < cnt) {
-                        const int li1 = (int)ids[swz ? slot(p) : p];    // local ancestor + 1
-                        if (awin) awin[it * kK3Threads] = abase + li1;
-                        if (NXF > 0) {
-                            real xv[NXF > 0 ? NXF : 1];
-#pragma unroll
-                            for (int d = 0; d < NXF; ++d) {
-                                xv[d] = xg[d * TILE + li1];
-                                dwin[d * a.ld + it * kK3Threads] = xv[d];
-                            }
-                            int k = 0;
-#pragma unroll
-                            for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
-#pragma unroll
-                            for (int d = 0; d < NXF; ++d)
-#pragma unroll
-                                for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
-                        }
-                    }
+                for (int d = 0; d < NXF; ++d) {
+                    xv[d] = x_s[d * TILE + li1 - 1];
+                    dcol[d * a.ld] = xv[d];
                 }
-            } else {
-                for (int p = tid; p < cnt; p += kK3Threads) {          // cross-shard migration path
-                    const int li = (int)ids[swz ? slot((uint32_t)p) : (uint32_t)p] - 1;
-                    const int64_t gi = g0 + p;
-                    const int64_t r = gi / a.shard_n;
-                    real* dbase = peer[r];
-                    const int64_t di = gi - r * a.shard_n;
-                    if (NXF > 0) {
-                        real xv[NXF > 0 ? NXF : 1];
+                int k = 0;
 #pragma unroll
-                        for (int d = 0; d < NXF; ++d) {
-                            xv[d] = x_s[d * TILE + li];
-                            dbase[d * a.ld + di] = xv[d];
-                        }
-                        int k = 0;
+                for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
 #pragma unroll
-                        for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
+                for (int d = 0; d < NXF; ++d)
 #pragma unroll
-                        for (int d = 0; d < NXF; ++d)
-#pragma unroll
-                            for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
-                    }
-                }
+                    for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
             }
         };
 
         if (direct) {
-            // ---- phase D (common case): every item writes its id straight into its offspring's slots
-            uint32_t r0 = e_start - E0;
+            // ---- phase D (common case): one marker per item with offspring -----------------------
+            {
+                uint32_t r0 = e_start - E0;
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                const uint32_t r1 = e[k] - E0;
-                const unsigned short v = (unsigned short)(tid * IPT + k + 1);
-                if (r0 < r1) {
-                    ids[slot(r0)] = v;
-                    if (r0 + 1 < r1) {
-                        ids[slot(r0 + 1)] = v;
-                        for (uint32_t r = r0 + 2; r < r1; ++r) ids[slot(r)] = v;
-                    }
+                for (int k = 0; k < IPT; ++k) {
+                    const uint32_t r1 = e[k] - E0;
+                    if (r0 < r1) ids[slot(r0)] = (unsigned short)(tid * IPT + k + 1);
+                    r0 = r1;
                 }
-                r0 = r1;
             }
             __syncthreads();   // S4
-            copy_out((int64_t)E0, (int)count, true);
+            // ---- phase E: coalesced copy-out -----------------------------------------------------
+            const int64_t g0 = (int64_t)E0 - a.offset;
+            real* dwin = xdst + g0 + tid;                              // this thread's output column
+            int32_t* awin = a.ancestors ? a.ancestors + g0 + tid : nullptr;
+            const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // markers are index + 1
+            const int nfull = (int)(count / kK3Threads);                  // rows in which every thread has an output
+            // cross-shard migration: outputs [E0, E1) start in shard s_E[2]; `thr` = first window
+            // position owned by the next shard
+            int64_t pr = 0, thr = 0;
+            if (peer) { pr = (int64_t)s_E[2]; thr = (pr + 1) * a.shard_n - (int64_t)E0; }
+            auto row = [&](const int it) {
+                int li1 = (int)ids[it * PADROW + slot_t];
+                if (li1 == 0) {                                           // same ancestor as the slot before
+                    li1 = (int)ids[it * PADROW + slot_b];
+                    if (li1 == 0) {                                       // three or more offspring: walk back
+                        uint32_t q = (uint32_t)(it * kK3Threads + tid) - 1u;
+                        do { --q; li1 = (int)ids[slot(q)]; } while (li1 == 0);
+                    }
+                }
+                if (!peer) {
+                    emit(dwin + it * kK3Threads, awin ? awin + it * kK3Threads : nullptr, li1, abase);
+                } else {
+                    const int64_t p = (int64_t)it * kK3Threads + tid;
+                    while (p >= thr) { ++pr; thr += a.shard_n; }          // rows advance, so pr only grows
+                    emit(peer[pr] + ((int64_t)E0 + p - pr * a.shard_n), nullptr, li1, abase);
+                }
+            };
+            const bool tail = (int)(count - nfull * kK3Threads) > tid;
+            if (NXF > 0 && !peer && !awin) {
+                // the hot form: no ancestor trace, no migration; all addresses are immediates
+                const unsigned short* idp = ids + slot_t;
+                const unsigned short* idb = ids + slot_b;
+                const real* xg = x_s - 1;                                 // markers are index + 1
+                auto hot = [&](const int it) {
+                    const int m0 = (int)idp[it * PADROW], m1 = (int)idb[it * PADROW];
+                    int li1 = m0 ? m0 : m1;
+                    if (li1 == 0) {                                       // three or more offspring: walk back
+                        uint32_t q = (uint32_t)(it * kK3Threads + tid) - 1u;
+                        do { --q; li1 = (int)ids[slot(q)]; } while (li1 == 0);
+                    }
+                    real xv[NXF > 0 ? NXF : 1];
+#pragma unroll
+                    for (int d = 0; d < NXF; ++d) {
+                        xv[d] = xg[d * TILE + li1];
+                        dwin[d * a.ld + it * kK3Threads] = xv[d];
+                    }
+                    int k = 0;
+#pragma unroll
+                    for (int d = 0; d < NXF; ++d) { xv[d] -= shift[d]; macc[k] += xv[d]; ++k; }
+#pragma unroll
+                    for (int d = 0; d < NXF; ++d)
+#pragma unroll
+                        for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
+                };
+#pragma unroll
+                for (int it = 0; it < CH; ++it)
+                    if (it < nfull) hot(it);
+                if (tail) hot(nfull);
+            } else {
+                for (int it = 0; it < nfull; ++it) row(it);
+                if (tail) row(nfull);
+            }
         } else {
-            // ---- phase D (skewed tile): head markers + max-scan fill, window by window ----------
+            // ---- skewed tile / cross-shard migration: head markers + max-scan fill, window by window
             for (uint32_t wbase = 0; wbase < count; wbase += W) {
-                {
+                if (wbase > 0) {
                     uint4* o4 = reinterpret_cast<uint4*>(ids);
                     for (int p = tid; p < W * 2 / 16; p += kK3Threads) o4[p] = make_uint4(0, 0, 0, 0);
+                    __syncthreads();
                 }
-                __syncthreads();
                 {   // head markers (local index + 1) at the first output of every item with offspring
                     uint32_t r0 = e_start - E0;
 #pragma unroll
@@ -1175,8 +1236,22 @@ k3_resample(K3Args<real> a) {
                     }
                 }
                 __syncthreads();
-                const uint32_t rem = count - wbase;
-                copy_out((int64_t)E0 + wbase, rem < (uint32_t)W ? (int)rem : W, false);
+                {
+                    const uint32_t rem = count - wbase;
+                    const int cnt = rem < (uint32_t)W ? (int)rem : W;
+                    const int64_t g0 = (int64_t)E0 + wbase;                  // global index of window slot 0
+                    const int32_t abase = (int32_t)(a.offset + tile_base) - 1;
+                    for (int p = tid; p < cnt; p += kK3Threads) {
+                        const int li1 = (int)ids[p];
+                        const int64_t gi = g0 + p;
+                        if (!peer) {
+                            emit(xdst + (gi - a.offset), a.ancestors ? a.ancestors + (gi - a.offset) : nullptr, li1, abase);
+                        } else {                                             // cross-shard migration
+                            const int64_t r = gi / a.shard_n;
+                            emit(peer[r] + (gi - r * a.shard_n), nullptr, li1, abase);
+                        }
+                    }
+                }
                 __syncthreads();
             }
         }
@@ -1185,6 +1260,7 @@ k3_resample(K3Args<real> a) {
             for (int k = 0; k < NMS; ++k) macc_d[k] += (double)macc[k];
         }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 
     // ---- per-CTA post-resample moment partials (+ the fused finish in the last CTA to arrive) ----
     if (NM > 0 && a.mom_parts) {
@@ -1303,13 +1379,13 @@ __global__ void k_reset_ctrl(Ctrl* c, const double* shift, int nx) {
         for (int d = 0; d < kMaxNx; ++d) c->shift[d] = (shift && d < nx) ? shift[d] : 0.0;
     }
 }
-__global__ void k_set_uniform(Ctrl* c, double u, int64_t n_global) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { c->u = u; ctrl_prepare_search(c, n_global); }
+__global__ void k_set_uniform(Ctrl* c, double u, int64_t n_global, int f32) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { c->u = u; ctrl_prepare_search(c, n_global, f32 != 0); }
 }
-__global__ void k_set_resample(Ctrl* c, double u, int64_t n_global) {
+__global__ void k_set_resample(Ctrl* c, double u, int64_t n_global, int f32) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         c->u = u; c->do_resample = 1; c->cur = 0; c->log_norm = 0.0;
-        ctrl_prepare_search(c, n_global);
+        ctrl_prepare_search(c, n_global, f32 != 0);
     }
 }
 
@@ -1575,8 +1651,9 @@ template <typename real, int NXF, bool LIN>
 int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
     using G = K3Geom<real>;
     static_assert(K3Occ<real, NXF>::value >= 1, "occupancy table");
-    constexpr int W = G::THREADS * (G::IPT + 2);
-    constexpr size_t ids_bytes = ((size_t)(W + 2 * (W / G::IPT) + 8) * 2 + 15) & ~size_t(15);
+    constexpr int PADROW = G::THREADS + 2 * (G::THREADS / G::IPT);
+    constexpr size_t ids_bytes = (size_t)(8 + (G::IPT + 2) * PADROW + 8) * 2;   // guard + window + tail, u16 slots
+    static_assert(ids_bytes % 16 == 0, "marker window must be a whole number of 16-byte units");
     const size_t smem = sizeof(real) * G::THREADS * G::IPT * (1 + NXF) + ids_bytes;
     auto kern = k3_resample<real, NXF, LIN>;
     static bool attr_set = false;   // one flag per template instantiation
@@ -1595,19 +1672,21 @@ int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
 }
 
 template <typename real>
-int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int force, unsigned long long* total_out) {
+int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, int force, unsigned long long* total_out) {
     const smc_sir_desc* d = l.d;
-    ulonglong2* tiles = reinterpret_cast<ulonglong2*>(l.agg());
-    const unsigned nt = (unsigned)l.L.n_tiles;
+    unsigned long long* rtot = l.agg();
+    const unsigned grid = (unsigned)k3_grid(l.L.n_tiles, d->dtype, nxf) * kPreSplit;   // refines the resampler's partition
     if (linear_w)
-        k3a_tile_totals<real, true><<<nt, K3Geom<real>::THREADS, 0, l.st>>>(l.ctrl(), static_cast<const real*>(wsrc), d->n,
-                                                               d->n_global, tiles, force);
+        k3a_range_totals<real, true><<<grid, K3Geom<real>::THREADS, 0, l.st>>>(
+            l.ctrl(), static_cast<const real*>(wsrc), d->n, d->n_global, l.L.n_tiles, rtot, force);
     else
-        k3a_tile_totals<real, false><<<nt, K3Geom<real>::THREADS, 0, l.st>>>(l.ctrl(), static_cast<const real*>(wsrc), d->n,
-                                                                d->n_global, tiles, force);
+        k3a_range_totals<real, false><<<grid, K3Geom<real>::THREADS, 0, l.st>>>(
+            l.ctrl(), static_cast<const real*>(wsrc), d->n, d->n_global, l.L.n_tiles, rtot, force);
     SMC_CHECK_CUDA(cudaGetLastError());
-    k3a_scan_tiles<<<1, 1024, 0, l.st>>>(l.ctrl(), tiles, l.L.n_tiles, 0ull, total_out, force);
-    SMC_CHECK_CUDA(cudaGetLastError());
+    if (total_out) {
+        k3a_sum_ranges<<<1, kThreads, 0, l.st>>>(l.ctrl(), rtot, (int)grid, total_out, force);
+        SMC_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -1616,9 +1695,8 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
               void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
               int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr) {
     const smc_sir_desc* d = l.d;
-    ulonglong2* tiles = reinterpret_cast<ulonglong2*>(l.agg());
     if (run_prepass) {
-        if (int rc = launch_prepass<real>(l, linear_w, wsrc, force, nullptr)) return rc;
+        if (int rc = launch_prepass<real>(l, linear_w, wsrc, nxf, force, nullptr)) return rc;
     }
     K3Args<real> a;
     a.ctrl = l.ctrl();
@@ -1633,7 +1711,7 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
         a.peer1 = reinterpret_cast<real* const*>(peer) + n_shards;
     }
     a.ancestors = ((d->flags & SMC_FLAG_WRITE_ANCESTORS) || nxf == 0) ? d->ancestors_dev : nullptr;
-    a.state = tiles;
+    a.rtot = l.agg();
     a.mom_parts = want_moments ? l.mom_parts() : nullptr;
     a.cdf_offset = cdf_offset;
     a.totals = totals; a.rank = rank;
@@ -1793,6 +1871,7 @@ int smc_sir_finalize(const smc_sir_desc* d, double resample_thresh, double u_hos
     a.n_global = d->n_global;
     a.nx = d->nx;
     a.inline_moments = inline_moments(d) ? 1 : 0;
+    a.f32 = d->dtype == SMC_F32;
     a.thresh = resample_thresh; a.u_host = u_host; a.seed = seed; a.t = (uint32_t)t;
     k2_finalize<<<1, kThreads, 0, l.st>>>(a);
     SMC_CHECK_CUDA(cudaGetLastError());
@@ -1803,7 +1882,7 @@ int smc_sir_set_uniform(const smc_sir_desc* d, double u, void* stream) {
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
-    k_set_uniform<<<1, 32, 0, l.st>>>(l.ctrl(), u, d->n_global);
+    k_set_uniform<<<1, 32, 0, l.st>>>(l.ctrl(), u, d->n_global, d->dtype == SMC_F32);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1814,8 +1893,10 @@ int smc_sir_shard_weight_total(const smc_sir_desc* d, uint64_t* total_dev, void*
     SMC_REQUIRE(total_dev, "smc: total_dev missing");
     // the tile pre-pass of the resampler: leaves the tile prefixes in the workspace for
     // smc_sir_resample_sharded and the shard total (0 when the step does not resample) in total_dev
-    return d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, 0, (unsigned long long*)total_dev)
-                               : launch_prepass<double>(l, false, d->logw_dev, 0, (unsigned long long*)total_dev);
+    SMC_REQUIRE(d->nx <= kFusedNxMax, "smc: sharded resampling requires nx <= %d", kFusedNxMax);
+    return d->dtype == SMC_F32
+               ? launch_prepass<float>(l, false, d->logw_dev, d->nx, 0, (unsigned long long*)total_dev)
+               : launch_prepass<double>(l, false, d->logw_dev, d->nx, 0, (unsigned long long*)total_dev);
 }
 
 static int sir_resample_impl(const smc_sir_desc* d, uint64_t cdf_offset_fix, void* const* peer_x_dev,
@@ -1958,6 +2039,7 @@ int smc_sir_step_weight(const smc_sir_desc* d, int32_t model_id, const double* p
     memset(&fin, 0, sizeof(fin));
     fin.stats = stats_row_dev; fin.n_global = d->n_global; fin.nx = d->nx;
     fin.inline_moments = inline_moments(d) ? 1 : 0;
+    fin.f32 = d->dtype == SMC_F32;
     fin.thresh = resample_thresh; fin.u_host = u_host; fin.seed = seed; fin.t = (uint32_t)t;
     return sir_propagate_weight_impl(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream, &fin);
 }
@@ -1973,8 +2055,8 @@ int smc_sir_step_resample(const smc_sir_desc* d, int32_t phases, double* stats_r
         return smc_sir_finish_step(d, stats_row_dev, nullptr, 0, stream);
     }
     if (phases & 1) {
-        int rc = d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, 0, nullptr)
-                                     : launch_prepass<double>(l, false, d->logw_dev, 0, nullptr);
+        int rc = d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, d->nx, 0, nullptr)
+                                     : launch_prepass<double>(l, false, d->logw_dev, d->nx, 0, nullptr);
         if (rc) return rc;
     }
     if (phases & 2) {
@@ -2013,7 +2095,7 @@ int smc_systematic_ancestors(const double* w_dev, int64_t n, double u, int32_t* 
     if (int rc = check_desc(&d, &l, stream)) return rc;
     SMC_REQUIRE(u >= 0.0 && u < 1.0, "smc: u must lie in [0, 1)");
     SMC_REQUIRE(w_dev && ancestors_dev, "smc: null buffer");
-    k_set_resample<<<1, 32, 0, l.st>>>(l.ctrl(), u, d.n_global);
+    k_set_resample<<<1, 32, 0, l.st>>>(l.ctrl(), u, d.n_global, 0);
     SMC_CHECK_CUDA(cudaGetLastError());
     return launch_k3<double>(l, true, w_dev, 0, 0ull, 1, nullptr, 0, false);
 }

@@ -102,7 +102,7 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     L.ctrl = off;      off = align256(off + 1024);
     L.params = off;    off = align256(off + size_t(kParamSlots) * kParamSlotDoubles * sizeof(double));
     L.k1_parts = off;  off = align256(off + size_t(L.n_k1_blocks) * partial_stride(nx) * sizeof(double));
-    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16);
+    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16 + 65536);   // range totals of the pre-pass
     L.ticket = off;    off = align256(off + 256);
     L.mom_parts = off; off = align256(off + size_t(L.n_tiles) * moment_stride(nx) * sizeof(double));
     L.total = off;
