@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except Exception:
@@ -219,7 +219,13 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    time.sleep(0.25)
+    # nvidia-smi needs a moment before its first sample; keep the GPU on the same workload meanwhile so
+    # that every sample is taken under load (these steps are outside the timed region)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.4:
+        for k in range(W):
+            one_step(k)
+        torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     torch.cuda.synchronize()
     e0.record()
@@ -279,7 +285,7 @@ def run_gpu_arm(args):
            "api": "ParticleFilter.step(z) -> PFState.mean (host z in, host moments out, sync every step)"}
 
     # ---- CPU baseline: oracle port on the host, bounded sample --------------------------------
-    n_cpu = 1 << 22
+    n_cpu = 1 << (12 if args.no_cpu else 22)
     cpu_steps = 4
     dt_cpu, _, _ = cpu_sir_steps(n_cpu, cpu_steps, 1)
     cpu = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": 1, "kind": "port",
@@ -311,10 +317,11 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log2n", type=int, default=26)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

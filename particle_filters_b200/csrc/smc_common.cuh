@@ -37,9 +37,23 @@ void set_error(const char* fmt, ...);
 // ----------------------------------------------------------------------------------------------
 constexpr int kThreads = 256;          // CTA size of every streaming kernel
 constexpr int kWarps = kThreads / 32;
-constexpr int kK1Quads = 4;            // quads (4 particles) per thread per K1 block
+// K1 tuning knobs (overridable at build time for experiments; the defaults are the measured best)
+#ifndef SMC_K1_QUADS
+#define SMC_K1_QUADS 4
+#endif
+#ifndef SMC_K1_OCC
+#define SMC_K1_OCC 4
+#endif
+#ifndef SMC_K1_PREFETCH
+#define SMC_K1_PREFETCH 1
+#endif
+constexpr int kK1Quads = SMC_K1_QUADS; // quads (4 particles) per thread per K1 block
 constexpr int kK1Block = kThreads * 4 * kK1Quads;   // particles per K1 chunk (4096)
-constexpr int kK1MaxBlocks = 148 * 4;  // persistent K1 grid: CTAs loop over chunks (B200: 148 SMs)
+constexpr int kK1Occ = SMC_K1_OCC;     // resident K1 CTAs per SM for the light (fp32, nx <= 2) functors
+#ifndef SMC_K1_GRID_PER_SM
+#define SMC_K1_GRID_PER_SM SMC_K1_OCC
+#endif
+constexpr int kK1MaxBlocks = 148 * SMC_K1_GRID_PER_SM;  // persistent K1 grid: CTAs loop over chunks (B200: 148 SMs)
 constexpr int kMaxNx = 64;             // control block moment shift capacity
 constexpr int kFusedNxMax = 4;         // K3 moves the payload itself up to this many dims
 
