@@ -321,6 +321,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log2n", type=int, default=26)
+    ap.add_argument("--exchange", default="mailbox", choices=("mailbox", "nccl"),
+                    help="multi-GPU record exchange: in-kernel NVLink peer stores (default) or NCCL all-gathers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":

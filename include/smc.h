@@ -207,6 +207,26 @@ int smc_sir_step_weight(const smc_sir_desc *d, int32_t model_id, const double *p
                         double *stats_row_dev, void *stream);
 int smc_sir_step_resample(const smc_sir_desc *d, int32_t phases, double *stats_row_dev, void *stream);
 
+/* Multi-GPU step without collective calls.  Every rank owns a mailbox (smc_mailbox_bytes() of
+ * zeroed, peer-mapped device memory, see smc_ipc_*).  The last CTA of K1 / the pre-pass / K3 stores
+ * this rank's partial record / weight total / moment record straight into the mailbox of EVERY rank
+ * (NVLink peer stores) and raises a stamped flag there; the consuming kernels (finalize, K3's
+ * prologue, finish) spin on the flags in their own memory.  mail_dev: device array of n_shards
+ * mailbox pointers (index = rank, own mailbox included); peer_x_dev: as for
+ * smc_sir_resample_sharded; stamp: positive, increased by one per step, identical on all ranks.
+ * Results are bit-identical to the single-GPU step (same reduction orders, integer CDF). */
+typedef struct smc_shard_ctx {
+    void *const *mail_dev;
+    void *const *peer_x_dev;
+    int32_t rank, n_shards;
+    uint64_t stamp;
+} smc_shard_ctx;
+uint64_t smc_mailbox_bytes(void);
+int smc_sir_step_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_t model_id,
+                         const double *params_host, int32_t n_params, const double *z_dev,
+                         double resample_thresh, uint64_t seed, int64_t t, double *stats_row_dev,
+                         void *stream);
+
 /* Stand-alone pieces used by the drop-in classes' private helpers. */
 
 /* ParticleFilter._systematic_resample(weights) (particle_filter.py:146-171):

@@ -47,6 +47,13 @@ class LedhDesc(C.Structure):
     ]
 
 
+class ShardCtx(C.Structure):
+    """Mirror of ``smc_shard_ctx`` (include/smc.h)."""
+
+    _fields_ = [("mail_dev", C.c_void_p), ("peer_x_dev", C.c_void_p), ("rank", C.c_int32), ("n_shards", C.c_int32),
+                ("stamp", C.c_uint64)]
+
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 _SIG = {
@@ -81,6 +88,9 @@ _SIG = {
     "smc_sir_step_weight": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _D, C.c_int32, _P, _P, C.c_double,
                                       C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_sir_step_resample": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _P, _P]),
+    "smc_mailbox_bytes": (C.c_uint64, []),
+    "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
+                                       C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_systematic_ancestors": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_uint64, _P]),
     "smc_gather": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
     "smc_sir_export_weights": (C.c_int, [C.POINTER(SirDesc), _P, _P]),

@@ -79,18 +79,54 @@ template <typename real, int NX_, int NZ_> struct LinGaussModel {
 // ==============================================================================================
 // K1: fused propagate + log-likelihood + block partials
 // ==============================================================================================
+// ==============================================================================================
+// Multi-GPU mailboxes.  Every rank owns one Mailbox in peer-mapped device memory (CUDA IPC); a rank
+// publishes its per-step records by storing them straight into the mailbox of every rank over
+// NVLink and then raising a stamped flag there.  Consumers spin on the flags in their OWN memory,
+// so the three per-step exchanges of the sharded filter (partial record, weight total, moment
+// record) need no collective call and no extra kernel: the producer is the last CTA of the kernel
+// that computes the record, the consumer the prologue of the kernel that needs it.
+// Stamps increase by one per step; a slot can be reused every step because a rank can publish
+// step t + 1 of an exchange only after every rank has consumed step t of it.
+// ==============================================================================================
+constexpr int kMaxShards = 16;
+struct Mailbox {
+    unsigned long long flag_rec[kMaxShards];
+    unsigned long long flag_tot[kMaxShards];
+    unsigned long long flag_mom[kMaxShards];
+    unsigned long long tot[kMaxShards];
+    double rec[kMaxShards][32];
+    double mom[kMaxShards][16];
+};
+struct ShardCtx {
+    Mailbox* const* mail;        // device array of n_shards mailbox pointers (own one included)
+    int32_t rank, n_shards;
+    unsigned long long stamp;    // this step's stamp (> 0)
+};
+__device__ inline void mailbox_wait(const volatile unsigned long long* flags, int n, unsigned long long stamp) {
+    // threads 0 .. n-1 of the CTA each watch one flag; CTA-wide barrier afterwards
+    if ((int)threadIdx.x < n) {
+        while (flags[threadIdx.x] != stamp) __nanosleep(20);
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
 struct K2Args {
     Ctrl* ctrl;
     const double* parts;
     double* stats;     // nullable
     int64_t n_global;
     int32_t n_parts, nx, inline_moments, f32;
+    int32_t rec_stride;   // doubles between records (0 = packed: the field count)
     double thresh, u_host;
     uint64_t seed;
     uint32_t t;
 };
 
 __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp);   // defined with K2
+__device__ inline void combine_partials(const double* parts, int n_parts, int ps, double* s_out, double* s_tmp,
+                                        int stride);
 
 template <typename real> struct K1Args {
     Ctrl* ctrl;
@@ -108,6 +144,7 @@ template <typename real> struct K1Args {
     int32_t fuse_finalize;      // the last CTA to finish also runs the K2 finalize (fin)
     unsigned int* ticket;       // arrival counter for fuse_finalize (zero between launches)
     K2Args fin;
+    ShardCtx shard;             // mail != nullptr: the last CTA publishes this shard's partial record instead
 };
 
 template <typename real, int NX>
@@ -399,6 +436,28 @@ k1_propagate_weight(K1Args<real> a, Model m) {
             finalize_body(a.fin, s_out, s_tmp);
             if (tid == 0) *a.ticket = 0u;
         }
+    } else if (a.shard.mail) {
+        // sharded: the last CTA folds the block partials into ONE record and stores it into every
+        // rank's mailbox (NVLink peer stores), then raises this rank's flag there
+        __shared__ int s_last;
+        __shared__ double s_out[32];
+        __shared__ double s_tmp[kWarps];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int ps = partial_stride(NX);
+            combine_partials(a.parts, (int)gridDim.x, ps, s_out, s_tmp, 0);
+            if (tid < ps)
+                for (int g = 0; g < a.shard.n_shards; ++g) a.shard.mail[g]->rec[a.shard.rank][tid] = s_out[tid];
+            __threadfence_system();
+            __syncthreads();
+            if (tid < a.shard.n_shards)
+                *(volatile unsigned long long*)&a.shard.mail[tid]->flag_rec[a.shard.rank] = a.shard.stamp;
+            if (tid == 0) *a.ticket = 0u;
+        }
     }
 }
 
@@ -411,7 +470,8 @@ __device__ inline void ctrl_prepare_search(Ctrl* c, int64_t n_global, bool f32);
 // Combine partial records (max-shifted sums) into one record `out` of the same layout
 // (out[0] = global max, sums relative to it).  All threads of the CTA return the record in smem.
 __device__ inline void combine_partials(const double* parts, int n_parts, int ps, double* s_out,
-                                        double* s_tmp) {
+                                        double* s_tmp, int stride) {
+    if (stride <= 0) stride = ps;
     // One pass over the records (thread-local online rescaling), one CTA-wide max, one CTA-wide sum
     // of all fields: 4 barriers and a single round of global loads on the critical path of a step.
     __shared__ double s_x[kWarps][20];
@@ -421,7 +481,7 @@ __device__ inline void combine_partials(const double* parts, int n_parts, int ps
 #pragma unroll
     for (int k = 0; k < 20; ++k) acc[k] = 0;
     for (int p = tid; p < n_parts; p += kThreads) {     // fixed record -> thread assignment
-        const double* r = parts + (int64_t)p * ps;
+        const double* r = parts + (int64_t)p * stride;
         const double r0 = __ldcg(r);
         double v[20];
 #pragma unroll
@@ -462,7 +522,7 @@ __global__ void __launch_bounds__(kThreads) k2_reduce_partials(const double* par
                                                                double* out) {
     __shared__ double s_out[32];
     __shared__ double s_tmp[kWarps];
-    combine_partials(parts, n_parts, ps, s_out, s_tmp);
+    combine_partials(parts, n_parts, ps, s_out, s_tmp, 0);
     if (threadIdx.x < ps) out[threadIdx.x] = s_out[threadIdx.x];
 }
 
@@ -470,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) k2_reduce_partials(const double* par
 // Runs in one 256-thread CTA: the stand-alone kernel below, or the last CTA of K1 to finish.
 __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp) {
     const int ps = a.inline_moments ? partial_stride(a.nx) : 3;
-    combine_partials(a.parts, a.n_parts, ps, s_out, s_tmp);
+    combine_partials(a.parts, a.n_parts, ps, s_out, s_tmp, a.rec_stride);
     if (threadIdx.x != 0) return;
     Ctrl* c = a.ctrl;
     const double M = s_out[0], S = s_out[1], Q = s_out[2];
@@ -517,6 +577,19 @@ __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_t
 __global__ void __launch_bounds__(kThreads) k2_finalize(K2Args a) {
     __shared__ double s_out[32];
     __shared__ double s_tmp[kWarps];
+    finalize_body(a, s_out, s_tmp);
+}
+
+// sharded: wait until every rank's partial record of this step sits in the own mailbox, then
+// reduce the G records in rank order (identical arithmetic, hence identical results, on all ranks)
+__global__ void __launch_bounds__(kThreads) k2_finalize_sharded(K2Args a, ShardCtx sc) {
+    __shared__ double s_out[32];
+    __shared__ double s_tmp[kWarps];
+    Mailbox* own = sc.mail[sc.rank];
+    mailbox_wait(own->flag_rec, sc.n_shards, sc.stamp);
+    a.parts = &own->rec[0][0];
+    a.n_parts = sc.n_shards;
+    a.rec_stride = 32;
     finalize_body(a, s_out, s_tmp);
 }
 
@@ -612,6 +685,7 @@ struct FinishArgs {
     double* stats;              // stats row (nullable)
     const double* mom_parts;    // n_mom_parts records of moment_stride(nx) doubles
     int32_t n_mom_parts, nx, inline_moments, no_moments;
+    int32_t mom_stride;         // doubles between records (0 = packed)
     int64_t n_global;
 };
 
@@ -636,6 +710,7 @@ template <typename real> struct K3Args {
     int32_t fuse_finish;        // the last CTA to finish also runs finish_body(fin)
     unsigned int* ticket;       // arrival counter for fuse_finish (zero between launches)
     FinishArgs fin;
+    ShardCtx shard;             // mail != nullptr: weight totals come from / moment record goes to the mailboxes
 };
 
 // Tile geometry: THREADS threads own IPT consecutive items each (fp32: 256 x 16 = 4096-particle
@@ -737,7 +812,8 @@ constexpr int kPreSplit = 4;
 template <typename real, bool LINEAR_W>
 __global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_range_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
                                                                          int64_t n_global, int64_t n_tiles,
-                                                                         unsigned long long* rtot, int force) {
+                                                                         unsigned long long* rtot, int force,
+                                                                         ShardCtx shard, unsigned int* ticket) {
     using G = K3Geom<real>;
     using unit = typename G::unit;
     constexpr int kK3Threads = G::THREADS, kK3Warps = kK3Threads / 32;
@@ -807,6 +883,34 @@ __global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_range_totals(const 
         for (int w = 0; w < kK3Warps; ++w) t += s_tot[w];
         rtot[blockIdx.x] = t;
     }
+    if (shard.mail) {
+        // sharded: the last CTA sums the range totals (integers: any order) and stores the shard total
+        // into every rank's mailbox, then raises this rank's flag there
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            unsigned long long t = 0;
+            for (int i = tid; i < (int)gridDim.x; i += kK3Threads) t += __ldcg(rtot + i);
+            t = warp_sum(t);
+            __syncthreads();
+            if (lane == 0) s_tot[warp] = t;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long tot = 0;
+#pragma unroll
+                for (int w = 0; w < kK3Warps; ++w) tot += s_tot[w];
+                for (int g = 0; g < shard.n_shards; ++g) shard.mail[g]->tot[shard.rank] = tot;
+                __threadfence_system();
+                for (int g = 0; g < shard.n_shards; ++g)
+                    *(volatile unsigned long long*)&shard.mail[g]->flag_tot[shard.rank] = shard.stamp;
+                *ticket = 0u;
+            }
+        }
+    }
 }
 
 // shard total = sum of the range totals (multi-GPU: input of the cross-shard exclusive scan)
@@ -840,8 +944,9 @@ __device__ inline void finish_body(Ctrl* ctrl, const FinishArgs& f, double (*s_w
 #pragma unroll
         for (int k = 0; k < 14; ++k) acc[k] = 0;
 #pragma unroll 2
+        const int mstride = f.mom_stride > 0 ? f.mom_stride : nm;
         for (int p = tid; p < f.n_mom_parts; p += nthreads) {    // fixed record -> thread assignment
-            const double* r = f.mom_parts + (int64_t)p * nm;
+            const double* r = f.mom_parts + (int64_t)p * mstride;
 #pragma unroll
             for (int k = 0; k < 14; ++k) if (k < nm) acc[k] += __ldcg(r + k);
         }
@@ -929,7 +1034,7 @@ k3_resample(K3Args<real> a) {
     unsigned short* ids_raw = reinterpret_cast<unsigned short*>(smem_raw + sizeof(real) * TILE * (1 + NXF));
     unsigned short* ids = ids_raw + GUARD;
     __shared__ unsigned long long s_warp_tot[kK3Warps];
-    __shared__ uint32_t s_E[3];
+    __shared__ uint32_t s_E[4];
     __shared__ int s_wmax[kK3Warps];
     __shared__ double s_mom[kK3Warps][16];
     __shared__ double s_m[16];
@@ -943,6 +1048,9 @@ k3_resample(K3Args<real> a) {
         // nothing to resample: only the moment-shift refresh of the fused finish remains
         if (a.fuse_finish && blockIdx.x == 0 && tid == 0 && a.fin.stats && !a.fin.no_moments)
             for (int d = 0; d < a.fin.nx && d < kMaxNx; ++d) ctrl->shift[d] = a.fin.stats[SMC_STATS_HEADER + d];
+        // sharded: the finish kernels of all ranks wait for this rank's flag (no data this step)
+        if (a.shard.mail && blockIdx.x == 0 && tid < a.shard.n_shards)
+            *(volatile unsigned long long*)&a.shard.mail[tid]->flag_mom[a.shard.rank] = a.shard.stamp;
         return;
     }
     const int cur = ctrl->cur;
@@ -1002,9 +1110,15 @@ k3_resample(K3Args<real> a) {
     // the ranges below this CTA's
     unsigned long long prefix;
     {
+        const unsigned long long* totals = a.totals;
+        if (a.shard.mail) {   // every rank's weight total of this step must have arrived in the own mailbox
+            Mailbox* own = a.shard.mail[a.shard.rank];
+            mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp);
+            totals = own->tot;
+        }
         unsigned long long part = 0;
         for (int i = tid; i < (int)blockIdx.x * kPreSplit; i += kK3Threads) part += a.rtot[i];
-        if (a.totals) for (int r = tid; r < a.rank; r += kK3Threads) part += a.totals[r];
+        if (totals) for (int r = tid; r < a.rank; r += kK3Threads) part += __ldcg(totals + r);
         part = warp_sum(part);
         if (lane == 0) s_warp_tot[warp] = part;
         __syncthreads();
@@ -1161,7 +1275,10 @@ k3_resample(K3Args<real> a) {
             s_E[0] = e_start;
             if (peer) s_E[2] = (uint32_t)((int64_t)e_start / a.shard_n);   // shard that owns the first output
         }
-        if (tid == kK3Threads - 1) s_E[1] = e[IPT - 1];
+        if (tid == kK3Threads - 1) {
+            s_E[1] = e[IPT - 1];
+            if (peer) s_E[3] = (uint32_t)((int64_t)(e[IPT - 1] > 0u ? e[IPT - 1] - 1u : 0u) / a.shard_n);   // ... and the last
+        }
         if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
         const int heavy = __syncthreads_or(e[IPT - 1] - e_start > MAXD);   // S3: publishes s_E, x_s and the cleared window;
                                                            //     nobody reads lw_s any more
@@ -1211,7 +1328,11 @@ k3_resample(K3Args<real> a) {
             __syncthreads();   // S4
             // ---- phase E: coalesced copy-out -----------------------------------------------------
             const int64_t g0 = (int64_t)E0 - a.offset;
-            real* dwin = xdst + g0 + tid;                              // this thread's output column
+            // cross-shard migration: almost every tile's outputs [E0, E1) belong to ONE shard (the own
+            // one or a neighbour); such a tile takes the same copy-out as the single-GPU case, only
+            // with a destination in that shard's buffer (NVLink peer stores when it is not the own)
+            const bool one_shard = !peer || s_E[2] == s_E[3];
+            real* dwin = (!peer ? xdst + g0 : peer[s_E[2]] + ((int64_t)E0 - (int64_t)s_E[2] * a.shard_n)) + tid;
             int32_t* awin = a.ancestors ? a.ancestors + g0 + tid : nullptr;
             const int32_t abase = (int32_t)(a.offset + tile_base) - 1;   // markers are index + 1
             const int nfull = (int)(count / kK3Threads);                  // rows in which every thread has an output
@@ -1238,8 +1359,8 @@ k3_resample(K3Args<real> a) {
                 }
             };
             const bool tail = (int)(count - nfull * kK3Threads) > tid;
-            if (NXF > 0 && !peer && !awin) {
-                // the hot form: no ancestor trace, no migration; all addresses are immediates
+            if (NXF > 0 && one_shard && !awin) {
+                // the hot form: no ancestor trace, one destination shard; all addresses are immediates
                 const unsigned short* idp = ids + slot_t;
                 const unsigned short* idb = ids + slot_b;
                 const real* xg = x_s - 1;                                 // markers are index + 1
@@ -1378,6 +1499,44 @@ k3_resample(K3Args<real> a) {
             finish_body(ctrl, a.fin, s_mom, s_m);
             if (tid == 0) *a.ticket = 0u;
         }
+    } else if (a.shard.mail) {
+        // sharded: every CTA's peer stores are made visible system-wide before it takes a ticket; the
+        // last CTA folds the per-CTA moment partials into one record, stores it into every rank's
+        // mailbox and raises this rank's flag there -- which also tells the other ranks that all
+        // particles this rank migrated into their buffers have landed
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (NM > 0 && a.mom_parts) {
+                double acc[NMS];
+#pragma unroll
+                for (int k = 0; k < NMS; ++k) acc[k] = 0.0;
+                for (int p = tid; p < (int)gridDim.x; p += kK3Threads)        // fixed record -> thread assignment
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) acc[k] += __ldcg(a.mom_parts + (int64_t)p * NM + k);
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < NM; ++k) {
+                    const double v = warp_sum(acc[k]);
+                    if (lane == 0) s_mom[warp][k] = v;
+                }
+                __syncthreads();
+                if (tid < NM) {
+                    double t = 0;
+#pragma unroll
+                    for (int w = 0; w < kK3Warps; ++w) t += s_mom[w][tid];
+                    for (int g = 0; g < a.shard.n_shards; ++g) a.shard.mail[g]->mom[a.shard.rank][tid] = t;
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < a.shard.n_shards)
+                *(volatile unsigned long long*)&a.shard.mail[tid]->flag_mom[a.shard.rank] = a.shard.stamp;
+            if (tid == 0) *a.ticket = 0u;
+        }
     }
 }
 
@@ -1388,6 +1547,19 @@ constexpr int kFinishThreads = 1024;
 __global__ void __launch_bounds__(kFinishThreads) k_finish_step(Ctrl* ctrl, FinishArgs f) {
     __shared__ double s_w[kFinishThreads / 32][16];
     __shared__ double s_m[16];
+    finish_body(ctrl, f, s_w, s_m);
+}
+
+// sharded: wait until every rank has raised its moment flag for this step (= all cross-shard particle
+// stores into this rank's buffers have landed), then combine the G moment records in rank order
+__global__ void __launch_bounds__(kThreads) k_finish_step_sharded(Ctrl* ctrl, FinishArgs f, ShardCtx sc) {
+    __shared__ double s_w[kWarps][16];
+    __shared__ double s_m[16];
+    Mailbox* own = sc.mail[sc.rank];
+    mailbox_wait(own->flag_mom, sc.n_shards, sc.stamp);
+    f.mom_parts = &own->mom[0][0];
+    f.n_mom_parts = sc.n_shards;
+    f.mom_stride = 16;
     finish_body(ctrl, f, s_w, s_m);
 }
 
@@ -1672,7 +1844,7 @@ int stage(const Launch& l, int slot, const double* host, int count, double** dev
 
 template <typename real, class Model>
 int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, const void* noise_dev, uint64_t seed,
-              int64_t t, const K2Args* fin) {
+              int64_t t, const K2Args* fin, const ShardCtx* shard) {
     const smc_sir_desc* d = l.d;
     K1Args<real> a;
     a.ctrl = l.ctrl();
@@ -1687,6 +1859,8 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
     a.keys = philox_expand(seed);
     a.fuse_finalize = 0; a.ticket = l.ticket();
     memset(&a.fin, 0, sizeof(a.fin));
+    memset(&a.shard, 0, sizeof(a.shard));
+    if (shard && (mode & SMC_MODE_WEIGHT)) a.shard = *shard;
     if (fin && (mode & SMC_MODE_WEIGHT)) {
         a.fuse_finalize = 1;
         a.fin = *fin;
@@ -1703,14 +1877,14 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
 
 template <typename real> int dispatch_k1(const Launch& l, int model_id, const double* p, int np, int mode,
                                          const double* z_dev, const void* noise_dev, uint64_t seed, int64_t t,
-                                         const K2Args* fin) {
+                                         const K2Args* fin, const ShardCtx* shard = nullptr) {
     const smc_sir_desc* d = l.d;
     if (model_id == SMC_MODEL_STOCH_VOL) {
         // params: alpha, lq (= chol(Q)), beta, lr (= chol(R + 1e-12))
         SMC_REQUIRE(np == 4 && d->nx == 1 && d->nz == 1, "smc: STOCH_VOL needs 4 params and nx = nz = 1");
         StochVolModel<real> m;
         m.alpha = (real)p[0]; m.lq = (real)p[1]; m.beta = (real)p[2]; m.rinv = (real)(1.0 / p[3]);
-        return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin);
+        return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin, shard);
     }
     if (model_id == SMC_MODEL_LINEAR_GAUSSIAN) {
         // params: A (nx*nx), Lq (nx*nx lower), H (nz*nx), LRinv (nz*nz lower), all row-major
@@ -1724,7 +1898,7 @@ template <typename real> int dispatch_k1(const Launch& l, int model_id, const do
             for (int i = 0; i < NX_ * NX_; ++i) m.Lq[i] = (real)*q++;                             \
             for (int i = 0; i < NZ_ * NX_; ++i) m.H[i] = (real)*q++;                              \
             for (int i = 0; i < NZ_ * NZ_; ++i) m.LRinv[i] = (real)*q++;                          \
-            return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin);                     \
+            return launch_k1<real>(l, m, mode, z_dev, noise_dev, seed, t, fin, shard);                     \
         }
         SMC_LG_CASE(1, 1) SMC_LG_CASE(2, 1) SMC_LG_CASE(2, 2) SMC_LG_CASE(4, 1) SMC_LG_CASE(4, 2) SMC_LG_CASE(4, 4)
 #undef SMC_LG_CASE
@@ -1780,18 +1954,23 @@ int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
 }
 
 template <typename real>
-int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, int force, unsigned long long* total_out) {
+int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, int force, unsigned long long* total_out,
+                   const ShardCtx* shard = nullptr) {
     const smc_sir_desc* d = l.d;
     unsigned long long* rtot = l.agg();
     const unsigned grid = (unsigned)k3_grid(l.L.n_tiles, d->dtype, nxf) * kPreSplit;   // refines the resampler's partition
     const Ctrl* ctrl = l.ctrl();
     const real* w = static_cast<const real*>(wsrc);
+    ShardCtx sc;
+    memset(&sc, 0, sizeof(sc));
+    if (shard) sc = *shard;
+    unsigned int* ticket = l.ticket() + 2;
     if (linear_w)
         SMC_CHECK_CUDA(launch_pdl(k3a_range_totals<real, true>, grid, K3Geom<real>::THREADS, 0, l.st, ctrl, w, d->n,
-                                  d->n_global, l.L.n_tiles, rtot, force));
+                                  d->n_global, l.L.n_tiles, rtot, force, sc, ticket));
     else
         SMC_CHECK_CUDA(launch_pdl(k3a_range_totals<real, false>, grid, K3Geom<real>::THREADS, 0, l.st, ctrl, w, d->n,
-                                  d->n_global, l.L.n_tiles, rtot, force));
+                                  d->n_global, l.L.n_tiles, rtot, force, sc, ticket));
     SMC_CHECK_CUDA(cudaGetLastError());
     if (total_out) {
         k3a_sum_ranges<<<1, kThreads, 0, l.st>>>(l.ctrl(), rtot, (int)grid, total_out, force);
@@ -1803,7 +1982,7 @@ int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, in
 template <typename real>
 int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
               void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
-              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr) {
+              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr, const ShardCtx* shard = nullptr) {
     const smc_sir_desc* d = l.d;
     if (run_prepass) {
         if (int rc = launch_prepass<real>(l, linear_w, wsrc, nxf, force, nullptr)) return rc;
@@ -1835,6 +2014,8 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
         a.fin = *fin;
         a.fin.mom_parts = l.mom_parts();
     }
+    memset(&a.shard, 0, sizeof(a.shard));
+    if (shard) a.shard = *shard;
     const int64_t nt = l.L.n_tiles;
     if (linear_w) {
         SMC_REQUIRE(nxf == 0, "smc: linear-weight resampling is ancestors-only");
@@ -1974,6 +2155,7 @@ int smc_sir_finalize(const smc_sir_desc* d, double resample_thresh, double u_hos
     Launch l;
     if (int rc = check_desc(d, &l, stream)) return rc;
     K2Args a;
+    memset(&a, 0, sizeof(a));
     a.ctrl = l.ctrl();
     a.parts = n_parts_override > 0 ? parts_dev : l.k1_parts();
     a.n_parts = n_parts_override > 0 ? n_parts_override : (int)l.L.n_k1_blocks;
@@ -2129,6 +2311,7 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
         SMC_CHECK_CUDA(cudaGetLastError());
     }
     FinishArgs f;
+    memset(&f, 0, sizeof(f));
     f.stats = stats_row_dev;
     f.mom_parts = mom_parts_dev ? mom_parts_dev : l.mom_parts();
     f.n_mom_parts = n_mom_parts > 0 ? n_mom_parts : (inl ? (int)k3_grid(l.L.n_tiles, d->dtype, d->nx) : 0);
@@ -2179,6 +2362,67 @@ int smc_sir_step_resample(const smc_sir_desc* d, int32_t phases, double* stats_r
                    ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f)
                    : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f);
     }
+    return 0;
+}
+
+// ---- multi-GPU: whole sharded step with mailbox exchanges (no collective calls) ----------------
+uint64_t smc_mailbox_bytes(void) { return sizeof(Mailbox); }
+
+int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t model_id, const double* params_host,
+                         int32_t n_params, const double* z_dev, double resample_thresh, uint64_t seed, int64_t t,
+                         double* stats_row_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(ctx && ctx->mail_dev && ctx->peer_x_dev, "smc: shard context incomplete");
+    const int G = ctx->n_shards, rank = ctx->rank;
+    SMC_REQUIRE(G >= 1 && G <= kMaxShards && rank >= 0 && rank < G, "smc: bad shard geometry (rank %d of %d)", rank, G);
+    SMC_REQUIRE(d->n_global % G == 0 && d->n == d->n_global / G && d->offset == (int64_t)rank * d->n,
+                "smc: inconsistent shard geometry (rank %d of %d)", rank, G);
+    SMC_REQUIRE(d->nx <= kFusedNxMax && inline_moments(d), "smc: sharded step requires nx <= %d", kFusedNxMax);
+    SMC_REQUIRE(ctx->stamp > 0, "smc: stamp must be positive and increase by one per step");
+    SMC_REQUIRE(partial_stride(d->nx) <= 32 && moment_stride(d->nx) <= 16, "smc: record too wide for the mailbox");
+    ShardCtx sc;
+    sc.mail = reinterpret_cast<Mailbox* const*>(ctx->mail_dev);
+    sc.rank = rank; sc.n_shards = G; sc.stamp = ctx->stamp;
+    // 1. K1; its last CTA publishes the shard's partial record
+    const int mode = SMC_MODE_STEP | (resample_thresh > 1.0 ? 4 : 0);
+    SMC_REQUIRE(params_host != nullptr && z_dev != nullptr, "smc: params / observation missing");
+    int rc = d->dtype == SMC_F32
+                 ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, nullptr, seed, t, nullptr, &sc)
+                 : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, nullptr, seed, t, nullptr, &sc);
+    if (rc) return rc;
+    // 2. finalize once all G records have arrived
+    K2Args fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.ctrl = l.ctrl(); fin.stats = stats_row_dev; fin.n_global = d->n_global; fin.nx = d->nx;
+    fin.inline_moments = 1; fin.f32 = d->dtype == SMC_F32;
+    fin.thresh = resample_thresh; fin.u_host = -1.0; fin.seed = seed; fin.t = (uint32_t)t;
+    k2_finalize_sharded<<<1, kThreads, 0, l.st>>>(fin, sc);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.stats = stats_row_dev; f.nx = d->nx; f.inline_moments = 1;
+    f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+    if (resample_thresh > 0.0) {
+        // 3. range pre-pass; its last CTA publishes the shard's weight total
+        rc = d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, d->nx, 0, nullptr, &sc)
+                                 : launch_prepass<double>(l, false, d->logw_dev, d->nx, 0, nullptr, &sc);
+        if (rc) return rc;
+        // 4. resampling with migration by peer stores; its last CTA publishes the moment record
+        const bool want_m = !(d->flags & SMC_FLAG_NO_MOMENTS);
+        rc = d->dtype == SMC_F32
+                 ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, ctx->peer_x_dev, G, want_m, nullptr, rank, false,
+                                    nullptr, &sc)
+                 : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, ctx->peer_x_dev, G, want_m, nullptr, rank, false,
+                                     nullptr, &sc);
+        if (rc) return rc;
+        // 5. finish once all G moment flags are up
+        k_finish_step_sharded<<<1, kThreads, 0, l.st>>>(l.ctrl(), f, sc);
+    } else {
+        f.n_mom_parts = 0;
+        k_finish_step<<<1, kFinishThreads, 0, l.st>>>(l.ctrl(), f);
+    }
+    SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

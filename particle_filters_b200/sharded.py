@@ -53,7 +53,11 @@ def combine_partial_records(records: np.ndarray) -> np.ndarray:
     return out
 
 
-def frac_bits_for(n_global: int) -> int:
+def frac_bits_for(n_global: int, f32: bool = False) -> int:
+    """Fraction bits of the fixed-point CDF (csrc/sir_kernels.cu ``frac_bits_for``): 32 for fp32
+    populations, 62 - ceil(log2 N) clamped to [32, 60] for the fp64 parity mode."""
+    if f32:
+        return 32
     lg = 0
     while (1 << lg) < n_global:
         lg += 1
@@ -69,16 +73,16 @@ def shard_offsets(totals: List[int]) -> List[int]:
     return out
 
 
-def outputs_below(C_fix: int, u: float, n_global: int) -> int:
+def outputs_below(C_fix: int, u: float, n_global: int, f32: bool = False) -> int:
     """Number of stratified positions (u + i) / N below the fixed-point CDF value C (away from
     round-off ties this equals the device's closed form)."""
-    F = frac_bits_for(n_global)
+    F = frac_bits_for(n_global, f32)
     uq = int(np.floor(np.ldexp(u, F)))
     e = (C_fix + ((1 << F) - 1 - uq)) >> F
     return int(min(max(e, 0), n_global))
 
 
-def migration_plan(totals: List[int], u: float, n_global: int) -> np.ndarray:
+def migration_plan(totals: List[int], u: float, n_global: int, f32: bool = False) -> np.ndarray:
     """``plan[src, dst]`` = number of output particles whose ancestor lives on shard ``src``
     and whose index belongs to shard ``dst`` (what an alltoallv would have to move)."""
     G = len(totals)
@@ -86,8 +90,8 @@ def migration_plan(totals: List[int], u: float, n_global: int) -> np.ndarray:
     off = shard_offsets(totals) + [sum(int(t) for t in totals)]
     plan = np.zeros((G, G), dtype=np.int64)
     for s in range(G):
-        lo = outputs_below(off[s], u, n_global)
-        hi = n_global if s == G - 1 else outputs_below(off[s + 1], u, n_global)
+        lo = outputs_below(off[s], u, n_global, f32)
+        hi = n_global if s == G - 1 else outputs_below(off[s + 1], u, n_global, f32)
         for d in range(G):
             a, b = max(lo, d * shard), min(hi, (d + 1) * shard)
             plan[s, d] = max(0, b - a)
@@ -105,7 +109,10 @@ class _RawCuda:
 class ShardedSir:
     """One rank of a G-way sharded SIR filter (torch.distributed must be initialised, NCCL)."""
 
-    def __init__(self, n_global: int, nx: int, nz: int, *, dtype: str = "f32", trace_len: int = 1):
+    def __init__(self, n_global: int, nx: int, nz: int, *, dtype: str = "f32", trace_len: int = 1,
+                 exchange: str = "mailbox"):
+        """``exchange``: "mailbox" = records travel by NVLink peer stores issued inside the kernels
+        (no collective call in the step); "nccl" = three NCCL all-gathers per step (baseline)."""
         import torch
         import torch.distributed as dist
 
@@ -121,13 +128,15 @@ class ShardedSir:
         # particle buffers from raw cudaMalloc so that they can be exported through CUDA IPC
         elt = 4 if dtype == "f32" else 8
         ld = _round4(self.n)
+        self.exchange = exchange
+        self.stamp = 0
         self._raw = []
-        for _ in range(2):
+        for nbytes in (nx * ld * elt, nx * ld * elt, int(self.lib.smc_mailbox_bytes())):   # x0, x1, mailbox
             p = C.c_void_p()
-            _lib.check(self.lib.smc_dev_alloc(C.c_uint64(nx * ld * elt), C.byref(p)))
+            _lib.check(self.lib.smc_dev_alloc(C.c_uint64(nbytes), C.byref(p)))
             self._raw.append(p.value)
         typestr = "<f4" if dtype == "f32" else "<f8"
-        xbufs = [torch.as_tensor(_RawCuda(p, (nx, ld), typestr), device=dev) for p in self._raw]
+        xbufs = [torch.as_tensor(_RawCuda(p, (nx, ld), typestr), device=dev) for p in self._raw[:2]]
         self.eng = SirEngine(self.n, nx, nz, dtype=dtype, n_global=n_global, offset=self.rank * self.n,
                              trace_len=trace_len, x_buffers=xbufs)
         # exchange IPC handles; table = [buffer 0 of every rank][buffer 1 of every rank]
@@ -138,10 +147,10 @@ class ShardedSir:
             mine.append(bytes(h.raw))
         allh = [None] * self.G
         dist.all_gather_object(allh, mine)
-        table = np.zeros(2 * self.G, dtype=np.int64)
+        table = np.zeros(3 * self.G, dtype=np.int64)      # [x0 of every rank][x1 of every rank][mailboxes]
         self._opened = []
         for r in range(self.G):
-            for b in range(2):
+            for b in range(3):
                 if r == self.rank:
                     table[b * self.G + r] = self._raw[b]
                 else:
@@ -150,6 +159,8 @@ class ShardedSir:
                     self._opened.append(q.value)
                     table[b * self.G + r] = q.value
         self.peer_table = torch.from_numpy(table).to(dev)
+        self.ctx = _lib.ShardCtx(mail_dev=self.peer_table.data_ptr() + 8 * 2 * self.G,
+                                 peer_x_dev=self.peer_table.data_ptr(), rank=self.rank, n_shards=self.G, stamp=0)
         ps = int(self.lib.smc_partial_stride(nx))
         nm = nx + nx * (nx + 1) // 2
         self.rec_local = torch.zeros(ps, dtype=torch.float64, device=dev)
@@ -161,6 +172,22 @@ class ShardedSir:
         dist.barrier()
 
     def step(self, model_id, params, thresh, z_index, seed, t, row):
+        if self.exchange == "mailbox":
+            return self.step_mailbox(model_id, params, thresh, z_index, seed, t, row)
+        return self.step_nccl(model_id, params, thresh, z_index, seed, t, row)
+
+    def step_mailbox(self, model_id, params, thresh, z_index, seed, t, row):
+        """One sharded step = five launches, no collective: K1 (publishes the partial record),
+        finalize (waits for G records), range pre-pass (publishes the weight total), K3 (waits for
+        G totals, migrates by peer stores, publishes the moment record), finish (waits for G flags)."""
+        eng = self.eng
+        self.stamp += 1
+        self.ctx.stamp = self.stamp
+        kp, pp = _lib.as_doubles(params)
+        _lib.check(self.lib.smc_sir_step_sharded(eng._d, C.byref(self.ctx), model_id, pp, kp.size, eng._zptr(z_index),
+                                                 float(thresh), C.c_uint64(seed), t, eng._row(row), eng.stream))
+
+    def step_nccl(self, model_id, params, thresh, z_index, seed, t, row):
         eng, lib, dist = self.eng, self.lib, self.dist
         eng.propagate_weight(model_id, params, _lib.SMC_MODE_STEP, z_index=z_index, seed=seed, t=t)
         _lib.check(lib.smc_sir_reduce_partials(eng._d, C.c_void_p(self.rec_local.data_ptr()), eng.stream))
@@ -173,6 +200,14 @@ class ShardedSir:
         _lib.check(lib.smc_sir_reduce_moment_partials(eng._d, C.c_void_p(self.mom_local.data_ptr()), eng.stream))
         dist.all_gather_into_tensor(self.mom_all, self.mom_local)     # also orders the peer stores
         eng.finish_step(row=row, mom_parts=self.mom_all, n_mom_parts=self.G)
+
+    def shard_totals(self) -> np.ndarray:
+        """The G fixed-point weight totals of the last resampling step (rank order), as Python ints."""
+        if self.exchange == "nccl":
+            return self.tot_all.cpu().numpy().astype(object)
+        dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        mail = self.torch.as_tensor(_RawCuda(self._raw[2] + 8 * 3 * 16, (16,), "<i8"), device=dev)   # Mailbox.tot
+        return mail[: self.G].cpu().numpy().astype(np.uint64).astype(object)
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -211,7 +246,7 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     Q, R = np.array([[SIGMA ** 2]]), np.array([[BETA ** 2]])
     mid, params = StochVolSSM(ALPHA, BETA).device_functor(Q, R)
     Y = sv_observations(W + K + 2)
-    sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=W + K + 2)
+    sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=W + K + 2, exchange=getattr(args, "exchange", "mailbox"))
     sh.eng.init_gaussian(np.zeros(1), np.array([[SIGMA / np.sqrt(1 - ALPHA ** 2)]]), 42)
     sh.eng.set_observations(Y.reshape(-1, 1))
     thresh, seed = 2.0, 42
@@ -263,11 +298,13 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
                                    "systematic resampling every step with cross-shard migration "
                                    "(BASELINE.json configs[2])",
                        "n_particles": N, "nx": 1, "nz": 1, "parallelism": f"particle-sharded x{G}",
+                       "exchange": ("in-kernel NVLink peer stores + flags (no collective call)" if sh.exchange == "mailbox"
+                                    else "3 NCCL all-gathers per step"),
                        "l2": "per-step working set 3 x N/G x 4 B; no flush (strong scaling shrinks it)"},
             "clocks": clk,
             "e2e": {"value": N / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": 8,
                     "d2h_bytes_per_step": 8 * int(sh.eng.stride), "ms_per_step": float(e2e_dt.item()) * 1e3},
-            "gpu_launches": 7 * K,
+            "gpu_launches": (5 if sh.exchange == "mailbox" else 7) * K,
             "roofline": {"bound": "hbm", "kernel": "whole step (per-kernel split is taken at N=1)",
                          "achieved": 24.0 * value / 1e9 / G, "peak": peak, "unit": "GB/s",
                          "frac": 24.0 * value / 1e9 / G / peak, "traffic": None, "peak_source": peak_src},

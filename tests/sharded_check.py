@@ -32,15 +32,15 @@ def main():
     mid, params = StochVolSSM(0.95, 1.0).device_functor(Q, R)
     Y = np.random.default_rng(3).standard_normal(T) * 1.2
     ok = True
-    for thresh in (0.7, 2.0):
-        sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T)
+    for thresh, exchange in ((0.7, "mailbox"), (2.0, "mailbox"), (0.7, "nccl"), (2.0, "nccl")):
+        sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T, exchange=exchange)
         sh.eng.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
         sh.eng.set_observations(Y.reshape(-1, 1))
         for k in range(T):
             sh.step(mid, params, thresh, k, seed, k, k)
         rows = sh.eng.trace[:T].cpu().numpy()
         local = sh.eng.get_particles()[:, 0]
-        tot = sh.tot_all.cpu().numpy().astype(object)
+        tot = sh.shard_totals()
         gathered = [None] * G
         dist.all_gather_object(gathered, local)
         if rank == 0:
@@ -54,9 +54,9 @@ def main():
             dec_same = np.array_equal(rows[:, 2], rrows[:, 2])
             stat_err = np.max(np.abs(rows[:, :2] - rrows[:, :2]) / np.maximum(1.0, np.abs(rrows[:, :2])))
             mean_err = np.max(np.abs(rows[:, 4:6] - rrows[:, 4:6]))
-            plan = migration_plan([int(t) for t in tot], float(rows[-1, 3]), N)
+            plan = migration_plan([int(t) for t in tot], float(rows[-1, 3]), N, f32=True)
             crossing = int(plan.sum() - np.trace(plan))
-            print(f"[sharded_check] G={G} thresh={thresh}: resampled {int(rows[:, 2].sum())}/{T} steps, "
+            print(f"[sharded_check] G={G} {exchange} thresh={thresh}: resampled {int(rows[:, 2].sum())}/{T} steps, "
                   f"identical particles {same * 100:.4f}%, decisions equal {dec_same}, "
                   f"stat rel err {stat_err:.2e}, mean/var abs err {mean_err:.2e}, "
                   f"last-step cross-shard particles {crossing} of {N}")
