@@ -7,8 +7,8 @@ Importing the package does not need a GPU; running a filter does.
 
 from .particle_filter import DevicePFState, ParticleFilter, PFState  # noqa: F401
 from .ssm import (AcousticMeasurement, ExpMeasurement, LinearGaussianSSM, LinearMeasurement,  # noqa: F401
-                  StochVolSSM)
+                  Lorenz96SSM, StochVolSSM)
 from .ledh_particle_filter import LEDHConfig, LEDHFlowPF  # noqa: F401
 
-__all__ = ["ParticleFilter", "PFState", "DevicePFState", "StochVolSSM", "LinearGaussianSSM", "LEDHFlowPF",
+__all__ = ["ParticleFilter", "PFState", "DevicePFState", "StochVolSSM", "LinearGaussianSSM", "Lorenz96SSM", "LEDHFlowPF",
            "LEDHConfig", "LinearMeasurement", "AcousticMeasurement", "ExpMeasurement"]

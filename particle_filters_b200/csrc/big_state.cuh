@@ -1,0 +1,293 @@
+// High-dimensional state path of the SIR step (nx > 4), included by sir_kernels.cu:
+//   * k1_lorenz96: fused propagate + log-likelihood for the Lorenz-96 model of the reference's
+//     simulator (simulator/simulator_Lorenz_96.py: l96_rhs :35-58, rk4_step :61-83), one particle per
+//     thread with the whole state in registers (the RK4 stages are fully unrolled stencils);
+//   * k_moments_syrk: weighted mean / covariance of an (n, nx) particle set as a register-blocked
+//     X^T W X reduction (particle_filter.py:266-267) -- one pass over the particles instead of one
+//     pass per covariance entry.
+// BASELINE.json configs[3] ("C4"): nx = 40, every 4th variable observed, 20 RK4 sub-steps per
+// observation: ~1.9e4 FLOP per particle-step against 40 x 8 B of traffic -> bound by fp32 FMA issue.
+#pragma once
+
+namespace smc {
+
+constexpr int kL96MaxNx = 64;
+constexpr int kL96Threads = 128;
+
+template <typename real> struct L96Params {
+    real F, dt;
+    int32_t n_sub, obs_stride, nz;
+    real lq[kL96MaxNx];      // diagonal of chol(Q)
+    real rinv[kL96MaxNx];    // 1 / diagonal of chol(R + 1e-12 I)
+};
+
+// products / sums that must not be contracted in the fp64 parity mode (NumPy evaluates
+// (xp1 - xm2) * xm1 - x + F with one rounding per operation)
+__device__ __forceinline__ float l96_term(float xp1, float xm2, float xm1, float x, float F) {
+    return fmaf(xp1 - xm2, xm1, F - x);
+}
+__device__ __forceinline__ double l96_term(double xp1, double xm2, double xm1, double x, double F) {
+    return __dadd_rn(__dsub_rn(__dmul_rn(__dsub_rn(xp1, xm2), xm1), x), F);
+}
+__device__ __forceinline__ float axpy_nc(float a, float k, float x) { return fmaf(a, k, x); }
+__device__ __forceinline__ double axpy_nc(double a, double k, double x) { return __dadd_rn(x, __dmul_rn(a, k)); }
+
+template <typename real, int NX>
+__device__ __forceinline__ void l96_rhs_reg(const real (&x)[NX], real F, real (&k)[NX]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+        k[i] = l96_term(x[(i + 1) % NX], x[(i + NX - 2) % NX], x[(i + NX - 1) % NX], x[i], F);
+}
+
+// one RK4 step, x <- x + dt/6 (k1 + 2 k2 + 2 k3 + k4)   (rk4_step :78-83, same association)
+template <typename real, int NX>
+__device__ __forceinline__ void l96_rk4(real (&x)[NX], real F, real dt) {
+    real k[NX], xt[NX], acc[NX];
+    const real hdt = real(0.5) * dt;
+    l96_rhs_reg<real, NX>(x, F, k);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xt[i] = axpy_nc(hdt, k[i], x[i]); }
+    l96_rhs_reg<real, NX>(xt, F, k);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { acc[i] = axpy_nc(real(2), k[i], acc[i]); xt[i] = axpy_nc(hdt, k[i], x[i]); }
+    l96_rhs_reg<real, NX>(xt, F, k);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { acc[i] = axpy_nc(real(2), k[i], acc[i]); xt[i] = axpy_nc(dt, k[i], x[i]); }
+    l96_rhs_reg<real, NX>(xt, F, k);
+    const real dt6 = dt / real(6);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = axpy_nc(dt6, acc[i] + k[i], x[i]);
+}
+
+// the standard normal that draw_normals() hands to particle `gidx`, dimension d (same Philox block,
+// same Box-Muller lane), so results do not depend on which kernel propagates the particle
+__device__ inline float normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, float) {
+    uint32_t r[4];
+    philox_quad_keys(keys, gidx >> 2, t, kStreamProcess | (d << 8), r);
+    const int j = (int)(gidx & 3), p = j >> 1;
+    const float k2pow32inv = 2.3283064365386963e-10f, k2pi = 6.2831853071795865f;
+    const float u1 = fmaf((float)(p ? r[2] : r[0]), k2pow32inv, 0.5f * k2pow32inv);
+    const float u2 = fmaf((float)(p ? r[3] : r[1]), k2pow32inv * k2pi, 0.5f * k2pow32inv * k2pi);
+    const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
+    float s, c;
+    __sincosf(u2, &s, &c);
+    return (j & 1) ? rad * s : rad * c;
+}
+__device__ inline double normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, double) {
+    uint32_t r[4];
+    const int j = (int)(gidx & 3), h = j >> 1;
+    philox_quad_keys(keys, gidx >> 2, t, kStreamProcess | (d << 8) | ((uint32_t)h << 16), r);
+    double z2[2];
+    normals2_f64(r, z2);
+    return z2[j & 1];
+}
+
+template <typename real, int NX>
+__global__ void __launch_bounds__(kL96Threads) k1_lorenz96(K1Args<real> a, L96Params<real> p) {
+    constexpr int kW = kL96Threads / 32;
+    __shared__ real s_z[kL96MaxNx];
+    __shared__ real s_max[kW];
+    __shared__ double s_red[kW][2];
+    pdl_wait();
+    pdl_trigger();
+    const Ctrl* ctrl = a.ctrl;
+    real* x_all = ctrl->cur ? a.x1 : a.x0;
+    const bool uniform = ctrl->uniform != 0;
+    const real log_norm_prev = (real)ctrl->log_norm;
+    const real lw_uniform = (real)(-log((double)a.n_global));
+    const bool do_prop = a.mode & SMC_MODE_PROPAGATE, do_w = a.mode & SMC_MODE_WEIGHT;
+    const int tid = threadIdx.x;
+    if (do_w && tid < p.nz) s_z[tid] = (real)a.z[tid];
+    __syncthreads();
+
+    const real NEG_INF = -INFINITY;
+    real tm = NEG_INF, acc0 = 0, acc1 = 0;     // online (max, sum e, sum e^2)
+    for (int64_t i = (int64_t)blockIdx.x * kL96Threads + tid; i < a.n; i += (int64_t)gridDim.x * kL96Threads) {
+        real x[NX];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) x[d] = x_all[d * a.ld + i];
+        if (do_prop) {
+            for (int s = 0; s < p.n_sub; ++s) l96_rk4<real, NX>(x, p.F, p.dt);
+#pragma unroll
+            for (int d = 0; d < NX; ++d) {
+                const real nrm = a.noise ? a.noise[d * a.ld + i]
+                                         : normal_one(a.keys, (uint64_t)(a.offset + i), a.t, (uint32_t)d, real(0));
+                x[d] = fma(p.lq[d], nrm, x[d]);
+                x_all[d * a.ld + i] = x[d];
+            }
+        }
+        if (do_w) {
+            // h(x) = x[0 :: obs_stride]; y = (z - h(x)) / chol(R)_kk  (particle_filter.py:257-260, R diagonal)
+            real quad = 0;
+            int kobs = 0;
+#pragma unroll
+            for (int d = 0; d < NX; ++d) {
+                if (kobs < p.nz && d == kobs * p.obs_stride) {
+                    const real y = (s_z[kobs] - x[d]) * p.rinv[kobs];
+                    quad = fma(y, y, quad);
+                    ++kobs;
+                }
+            }
+            const real prev = uniform ? lw_uniform : prev_logweight(a.logw[i], log_norm_prev);
+            real v = prev - real(0.5) * quad;
+            v = fmax(v, NEG_INF);                       // NaN -> -inf (zero weight)
+            a.logw[i] = v;
+            if (v > tm) {
+                const real sc = fast_exp(tm - v);       // tm = -inf -> 0
+                acc0 *= sc; acc1 *= sc * sc; tm = v;
+            }
+            if (tm != NEG_INF) {
+                const real e = fast_exp(v - tm);
+                acc0 += e; acc1 = fma(e, e, acc1);
+            }
+        }
+    }
+    if (!do_w) return;
+    // ---- block combine (same record layout as k1_propagate_weight with 3 fields) -----------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const real wmax = warp_max(tm);
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    real bmax = s_max[0];
+#pragma unroll
+    for (int w = 1; w < kW; ++w) bmax = s_max[w] > bmax ? s_max[w] : bmax;
+    const real sc = (tm == NEG_INF) ? real(0) : fast_exp(tm - bmax);
+    const real v0 = warp_sum(acc0 * sc), v1 = warp_sum(acc1 * sc * sc);
+    if (lane == 0) { s_red[warp][0] = (double)v0; s_red[warp][1] = (double)v1; }
+    __syncthreads();
+    if (tid == 0) {
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) { s0 += s_red[w][0]; s1 += s_red[w][1]; }
+        double* out = a.parts + (int64_t)blockIdx.x * 3;
+        out[0] = (double)bmax; out[1] = s0; out[2] = s1;
+    }
+    // (the K2 finalize runs as its own launch here: a 10 us kernel next to milliseconds of RK4)
+}
+
+// ==============================================================================================
+// Weighted mean / covariance as one register-blocked X^T W X pass.
+//   raw[0] = sum w, raw[1 + a] = sum w y_a, raw[1 + nx + a nx + b] = sum w y_a y_b,  y = x - shift
+// CTA = 4 groups of 8 x 8 threads; a group takes every 4th particle of the staged tile and each of its
+// threads owns a BS x BS block of the covariance (BS = 5 covers nx <= 40, BS = 8 covers nx <= 64).
+// ==============================================================================================
+constexpr int kSyrkTile = 128;     // particles staged per iteration
+
+template <typename real, int BS>
+__global__ void __launch_bounds__(256) k_moments_syrk(const Ctrl* ctrl, const real* x0, const real* x1, const real* logw,
+                                                       int64_t n, int64_t ld, int nx, int post_flip, double* parts) {
+    constexpr int NP = 8 * BS;            // padded state dimension
+    constexpr int LDS = NP + 1;           // row stride (odd: conflict-free column walks)
+    extern __shared__ __align__(16) unsigned char syrk_smem[];
+    real* ys = reinterpret_cast<real*>(syrk_smem);          // [kSyrkTile][LDS]  y
+    real* yw = ys + kSyrkTile * LDS;                         // [kSyrkTile][LDS]  w * y
+    real* ws = yw + kSyrkTile * LDS;                         // [kSyrkTile]
+    const int cur = ctrl->cur ^ ((ctrl->do_resample && !post_flip) ? 1 : 0);
+    const real* x = cur ? x1 : x0;
+    const bool weighted = !ctrl->do_resample;
+    const double log_norm = ctrl->log_norm;
+    const int tid = threadIdx.x, grp = tid >> 6, ti = (tid >> 3) & 7, tj = tid & 7;
+    double acc[BS][BS], accm[BS], accw = 0;
+#pragma unroll
+    for (int a = 0; a < BS; ++a) {
+        accm[a] = 0;
+#pragma unroll
+        for (int b = 0; b < BS; ++b) acc[a][b] = 0;
+    }
+    for (int64_t base = (int64_t)blockIdx.x * kSyrkTile; base < n; base += (int64_t)gridDim.x * kSyrkTile) {
+        const int cnt = (int)((n - base) < kSyrkTile ? (n - base) : kSyrkTile);
+        __syncthreads();
+        // stage: thread handles particle (tid % 128), dimensions d = (tid / 128), +2, ... (coalesced over particles)
+        {
+            const int pl = tid & (kSyrkTile - 1);
+            real w = 0;
+            if (pl < cnt) w = weighted ? (real)exp((double)logw[base + pl] - log_norm) : real(1);
+            if (tid < kSyrkTile) ws[pl] = w;
+            for (int d = tid >> 7; d < NP; d += 2) {
+                real y = 0;
+                if (pl < cnt && d < nx) y = x[(int64_t)d * ld + base + pl] - (real)(d < kMaxNx ? ctrl->shift[d] : 0.0);
+                ys[pl * LDS + d] = y;
+                yw[pl * LDS + d] = w * y;
+            }
+        }
+        __syncthreads();
+        real t_acc[BS][BS], t_m[BS], t_w = 0;
+#pragma unroll
+        for (int a = 0; a < BS; ++a) {
+            t_m[a] = 0;
+#pragma unroll
+            for (int b = 0; b < BS; ++b) t_acc[a][b] = 0;
+        }
+        for (int pl = grp; pl < cnt; pl += 4) {
+            real ra[BS], rb[BS];
+#pragma unroll
+            for (int a = 0; a < BS; ++a) ra[a] = yw[pl * LDS + ti * BS + a];
+#pragma unroll
+            for (int b = 0; b < BS; ++b) rb[b] = ys[pl * LDS + tj * BS + b];
+#pragma unroll
+            for (int a = 0; a < BS; ++a)
+#pragma unroll
+                for (int b = 0; b < BS; ++b) t_acc[a][b] = fma(ra[a], rb[b], t_acc[a][b]);
+            if (tj == 0) {
+#pragma unroll
+                for (int a = 0; a < BS; ++a) t_m[a] += ra[a];
+                if (ti == 0) t_w += ws[pl];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < BS; ++a) {
+            accm[a] += (double)t_m[a];
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[a][b] += (double)t_acc[a][b];
+        }
+        accw += (double)t_w;
+    }
+    // ---- fold the 4 groups through shared memory, then one record per CTA ------------------------
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(syrk_smem);     // [4][1 + NP + NP * NP] doubles
+    constexpr int REC = 1 + NP + NP * NP;
+    double* mine = red + (size_t)grp * REC;
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b < BS; ++b) mine[1 + NP + (ti * BS + a) * NP + tj * BS + b] = acc[a][b];
+    if (tj == 0) {
+#pragma unroll
+        for (int a = 0; a < BS; ++a) mine[1 + ti * BS + a] = accm[a];
+        if (ti == 0) mine[0] = accw;
+    }
+    __syncthreads();
+    const int rec_out = 1 + nx + nx * nx;
+    double* out = parts + (size_t)blockIdx.x * rec_out;
+    for (int e = tid; e < rec_out; e += 256) {
+        int src;
+        if (e == 0) src = 0;
+        else if (e < 1 + nx) src = e;                                  // mean sums (unpadded index = padded index)
+        else { const int q = e - 1 - nx; src = 1 + NP + (q / nx) * NP + (q % nx); }
+        out[e] = red[src] + red[REC + src] + red[2 * REC + src] + red[3 * REC + src];
+    }
+}
+
+// combine the per-CTA records (fixed order) into the stats row: mean, covariance
+__global__ void __launch_bounds__(256) k_moments_syrk_finish(const Ctrl* ctrl, const double* parts, int n_parts, int nx,
+                                                              double* stats) {
+    extern __shared__ __align__(16) unsigned char syrk_smem[];
+    double* tot = reinterpret_cast<double*>(syrk_smem);     // 1 + nx + nx * nx
+    const int rec = 1 + nx + nx * nx;
+    for (int e = threadIdx.x; e < rec; e += 256) {
+        double s = 0;
+        for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * rec + e];
+        tot[e] = s;
+    }
+    __syncthreads();
+    double* mean = stats + SMC_STATS_HEADER;
+    double* cov = mean + nx;
+    const double W = tot[0];
+    for (int e = threadIdx.x; e < nx * nx; e += 256) {
+        const int a = e / nx, b = e % nx;
+        cov[e] = tot[1 + nx + e] / W - (tot[1 + a] / W) * (tot[1 + b] / W);
+    }
+    for (int a = threadIdx.x; a < nx; a += 256) mean[a] = (a < kMaxNx ? ctrl->shift[a] : 0.0) + tot[1 + a] / W;
+}
+
+}  // namespace smc

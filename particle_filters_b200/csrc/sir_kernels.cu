@@ -1769,6 +1769,8 @@ __global__ void __launch_bounds__(kThreads) k_gather_step(const Ctrl* ctrl, cons
 
 }  // namespace smc
 
+#include "big_state.cuh"
+
 // ================================================================================================
 // C-ABI
 // ================================================================================================
@@ -1787,6 +1789,7 @@ struct Launch {
     unsigned long long* agg() const { return reinterpret_cast<unsigned long long*>(ws + L.tile_agg); }
     unsigned int* ticket() const { return reinterpret_cast<unsigned int*>(ws + L.ticket); }
     double* mom_parts() const { return reinterpret_cast<double*>(ws + L.mom_parts); }
+    double* big_parts() const { return reinterpret_cast<double*>(ws + L.big_parts); }
 };
 
 // Launch with programmatic stream serialization (see pdl_wait / pdl_trigger).  Measured on B200 at
@@ -1904,6 +1907,40 @@ template <typename real> int dispatch_k1(const Launch& l, int model_id, const do
 #undef SMC_LG_CASE
         SMC_REQUIRE(false, "smc: LINEAR_GAUSSIAN supports (nx,nz) in {(1,1),(2,1),(2,2),(4,1),(4,2),(4,4)}, got (%d,%d)",
                     nx, nz);
+    }
+    if (model_id == SMC_MODEL_LORENZ96) {
+        // params: F, dt, n_sub, obs_stride, nz, then diag chol(Q) (nx), then diag chol(R + 1e-12 I) (nz)
+        const int nx = d->nx, nz = d->nz;
+        SMC_REQUIRE(np == 5 + nx + nz && nx <= kL96MaxNx, "smc: LORENZ96 parameter count mismatch");
+        L96Params<real> lp;
+        lp.F = (real)p[0]; lp.dt = (real)p[1]; lp.n_sub = (int)p[2]; lp.obs_stride = (int)p[3]; lp.nz = (int)p[4];
+        SMC_REQUIRE(lp.nz == nz && lp.n_sub >= 0 && lp.obs_stride >= 1 && (nz - 1) * lp.obs_stride < nx,
+                    "smc: LORENZ96 observation layout does not fit nx = %d", nx);
+        for (int i = 0; i < kL96MaxNx; ++i) { lp.lq[i] = 0; lp.rinv[i] = 0; }
+        for (int i = 0; i < nx; ++i) lp.lq[i] = (real)p[5 + i];
+        for (int i = 0; i < nz; ++i) lp.rinv[i] = (real)(1.0 / p[5 + nx + i]);
+        K1Args<real> a;
+        memset(&a, 0, sizeof(a));
+        a.ctrl = l.ctrl();
+        a.x0 = static_cast<real*>(d->x0_dev); a.x1 = static_cast<real*>(d->x1_dev);
+        a.logw = static_cast<real*>(d->logw_dev);
+        a.noise = static_cast<const real*>(noise_dev);
+        a.z = z_dev; a.parts = l.k1_parts();
+        a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
+        a.seed = seed; a.t = (uint32_t)t; a.mode = mode & 3;
+        a.keys = philox_expand(seed);
+        const unsigned grid = (unsigned)l.L.n_k1_blocks;
+        if (nx == 40) k1_lorenz96<real, 40><<<grid, kL96Threads, 0, l.st>>>(a, lp);
+        else if (nx == 8) k1_lorenz96<real, 8><<<grid, kL96Threads, 0, l.st>>>(a, lp);
+        else SMC_REQUIRE(false, "smc: LORENZ96 is compiled for nx in {8, 40}, got %d", nx);
+        SMC_CHECK_CUDA(cudaGetLastError());
+        if (fin && (mode & SMC_MODE_WEIGHT)) {   // finalize as its own launch (see big_state.cuh)
+            K2Args f2 = *fin;
+            f2.ctrl = l.ctrl(); f2.parts = l.k1_parts(); f2.n_parts = (int)grid;
+            k2_finalize<<<1, kThreads, 0, l.st>>>(f2);
+            SMC_CHECK_CUDA(cudaGetLastError());
+        }
+        return 0;
     }
     SMC_REQUIRE(false, "smc: unknown model id %d", model_id);
 }
@@ -2031,6 +2068,33 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
     SMC_REQUIRE(false, "smc: bad fused nx %d", nxf);
 }
 
+template <typename real, int BS>
+int launch_syrk_t(const Launch& l, double* stats_row_dev) {
+    const smc_sir_desc* d = l.d;
+    constexpr int NP = 8 * BS;
+    const size_t stage = sizeof(real) * (2 * (size_t)kSyrkTile * (NP + 1) + kSyrkTile);
+    const size_t fold = sizeof(double) * 4 * (1 + NP + (size_t)NP * NP);
+    const size_t smem = stage > fold ? stage : fold;
+    auto kern = k_moments_syrk<real, BS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int64_t grid = cdiv64(d->n, kSyrkTile);
+    if (grid > kSyrkMaxBlocks) grid = kSyrkMaxBlocks;
+    kern<<<(unsigned)grid, 256, smem, l.st>>>(l.ctrl(), (const real*)d->x0_dev, (const real*)d->x1_dev,
+                                              (const real*)d->logw_dev, d->n, d->ld, d->nx, 0, l.big_parts());
+    SMC_CHECK_CUDA(cudaGetLastError());
+    const size_t fsm = sizeof(double) * (1 + d->nx + (size_t)d->nx * d->nx);
+    k_moments_syrk_finish<<<1, 256, fsm, l.st>>>(l.ctrl(), l.big_parts(), (int)grid, d->nx, stats_row_dev);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename real> int launch_syrk(const Launch& l, double* stats_row_dev) {
+    return l.d->nx <= 40 ? launch_syrk_t<real, 5>(l, stats_row_dev) : launch_syrk_t<real, 8>(l, stats_row_dev);
+}
+
 }  // namespace
 
 extern "C" {
@@ -2084,7 +2148,8 @@ static int sir_propagate_weight_impl(const smc_sir_desc* d, int32_t model_id, co
     SMC_REQUIRE((mode & 3) >= 1 && mode <= 7, "smc: bad mode %d", mode);
     SMC_REQUIRE(!(mode & SMC_MODE_WEIGHT) || z_dev, "smc: z_dev required when weighting");
     SMC_REQUIRE(params_host != nullptr, "smc: params missing");
-    SMC_REQUIRE(!(d->flags & SMC_FLAG_GENERIC_MOMENTS), "smc: fused K1 carries inline moments; clear GENERIC_MOMENTS");
+    SMC_REQUIRE(model_id == SMC_MODEL_LORENZ96 || !(d->flags & SMC_FLAG_GENERIC_MOMENTS),
+                "smc: fused K1 carries inline moments; clear GENERIC_MOMENTS");
     return d->dtype == SMC_F32
                ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, fin)
                : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, fin);
@@ -2293,7 +2358,13 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
     // POST_MOMENTS_GENERIC: the particle set was modified after K3 (regularisation jitter) or was
     // not produced by K3 at all (multinomial gather), so its moments are recomputed from memory
     const bool inl = inline_moments(d) && !(d->flags & SMC_FLAG_POST_MOMENTS_GENERIC);
-    if (!inl && !no_m && stats_row_dev) {
+    if (!inl && !no_m && stats_row_dev && d->nx > kFusedNxMax) {
+        // high-dimensional states: one register-blocked X^T W X pass (weighted or uniform, decided on device)
+        SMC_REQUIRE(d->n == d->n_global, "smc: high-dimensional moments are single-shard only");
+        SMC_REQUIRE(d->nx <= 64, "smc: moments are compiled for nx <= 64");
+        if (int rc = (d->dtype == SMC_F32 ? launch_syrk<float>(l, stats_row_dev) : launch_syrk<double>(l, stats_row_dev)))
+            return rc;
+    } else if (!inl && !no_m && stats_row_dev) {
         // any-nx moments straight into the stats row (weighted or uniform, decided on device)
         SMC_REQUIRE(d->n == d->n_global, "smc: generic moments are single-shard only");
         const int nx = d->nx;

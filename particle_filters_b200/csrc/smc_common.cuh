@@ -56,6 +56,7 @@ constexpr int kK1Occ = SMC_K1_OCC;     // resident K1 CTAs per SM for the light 
 constexpr int kK1MaxBlocks = 148 * SMC_K1_GRID_PER_SM;  // persistent K1 grid: CTAs loop over chunks (B200: 148 SMs)
 constexpr int kMaxNx = 64;             // control block moment shift capacity
 constexpr int kFusedNxMax = 4;         // K3 moves the payload itself up to this many dims
+constexpr int kSyrkMaxBlocks = 148 * 2;  // grid of the high-dimensional moment kernel
 
 // Fixed-point CDF: "index units" (N * w) with F = 62 - ceil(log2 N) fractional bits (>= 32);
 // bit 63 of a published tile word is its "valid" flag.
@@ -82,7 +83,7 @@ static_assert(sizeof(Ctrl) <= 1024, "control block must fit its slot");
 
 // Workspace layout (all offsets 256-B aligned), computed identically on host and device.
 struct WsLayout {
-    size_t ctrl, params, k1_parts, tile_agg, ticket, mom_parts, total;   // tile_agg: 16-B {aggregate, inclusive} records
+    size_t ctrl, params, k1_parts, tile_agg, ticket, mom_parts, big_parts, total;   // tile_agg: 16-B {aggregate, inclusive} records
     int64_t n_k1_blocks, n_tiles;
 };
 constexpr int kParamSlots = 4;            // host->device staging slots for small matrices
@@ -119,6 +120,9 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16 + 65536);   // range totals of the pre-pass
     L.ticket = off;    off = align256(off + 256);
     L.mom_parts = off; off = align256(off + size_t(L.n_tiles) * moment_stride(nx) * sizeof(double));
+    // per-CTA records of the X^T W X moment kernel (nx > kFusedNxMax): (1 + nx + nx^2) doubles each
+    L.big_parts = off;
+    if (nx > kFusedNxMax) off = align256(off + size_t(kSyrkMaxBlocks) * (1 + nx + size_t(nx) * nx) * sizeof(double));
     L.total = off;
     return L;
 }

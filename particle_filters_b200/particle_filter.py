@@ -318,12 +318,16 @@ class ParticleFilter:
         self._generation += 1
         mid, params = self._functor
         eng.set_observations(z.reshape(1, -1))
+        host_rng = self._noise == "reference" or self.resample_method != "systematic" \
+            or self.regularize_after_resample
+        if not host_rng and mode == _lib.SMC_MODE_STEP:
+            # whole step on the device clock: K1 (+ finalize), range pre-pass, K3 (+ finish)
+            eng.step(mid, params, self.resample_thresh, z_index=0, seed=self._seed, t=self._t_phil)
+            return self._publish_device_state(eng, t_next)
         noise = None
         if (mode & _lib.SMC_MODE_PROPAGATE) and self._noise == "reference":
             noise = eng.upload_soa(self.rng.standard_normal((self.Np, self.nx)), self.nx)
         eng.propagate_weight(mid, params, mode, z_index=0, noise=noise, seed=self._seed, t=self._t_phil)
-        host_rng = self._noise == "reference" or self.resample_method != "systematic" \
-            or self.regularize_after_resample
         if host_rng:
             eng.finalize(self.resample_thresh, u=0.0)
             row = eng.read_row()
@@ -341,6 +345,9 @@ class ParticleFilter:
             if self.resample_thresh > 0:
                 eng.resample()
         eng.finish_step()
+        return self._publish_device_state(eng, t_next)
+
+    def _publish_device_state(self, eng, t_next: int) -> PFState:
         self._t_phil += 1
         row = eng.read_row()
         self.last_log_norm, self.last_ess, self.last_resampled = float(row[0]), float(row[1]), bool(row[2])

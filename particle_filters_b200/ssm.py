@@ -78,6 +78,52 @@ class LinearGaussianSSM(_Spec):
             [self.A.ravel(), np.tril(Lq).ravel(), self.H.ravel(), np.tril(LRinv).ravel()])
 
 
+class Lorenz96SSM(_Spec):
+    """Lorenz-96 forecast model of the reference's simulator: ``g`` = ``n_sub`` RK4 steps of
+    ``dx_a/dt = (x_{a+1} - x_{a-2}) x_{a-1} - x_a + F`` (simulator/simulator_Lorenz_96.py:
+    ``l96_rhs`` :35-58, ``rk4_step`` :61-83, same operation order), ``h(x) = x[::obs_stride]``
+    (``ObsModel.H`` with ``H_idx = arange(0, nx, obs_fraction)``, :386).  Q and R must be diagonal."""
+
+    smc_model_id = _lib.SMC_MODEL_LORENZ96
+
+    def __init__(self, nx: int = 40, F: float = 8.0, dt: float = 0.01, n_sub: int = 20, obs_stride: int = 4):
+        self.nx, self.F, self.dt, self.n_sub, self.obs_stride = int(nx), float(F), float(dt), int(n_sub), int(obs_stride)
+        self.H_idx = np.arange(0, self.nx, self.obs_stride)
+        self.nz = self.H_idx.size
+
+    def rhs(self, x):
+        x = np.asarray(x)
+        return (np.roll(x, -1, axis=-1) - np.roll(x, 2, axis=-1)) * np.roll(x, 1, axis=-1) - x + self.F
+
+    def rk4(self, x):
+        dt = self.dt
+        k1 = self.rhs(x)
+        k2 = self.rhs(x + 0.5 * dt * k1)
+        k3 = self.rhs(x + 0.5 * dt * k2)
+        k4 = self.rhs(x + dt * k3)
+        return x + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    def g(self, x, u=None):
+        x = np.asarray(x, float)
+        for _ in range(self.n_sub):
+            x = self.rk4(x)
+        return x
+
+    def h(self, x):
+        return np.asarray(x)[..., self.H_idx]
+
+    def device_functor(self, Q, R):
+        Q, R = np.asarray(Q, float), np.asarray(R, float)
+        if np.any(Q - np.diag(np.diag(Q))) or np.any(R - np.diag(np.diag(R))):
+            raise ValueError("Lorenz96SSM needs diagonal Q and R")
+        if Q.shape[0] != self.nx or R.shape[0] != self.nz:
+            raise ValueError("Q / R shapes do not match the Lorenz-96 spec")
+        Lq = _chol_jitter(Q, 1e-10)
+        LR = np.linalg.cholesky(R + 1e-12 * np.eye(self.nz))
+        return self.smc_model_id, np.concatenate(
+            [[self.F, self.dt, self.n_sub, self.obs_stride, self.nz], np.diag(Lq), np.diag(LR)])
+
+
 def spec_of(g, h):
     """Return the spec object if ``g`` and ``h`` are bound methods of one spec."""
     sg, sh = getattr(g, "__self__", None), getattr(h, "__self__", None)

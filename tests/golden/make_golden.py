@@ -29,7 +29,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("SMC_REFERENCE_ROOT", "/root/reference")
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
-from ssm_zoo import AcousticCVModel, LGSSMModel, Linear1DModel, SVModel  # noqa: E402
+from ssm_zoo import AcousticCVModel, LGSSMModel, Linear1DModel, Lorenz96Model, SVModel  # noqa: E402
 
 
 def load_ref(relpath: str, alias: str):
@@ -44,6 +44,7 @@ ref_pf = load_ref("models/particle_filter.py", "ref_particle_filter")
 ref_ledh = load_ref("models/LEDH_particle_filter.py", "ref_ledh_particle_filter")
 ref_sv = load_ref("simulator/simulator_sto_volatility_model.py", "ref_sim_sv")
 ref_lgssm = load_ref("simulator/simulator_LGSSM.py", "ref_sim_lgssm")
+ref_l96 = load_ref("simulator/simulator_Lorenz_96.py", "ref_sim_l96")
 
 
 class FixedU:
@@ -194,6 +195,34 @@ def gen_sir():
     print("sir_lgssm: resampled", int(out["resampled"].sum()), "/ 200")
 
 
+def gen_l96():
+    """C4-shaped (reduced): Lorenz-96 through the reference PF, dynamics = the reference's own
+    rk4_step / l96_rhs, observations = ObsModel.H with H_idx = arange(0, nx, obs_fraction)."""
+    for tag, nx, n_sub, stride, Np, T in (("nx8", 8, 5, 2, 400, 40), ("nx40", 40, 20, 4, 256, 12)):
+        m = Lorenz96Model(nx=nx, n_sub=n_sub, obs_stride=stride, q=0.1, r=1.0)
+        obs = ref_l96.ObsModel(H_idx=np.arange(0, nx, stride), R=m.R)
+
+        class RefDyn:
+            Q, R = m.Q, m.R
+
+            @staticmethod
+            def g(x, u=None):
+                for _ in range(n_sub):
+                    x = ref_l96.rk4_step(x, m.dt, lambda z: ref_l96.l96_rhs(z, m.F))
+                return x
+
+            h = staticmethod(obs.H)
+
+        X, Y = m.simulate(T, seed=42)
+        x0 = X[0] + 0.5
+        out = run_ref_pf(RefDyn, Y, Np=Np, seed=11, mean0=x0, cov0=0.5 * np.eye(nx))
+        out["X_true"] = X
+        for k in ("nx", "n_sub", "obs_stride", "F", "dt"):
+            out[k] = np.array(getattr(m, k))
+        np.savez_compressed(os.path.join(HERE, f"sir_l96_{tag}.npz"), **out)
+        print(f"sir_l96_{tag}: resampled", int(out["resampled"].sum()), "/", T)
+
+
 class ScriptedTracker:
     """GaussianTracker (LEDH_particle_filter.py:13-16) replaying scripted (m, P)."""
 
@@ -279,5 +308,6 @@ def gen_rng_checksum():
 if __name__ == "__main__":
     gen_resample()
     gen_sir()
+    gen_l96()
     gen_ledh()
     gen_rng_checksum()

@@ -52,6 +52,57 @@ class SVModel:
         return self.beta * np.exp(0.5 * X)
 
 
+class Lorenz96Model:
+    """Lorenz-96 forecast model in the reference simulator's formulas
+    (simulator/simulator_Lorenz_96.py: l96_rhs :35-58, rk4_step :61-83, ObsModel.H :147):
+    g = n_sub RK4 steps, h = x[::obs_stride]; Q = q^2 I, R = r^2 I."""
+
+    def __init__(self, nx=8, F=8.0, dt=0.01, n_sub=5, obs_stride=2, q=0.1, r=1.0):
+        self.nx, self.F, self.dt, self.n_sub, self.obs_stride = nx, F, dt, n_sub, obs_stride
+        self.H_idx = np.arange(0, nx, obs_stride)
+        self.nz = self.H_idx.size
+        self.Q = q ** 2 * np.eye(nx)
+        self.R = r ** 2 * np.eye(self.nz)
+
+    def rhs(self, x):
+        return (np.roll(x, -1, axis=-1) - np.roll(x, 2, axis=-1)) * np.roll(x, 1, axis=-1) - x + self.F
+
+    def rk4(self, x):
+        dt = self.dt
+        k1 = self.rhs(x)
+        k2 = self.rhs(x + 0.5 * dt * k1)
+        k3 = self.rhs(x + 0.5 * dt * k2)
+        k4 = self.rhs(x + dt * k3)
+        return x + (dt / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+
+    def g(self, x, u=None):
+        x = np.asarray(x, float)
+        for _ in range(self.n_sub):
+            x = self.rk4(x)
+        return x
+
+    def h(self, x):
+        return np.asarray(x)[..., self.H_idx]
+
+    g_batch = g
+    h_batch = h
+
+    def simulate(self, T, seed):
+        """Truth trajectory observed every n_sub RK4 steps (standard initial pattern, short spin-up)."""
+        rng = np.random.default_rng(seed)
+        x = np.full(self.nx, self.F)
+        x[::5] = self.F + 1.0
+        for _ in range(200):
+            x = self.rk4(x)
+        X, Y = np.empty((T, self.nx)), np.empty((T, self.nz))
+        r = np.sqrt(self.R[0, 0])
+        for t in range(T):
+            x = self.g(x)
+            X[t] = x
+            Y[t] = self.h(x) + r * rng.standard_normal(self.nz)
+        return X, Y
+
+
 class LGSSMModel:
     """README A/B/C/D linear-Gaussian model (reference README.md:104-113)."""
 

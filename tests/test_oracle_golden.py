@@ -11,7 +11,7 @@ import pytest
 
 from oracle import (SIROracle, ledh_step, systematic_ancestors, systematic_ancestors_loop)
 from oracle.build import c_systematic_ancestors
-from ssm_zoo import AcousticCVModel, LGSSMModel, Linear1DModel, SVModel
+from ssm_zoo import AcousticCVModel, LGSSMModel, Linear1DModel, SVModel, Lorenz96Model
 
 
 def test_golden_rng_stream_is_stable(golden):
@@ -70,6 +70,8 @@ def _run_oracle(g, model, T=None):
     ("sir_sv_regularized.npz", SVModel(0.95, 0.2, 1.0)),
     ("sir_sv_multinomial.npz", SVModel(0.95, 0.2, 1.0)),
     ("sir_lgssm.npz", LGSSMModel()),
+    ("sir_l96_nx8.npz", Lorenz96Model(nx=8, n_sub=5, obs_stride=2)),       # C4-shaped, reduced
+    ("sir_l96_nx40.npz", Lorenz96Model(nx=40, n_sub=20, obs_stride=4)),    # C4 dynamics at small N
 ])
 def test_sir_oracle_reproduces_reference_run(golden, name, model):
     """Whole filter runs: identical resampling decisions and ancestors; moments
