@@ -299,6 +299,10 @@ __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a
 }
 
 
+}  // namespace smc
+#include "ledh_fast.cuh"
+namespace smc {
+
 // ---- device-resident linear-Gaussian pieces (thread per particle, constants in shared memory) ----
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_ledh_propagate_linear(const real* x, real* eta0, real* eta, real* theta,
@@ -550,6 +554,21 @@ int launch_flow(const smc_ledh_desc* d, const double* P, const double* R, const 
     a.Hsup = Hsup; a.hsup = hsup;
     a.n = d->n; a.ld = d->ld; a.nx = nx; a.nz = nz; a.n_hp = n_hp > 0 ? n_hp : 0; a.kind = kind;
     a.L = L; a.step0 = step0; a.lam0 = lam0; a.dlam = dlam;
+    // compile-time-dimension fast path (lane = row, matrices in registers) for the benchmarked shapes
+    if (!Hsup) {
+#define SMC_LEDH_FAST(NX_, NZ_)                                                                          \
+        if (nx == NX_ && nz == NZ_) {                                                                    \
+            auto kf = k4_ledh_flow_fast<real, NX_, NZ_>;                                                 \
+            const size_t sm = LedhFastSmem<real, NX_, NZ_>::bytes(a.n_hp);                               \
+            SMC_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            kf<<<(unsigned)cdiv64(d->n, kLedhFastWarps), 32 * kLedhFastWarps, sm, st>>>(a);              \
+            SMC_CHECK_CUDA(cudaGetLastError());                                                          \
+            SMC_CHECK_CUDA(cudaFreeAsync(dev, st));                                                      \
+            return 0;                                                                                    \
+        }
+        SMC_LEDH_FAST(16, 25) SMC_LEDH_FAST(8, 16) SMC_LEDH_FAST(4, 9)
+#undef SMC_LEDH_FAST
+    }
     const int per_warp = 3 * nz * nx + nz * nz + 2 * nx * nx + 5 * nx + 3 * nz;
     const size_t smem = sizeof(real) * ((size_t)nx * nx + 2 * (size_t)nz * nz + nz + a.n_hp + (size_t)kLedhWarps * per_warp);
     SMC_REQUIRE(smem <= 227 * 1024, "smc_ledh: shared memory need %zu B exceeds 227 KiB (nx=%d nz=%d)", smem, nx, nz);
