@@ -987,6 +987,25 @@ __device__ inline void finish_body(Ctrl* ctrl, const FinishArgs& f, double (*s_w
     }
 }
 
+// explicit shared-memory loads by 32-bit address (volatile + memory clobber: the window is rewritten
+// every tile, so the loads must neither be cached in registers nor moved across the barriers)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory");
+    return (uint32_t)v;
+}
+template <typename real> __device__ __forceinline__ real lds_real(uint32_t saddr);
+template <> __device__ __forceinline__ float lds_real<float>(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+template <> __device__ __forceinline__ double lds_real<double>(uint32_t saddr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
 // Resident CTAs per SM of the resampler (shared memory: (1 + NXF) tiles + the id window)
 template <typename real, int NXF> struct K3Occ {
     static constexpr int value = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
@@ -1361,21 +1380,18 @@ k3_resample(K3Args<real> a) {
             const bool tail = (int)(count - nfull * kK3Threads) > tid;
             if (NXF > 0 && one_shard && !awin) {
                 // the hot form: no ancestor trace, one destination shard; all addresses are immediates
-                const unsigned short* idp = ids + slot_t;
-                const unsigned short* idb = ids + slot_b;
-                const real* xg = x_s - 1;                                 // markers are index + 1
-                auto hot = [&](const int it) {
-                    const int m0 = (int)idp[it * PADROW], m1 = (int)idb[it * PADROW];
-                    int li1 = m0 ? m0 : m1;
-                    if (li1 == 0) {                                       // three or more offspring: walk back
-                        uint32_t q = (uint32_t)(it * kK3Threads + tid) - 1u;
-                        do { --q; li1 = (int)ids[slot(q)]; } while (li1 == 0 && q > 0u);
-                        if (li1 == 0) li1 = 1;                            // (only on inconsistent input)
-                    }
+                // Row `it` = output position it * 256 + tid.  A slot that holds no marker (0) shares the
+                // ancestor of the slot before; a run of three or more offspring is rare and is finished
+                // after the unrolled rows (bit mask `pending`), so that the rows themselves are branch-free.
+                const uint32_t a_t = (uint32_t)__cvta_generic_to_shared(ids + slot_t);
+                const uint32_t a_b = (uint32_t)__cvta_generic_to_shared(ids + slot_b);
+                const uint32_t a_x = (uint32_t)__cvta_generic_to_shared(x_s) - (uint32_t)sizeof(real);   // markers are index + 1
+                uint32_t pending = 0;
+                auto payload = [&](const int it, const uint32_t li1) {
                     real xv[NXF > 0 ? NXF : 1];
 #pragma unroll
                     for (int d = 0; d < NXF; ++d) {
-                        xv[d] = xg[d * TILE + li1];
+                        xv[d] = lds_real<real>(a_x + (uint32_t)(d * TILE * sizeof(real)) + li1 * (uint32_t)sizeof(real));
                         dwin[d * a.ld + it * kK3Threads] = xv[d];
                     }
                     int k = 0;
@@ -1386,10 +1402,34 @@ k3_resample(K3Args<real> a) {
 #pragma unroll
                         for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xv[d], xv[d2], macc[k]); ++k; }
                 };
+                auto hot = [&](const int it) {
+                    const uint32_t m0 = lds_u16(a_t + (uint32_t)(it * PADROW * 2));
+                    const uint32_t m1 = lds_u16(a_b + (uint32_t)(it * PADROW * 2));
+                    const uint32_t li1 = m0 ? m0 : m1;
+                    if (li1) payload(it, li1);
+                    else pending |= 1u << it;
+                };
+                constexpr int NB = IPT - 2;          // rows virtually every tile has in full
+                if (nfull >= NB) {
 #pragma unroll
-                for (int it = 0; it < CH; ++it)
-                    if (it < nfull) hot(it);
+                    for (int it = 0; it < NB; ++it) hot(it);
+#pragma unroll
+                    for (int it = NB; it < CH; ++it)
+                        if (it < nfull) hot(it);
+                } else {
+#pragma unroll
+                    for (int it = 0; it < NB; ++it)
+                        if (it < nfull) hot(it);
+                }
                 if (tail) hot(nfull);
+                while (pending) {                     // three or more offspring: walk back to the marker
+                    const int it = __ffs(pending) - 1;
+                    pending &= pending - 1u;
+                    uint32_t q = (uint32_t)(it * kK3Threads + tid) - 1u, li1;
+                    do { --q; li1 = ids[slot(q)]; } while (li1 == 0u && q > 0u);
+                    if (li1 == 0u) li1 = 1u;          // (only on inconsistent input)
+                    payload(it, li1);
+                }
             } else {
                 for (int it = 0; it < nfull; ++it) row(it);
                 if (tail) row(nfull);

@@ -67,6 +67,10 @@ class SirEngine:
             self.stride = _lib.stats_stride(self.nx)
             self.trace = torch.zeros((max(1, trace_len), self.stride), dtype=torch.float64, device=self.device)
             self.zbuf = torch.zeros((max(1, trace_len), self.nz), dtype=torch.float64, device=self.device)
+            # pinned staging for the per-step host <-> device traffic of the class API (one observation in,
+            # one statistics row out): asynchronous copies on the engine's stream, one stream sync per step
+            self._z_pin = torch.zeros((self.nz,), dtype=torch.float64).pin_memory()
+            self._row_pin = torch.zeros((self.stride,), dtype=torch.float64).pin_memory()
         flags = 0
         if write_ancestors:
             flags |= _lib.SMC_FLAG_WRITE_ANCESTORS
@@ -149,6 +153,11 @@ class SirEngine:
         self.zbuf[: Z.shape[0]].copy_(torch.from_numpy(Z))
         return Z.shape[0]
 
+    def set_observation(self, z: np.ndarray, index: int = 0):
+        """Stage ONE observation (nz,) into slot ``index`` through pinned memory (no sync)."""
+        self._z_pin.numpy()[:] = np.asarray(z, dtype=np.float64).reshape(-1)
+        self.zbuf[index].copy_(self._z_pin, non_blocking=True)
+
     def _zptr(self, t: int):
         return C.c_void_p(self.zbuf.data_ptr() + 8 * self.nz * t)
 
@@ -202,7 +211,10 @@ class SirEngine:
         check(self.lib.smc_sir_step_resample(self._d, int(phases), self._row(row), self.stream))
 
     def read_row(self, row: int = 0) -> np.ndarray:
-        return self.trace[row % self.trace.shape[0]].cpu().numpy()
+        """Statistics row -> host (pinned staging, one stream synchronisation)."""
+        self._row_pin.copy_(self.trace[row % self.trace.shape[0]], non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return self._row_pin.numpy().copy()
 
     def run(self, model_id: int, params, Z: np.ndarray, thresh: float, seed: int, t0: int = 0) -> np.ndarray:
         """Enqueue ``len(Z)`` SIR steps without any host synchronisation and return

@@ -317,7 +317,7 @@ class ParticleFilter:
         eng = self._eng
         self._generation += 1
         mid, params = self._functor
-        eng.set_observations(z.reshape(1, -1))
+        eng.set_observation(z, 0)
         host_rng = self._noise == "reference" or self.resample_method != "systematic" \
             or self.regularize_after_resample
         if not host_rng and mode == _lib.SMC_MODE_STEP:
