@@ -229,38 +229,59 @@ def run_gpu_arm(args):
     e0, e1 = ev(), ev()
     torch.cuda.synchronize()
     e0.record()
-    for k in range(W, W + K):
-        one_step(k)
+    # K full filter steps, enqueued back to back: the engine's run() pipeline (for this bootstrap filter:
+    # one weighting launch, K - 1 fused resample->propagate launches with their range pre-passes, one
+    # closing resample; --no-fuse times the three-launch step instead)
+    fused_used = eng.enqueue(mid, params, K, thresh, seed, t0=W, z0=W, row0=W, fused=False if args.no_fuse else None)
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     ms_step = ms_total / K
 
-    # ---- per-kernel breakdown (same fused step, split at its three launch groups) --------------
-    phases = ("k1_propagate_weight+finalize", "k3a_range_totals", "k3_resample+finish")
-    acc = {p: 0.0 for p in phases}
-    NB = 4
-    for k in range(W + K, W + K + NB):   # extra steps reuse trace rows / observations via modulo
-        evs = [ev() for _ in range(4)]
-        kk = k % (W + K)
-        evs[0].record()
-        eng.step_weight(mid, params, thresh, z_index=kk, seed=seed, t=k, row=kk)
-        evs[1].record()
-        eng.step_resample(1, row=kk)
-        evs[2].record()
-        eng.step_resample(2, row=kk)
-        evs[3].record()
+    # ---- per-kernel breakdown: the same steps again with CUDA events between the launch groups -------
+    NB = 6
+    if fused_used:
+        phases = ("k3_resample_fused(+finish, +finalize)", "k3a_range_totals")
+        acc = {p: 0.0 for p in phases}
+        marks = []
+
+        def mark(tag):
+            e = ev()
+            e.record()
+            marks.append((tag, e))
+
+        eng._run_fused(mid, params, NB + 1, thresh, seed, t0=W + K, z0=0, row0=0, events=mark)
         torch.cuda.synchronize()
-        for i, p in enumerate(phases):
-            acc[p] += evs[i].elapsed_time(evs[i + 1]) / NB
+        for (tag, e_a), (_, e_b) in zip(marks[:-1], marks[1:]):
+            if tag == "fused":
+                acc[phases[0]] += e_a.elapsed_time(e_b) / NB
+            elif tag == "prepass":
+                acc[phases[1]] += e_a.elapsed_time(e_b) / NB
+        dom, alg_bytes = phases[0], 16.0 * N      # fused kernel: R logw, R x, W x, W logw (fp32, nx = 1)
+    else:
+        phases = ("k1_propagate_weight+finalize", "k3a_range_totals", "k3_resample+finish")
+        acc = {p: 0.0 for p in phases}
+        for k in range(W + K, W + K + NB):   # extra steps reuse trace rows / observations via modulo
+            evs = [ev() for _ in range(4)]
+            kk = k % (W + K)
+            evs[0].record()
+            eng.step_weight(mid, params, thresh, z_index=kk, seed=seed, t=k, row=kk)
+            evs[1].record()
+            eng.step_resample(1, row=kk)
+            evs[2].record()
+            eng.step_resample(2, row=kk)
+            evs[3].record()
+            torch.cuda.synchronize()
+            for i, p in enumerate(phases):
+                acc[p] += evs[i].elapsed_time(evs[i + 1]) / NB
+        dom = max((phases[0], phases[2]), key=lambda p: acc[p])
+        alg_bytes = 12.0 * N          # K1: R x, W x, W logw ; K3: R logw, R x, W x   (fp32, nx = 1)
     clk = clocks.stop()
     rows = eng.trace[: W + K].cpu().numpy()
     assert np.all(np.isfinite(rows[:, :5])), "non-finite filter statistics"
     assert np.all(rows[W:, 2] == 1.0), "bootstrap filter must resample every step"
 
     peak, peak_src = measured_peak()
-    dom = max((phases[0], phases[2]), key=lambda p: acc[p])
-    alg_bytes = 12.0 * N          # K1: R x, W x, W logw ; K3: R logw, R x, W x   (fp32, nx = 1)
     achieved = alg_bytes / (acc[dom] * 1e-3) / 1e9
     value = N / (ms_step * 1e-3)
     step_alg = 32.0               # SURVEY 8d closed form 16 nx + 16 bytes per particle-update
@@ -300,14 +321,16 @@ def run_gpu_arm(args):
                                "(BASELINE.json configs[2] / SURVEY 8d C3)",
                    "n_particles": N, "nx": 1, "nz": 1, "resample": "every step", "noise": "philox4x32-10 on chip",
                    "l2": "inputs (2 x 256 MiB per step) exceed the 126 MB L2; no flush needed"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": 3 * K,   # K1(+finalize), range pre-pass, K3(+finish)
+        "clocks": clk, "e2e": e2e, "gpu_launches": (2 * K + 1) if fused_used else 3 * K,   # fused: K pre-passes + K-1 fused + K1 + K3; else K1, pre-pass, K3 per step
+        "pipeline": ("fused resample->propagate (2 launches per step, 20 B per particle-update)" if fused_used
+                     else "three launches per step (28 B per particle-update)"),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": acc[dom]},
         "roofline_step": {"alg_bytes_per_particle_update": step_alg,
                           "achieved": step_alg * value / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": step_alg * value / 1e9 / peak,
-                          "note": "SURVEY 8d closed form 16 nx + 16 B; the pipeline actually moves 28 B (12 K1 + 4 pre-pass + 12 K3)"},
+                          "note": "SURVEY 8d closed form 16 nx + 16 B; the three-launch step moves 28 B (12 K1 + 4 pre-pass + 12 K3), the fused run() pipeline 20 B"},
         "kernel_ms": acc, "cpu_baseline": cpu,
         "filter": {"mean_last": float(rows[-1, 4]), "ess_last": float(rows[-1, 1])},
     }
@@ -323,6 +346,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=26)
     ap.add_argument("--exchange", default="mailbox", choices=("mailbox", "nccl"),
                     help="multi-GPU record exchange: in-kernel NVLink peer stores (default) or NCCL all-gathers")
+    ap.add_argument("--no-fuse", action="store_true", help="time the three-launch step instead of the fused run() pipeline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (kernel tuning sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":

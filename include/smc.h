@@ -207,6 +207,21 @@ int smc_sir_step_weight(const smc_sir_desc *d, int32_t model_id, const double *p
                         double *stats_row_dev, void *stream);
 int smc_sir_step_resample(const smc_sir_desc *d, int32_t phases, double *stats_row_dev, void *stream);
 
+/* Fused "resample step t-1, then propagate + weigh step t" for back-to-back runs of filters that
+ * resample every step (resample_thresh > 1), fp32, single GPU, nx <= 2 spec models: the resampler's
+ * copy-out hands every gathered particle straight to the model functor, so the resampled set never
+ * travels through HBM (20 B instead of 28 B per particle-update) and a step is two launches.
+ * Precondition: step t-1 has been weighed and finalized (smc_sir_step_weight or a previous fused call)
+ * and its range pre-pass has run (smc_sir_step_resample phase 1 / a previous fused call).  Reads
+ * d->logw_dev, writes the log-weights of step t to logw_out_dev (a second array; swap them for the next
+ * call), the moments of step t-1 to stats_prev_dev and the header of step t to stats_row_dev.  Finish
+ * the run with smc_sir_step_resample(d', 2, last_row) on the descriptor holding the last weights.
+ * phases: bit 1 = the fused kernel, bit 2 = the range pre-pass of step t (3 = both). */
+int smc_sir_step_fused(const smc_sir_desc *d, void *logw_out_dev, int32_t model_id,
+                       const double *params_host, int32_t n_params, const double *z_dev,
+                       double resample_thresh, uint64_t seed, int64_t t, double *stats_prev_dev,
+                       double *stats_row_dev, int32_t phases, void *stream);
+
 /* Multi-GPU step without collective calls.  Every rank owns a mailbox (smc_mailbox_bytes() of
  * zeroed, peer-mapped device memory, see smc_ipc_*).  The last CTA of K1 / the pre-pass / K3 stores
  * this rank's partial record / weight total / moment record straight into the mailbox of EVERY rank

@@ -88,6 +88,8 @@ _SIG = {
     "smc_sir_step_weight": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _D, C.c_int32, _P, _P, C.c_double,
                                       C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_sir_step_resample": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _P, _P]),
+    "smc_sir_step_fused": (C.c_int, [C.POINTER(SirDesc), _P, C.c_int32, _D, C.c_int32, _P, C.c_double, C.c_uint64,
+                                     C.c_int64, _P, _P, C.c_int32, _P]),
     "smc_mailbox_bytes": (C.c_uint64, []),
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),

@@ -689,6 +689,19 @@ struct FinishArgs {
     int64_t n_global;
 };
 
+// Fused "resample step t-1, then propagate + weigh step t" (run() pipeline, bootstrap filters): the
+// copy-out of the resampler hands every gathered particle straight to the model functor, so the
+// resampled set is never written to and re-read from HBM (20 B instead of 28 B per particle-update).
+struct NoFuse { static constexpr int NX = 0, NZ = 1; };
+template <typename real> struct FuseK1 {
+    real* lw_out;            // log-weights of step t (a second array: other CTAs still read step t-1's)
+    const double* z;         // observation of step t (device)
+    PhiloxKeys keys;
+    uint32_t t;
+    double* parts;           // per-CTA (max, sum e, sum e^2) records of step t
+    K2Args fin;              // finalize of step t, run by the last CTA after the finish of step t-1
+};
+
 template <typename real> struct K3Args {
     Ctrl* ctrl;
     const real* wsrc;           // log-weights (or linear normalised weights)
@@ -711,6 +724,8 @@ template <typename real> struct K3Args {
     unsigned int* ticket;       // arrival counter for fuse_finish (zero between launches)
     FinishArgs fin;
     ShardCtx shard;             // mail != nullptr: weight totals come from / moment record goes to the mailboxes
+    FuseK1<real> fk;            // used by the fused instantiations only
+    int32_t ranges_per_cta;     // pre-pass ranges owned by one CTA of this launch
 };
 
 // Tile geometry: THREADS threads own IPT consecutive items each (fp32: 256 x 16 = 4096-particle
@@ -805,9 +820,9 @@ __device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bia
 __host__ __device__ inline int64_t k3_range_begin(int64_t b, int64_t n_tiles, int64_t grid) {
     return (b * n_tiles) / grid;
 }
-// The pre-pass cuts every resampler range into kPreSplit sub-ranges (more CTAs in flight for a pure
-// streaming kernel): range b of the resampler starts where sub-range kPreSplit * b starts.
-constexpr int kPreSplit = 4;
+// The pre-pass cuts the tiles into R ranges with R a multiple of every resampler grid (148 x 12 ranges
+// for grids of 148 x {4, 3, 2} CTAs): CTA b of a grid of G owns ranges [b R / G, (b + 1) R / G), whose
+// first tile is floor(b T / G) -- the plain and the fused resampler can consume the same pre-pass.
 
 template <typename real, bool LINEAR_W>
 __global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_range_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
@@ -1007,8 +1022,9 @@ template <> __device__ __forceinline__ double lds_real<double>(uint32_t saddr) {
 }
 
 // Resident CTAs per SM of the resampler (shared memory: (1 + NXF) tiles + the id window)
-template <typename real, int NXF> struct K3Occ {
-    static constexpr int value = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
+template <typename real, int NXF, bool FUSED = false> struct K3Occ {
+    static constexpr int plain = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
+    static constexpr int value = FUSED ? (plain > 2 ? plain - 1 : 2) : plain;   // the fused functor needs the registers
 };
 
 // K3 proper.  Persistent grid: CTA b owns the contiguous tiles [b T / G, (b + 1) T / G) (static
@@ -1028,9 +1044,11 @@ template <typename real, int NXF> struct K3Occ {
 //      shared -> coalesced global stores, moments.
 //   Tiles with a very heavy item or more than W outputs take the marker + max-scan route instead,
 //   which costs O(window) whatever the skew.
-template <typename real, int NXF, bool LINEAR_W>
-__global__ void __launch_bounds__(K3Geom<real>::THREADS, K3Occ<real, NXF>::value)
-k3_resample(K3Args<real> a) {
+template <typename real, int NXF, bool LINEAR_W, class FM = NoFuse>
+__global__ void __launch_bounds__(K3Geom<real>::THREADS, K3Occ<real, NXF, (FM::NX > 0)>::value)
+k3_resample(K3Args<real> a, FM fm) {
+    constexpr bool FUSED = FM::NX > 0;
+    static_assert(!FUSED || (FM::NX == NXF && !LINEAR_W), "the fused functor moves the resampler's own payload");
     using G = K3Geom<real>;
     using unit = typename G::unit;
     constexpr int kK3Threads = G::THREADS, kK3Warps = kK3Threads / 32;
@@ -1136,7 +1154,7 @@ k3_resample(K3Args<real> a) {
             totals = own->tot;
         }
         unsigned long long part = 0;
-        for (int i = tid; i < (int)blockIdx.x * kPreSplit; i += kK3Threads) part += a.rtot[i];
+        for (int i = tid; i < (int)blockIdx.x * a.ranges_per_cta; i += kK3Threads) part += a.rtot[i];
         if (totals) for (int r = tid; r < a.rank; r += kK3Threads) part += __ldcg(totals + r);
         part = warp_sum(part);
         if (lane == 0) s_warp_tot[warp] = part;
@@ -1153,6 +1171,65 @@ k3_resample(K3Args<real> a) {
     double macc_d[NMS];
 #pragma unroll
     for (int k = 0; k < NMS; ++k) macc_d[k] = 0.0;
+
+    // ---- fused functor state: observation of step t, online (max, sum e, sum e^2) of its log-weights ---
+    constexpr int FNX = FUSED ? FM::NX : 1, FNZ = FUSED ? FM::NZ : 1;
+    real fz[FNZ];
+    real f_tm = -INFINITY, f_acc0 = 0, f_acc1 = 0;
+    const real f_lw_uniform = (real)(-log((double)a.n_global));
+    if constexpr (FUSED) {
+#pragma unroll
+        for (int k = 0; k < FNZ; ++k) fz[k] = (real)a.fk.z[k];
+    }
+    // one quad of resampled particles (global indices gi0 .. gi0 + 3, gi0 % 4 == 0; `mask` = lanes that
+    // belong to this tile): Philox normals of step t, propagate, log-likelihood, stores, online sums --
+    // exactly k1_chunk's arithmetic on exactly its Philox blocks, so the particles are bit-identical
+    // to the unfused pipeline's
+    auto process_quad = [&](real (&xt)[FNX][4], const int64_t gi0, const unsigned mask, real* xout) {
+        if constexpr (FUSED) {
+            real nrm[FNX][4];
+            Draw<FNX>::run(a.fk.keys, (uint64_t)gi0 >> 2, a.fk.t, nrm);
+            real lwq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                real xv[FNX], nv[FNX];
+#pragma unroll
+                for (int d = 0; d < FNX; ++d) { xv[d] = xt[d][j]; nv[d] = nrm[d][j]; }
+                fm.propagate(xv, nv);
+#pragma unroll
+                for (int d = 0; d < FNX; ++d) xt[d][j] = xv[d];
+                real v = f_lw_uniform + fm.loglik(xv, fz);
+                v = fmax(v, real(-INFINITY));                     // NaN -> -inf (zero weight)
+                lwq[j] = ((mask >> j) & 1u) ? v : real(-INFINITY);
+            }
+            const int64_t li = gi0 - a.offset;
+            if (mask == 15u) {
+#pragma unroll
+                for (int d = 0; d < FNX; ++d) store4<real>(xout + d * a.ld + li, xt[d]);
+                store4<real>(a.fk.lw_out + li, lwq);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((mask >> j) & 1u) {
+#pragma unroll
+                        for (int d = 0; d < FNX; ++d) xout[d * a.ld + li + j] = xt[d][j];
+                        a.fk.lw_out[li + j] = lwq[j];
+                    }
+            }
+            real cmax = fmax(fmax(lwq[0], lwq[1]), fmax(lwq[2], lwq[3]));
+            if (cmax > f_tm) {
+                const real sc = fast_exp(f_tm - cmax);            // f_tm = -inf -> 0
+                f_acc0 *= sc; f_acc1 *= sc * sc; f_tm = cmax;
+            }
+            if (f_tm != real(-INFINITY)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const real e = fast_exp(lwq[j] - f_tm);       // masked lanes: exp(-inf) = 0
+                    f_acc0 += e; f_acc1 = fma(e, e, f_acc1);
+                }
+            }
+        }
+    };
 
     // window slot of output position s: two pad slots per IPT positions, so that the CTA-wide marker
     // stores of phase D (lane stride ~ IPT positions) spread over the banks
@@ -1307,7 +1384,9 @@ k3_resample(K3Args<real> a) {
         // CDF): a tile whose output range is not inside [0, N] writes nothing.
         const bool sane = E0 <= E1 && E1 <= fs.n_global;
         const uint32_t count = sane ? E1 - E0 : 0u;
-        const bool direct = !heavy && count <= (uint32_t)W;
+        // fused mode lays the window out on global quads: position r sits at r + (E0 & 3)
+        const uint32_t s0 = FUSED ? (E0 & 3u) : 0u;
+        const bool direct = !heavy && count + s0 <= (uint32_t)W;
 
         real macc[NMS];
 #pragma unroll
@@ -1340,11 +1419,54 @@ k3_resample(K3Args<real> a) {
 #pragma unroll
                 for (int k = 0; k < IPT; ++k) {
                     const uint32_t r1 = e[k] - E0;
-                    if (r0 < r1 && r1 <= count) ids[slot(r0)] = (unsigned short)(tid * IPT + k + 1);
+                    if (r0 < r1 && r1 <= count) ids[slot(r0 + s0)] = (unsigned short)(tid * IPT + k + 1);
                     r0 = r1;
                 }
             }
             __syncthreads();   // S4
+            if constexpr (FUSED) {
+                // ---- phase E (fused): gather a quad of ancestors, propagate + weigh it, store step t ------
+                const uint32_t wend = s0 + count;                         // valid window positions [s0, wend)
+                const uint32_t nquad = (wend + 3u) >> 2;
+                const int64_t gw0 = (int64_t)(E0 - s0);                   // global index of window position 0
+                for (uint32_t q = tid; q < nquad; q += kK3Threads) {
+                    const uint32_t w0 = 4u * q, sl = slot(w0);            // four consecutive slots of one 16-group
+                    const uint32_t p01 = *reinterpret_cast<const uint32_t*>(ids + sl);
+                    const uint32_t p23 = *reinterpret_cast<const uint32_t*>(ids + sl + 2);
+                    uint32_t m[4] = {p01 & 0xffffu, p01 >> 16, p23 & 0xffffu, p23 >> 16};
+                    if (m[0] == 0u && w0 > s0) {                          // ancestor of the slots before this quad
+                        uint32_t qq = w0;
+                        do { --qq; m[0] = ids[slot(qq)]; } while (m[0] == 0u && qq > 0u);
+                    }
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) m[j] = m[j] ? m[j] : m[j - 1];
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (w0 + j >= s0 && w0 + j < wend) mask |= 1u << j;
+                        if (m[j] == 0u) m[j] = 1u;                        // lanes in front of the tile's first output
+                    }
+                    real xt[FNX][4];
+#pragma unroll
+                    for (int d = 0; d < FNX; ++d)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xt[d][j] = x_s[d * TILE + m[j] - 1];
+                    // post-resample moments of step t-1 (the gathered, not yet propagated, particles)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((mask >> j) & 1u) {
+                            real xc[FNX];
+                            int k = 0;
+#pragma unroll
+                            for (int d = 0; d < FNX; ++d) { xc[d] = xt[d][j] - shift[d]; macc[k] += xc[d]; ++k; }
+#pragma unroll
+                            for (int d = 0; d < FNX; ++d)
+#pragma unroll
+                                for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fma(xc[d], xc[d2], macc[k]); ++k; }
+                        }
+                    process_quad(xt, gw0 + w0, mask, xdst);
+                }
+            } else {
             // ---- phase E: coalesced copy-out -----------------------------------------------------
             const int64_t g0 = (int64_t)E0 - a.offset;
             // cross-shard migration: almost every tile's outputs [E0, E1) belong to ONE shard (the own
@@ -1434,6 +1556,7 @@ k3_resample(K3Args<real> a) {
                 for (int it = 0; it < nfull; ++it) row(it);
                 if (tail) row(nfull);
             }
+            }   // !FUSED
         } else {
             // ---- skewed tile / cross-shard migration: head markers + max-scan fill, window by window
             for (uint32_t wbase = 0; wbase < count; wbase += W) {
@@ -1505,6 +1628,29 @@ k3_resample(K3Args<real> a) {
                 }
                 __syncthreads();
             }
+            if constexpr (FUSED) {
+                // skewed tile: the window loop has written the resampled particles of this tile to the
+                // destination buffer; run the functor over them in place (block-visible after the barrier)
+                if (count > 0u) {
+                    const int64_t gq0 = (int64_t)(E0 & ~3u);
+                    const uint32_t nq = (uint32_t)((((int64_t)E1 + 3) >> 2) - (gq0 >> 2));
+                    for (uint32_t q = tid; q < nq; q += kK3Threads) {
+                        const int64_t gi0 = gq0 + 4 * (int64_t)q;
+                        unsigned mask = 0;
+                        real xt[FNX][4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int64_t gi = gi0 + j;
+                            const bool valid = gi >= (int64_t)E0 && gi < (int64_t)E1;
+                            if (valid) mask |= 1u << j;
+#pragma unroll
+                            for (int d = 0; d < FNX; ++d) xt[d][j] = valid ? xdst[d * a.ld + gi - a.offset] : real(0);
+                        }
+                        process_quad(xt, gi0, mask, xdst);
+                    }
+                }
+                __syncthreads();
+            }
         }
         if (NM > 0) {
 #pragma unroll
@@ -1512,6 +1658,28 @@ k3_resample(K3Args<real> a) {
         }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+    if constexpr (FUSED) {
+        // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
+        __shared__ real s_fmax[kK3Warps];
+        __shared__ double s_fred[kK3Warps][2];
+        const real wmax = warp_max(f_tm);
+        if (lane == 0) s_fmax[warp] = wmax;
+        __syncthreads();
+        real bmax = s_fmax[0];
+#pragma unroll
+        for (int w = 1; w < kK3Warps; ++w) bmax = s_fmax[w] > bmax ? s_fmax[w] : bmax;
+        const real sc = (f_tm == real(-INFINITY)) ? real(0) : fast_exp(f_tm - bmax);
+        const real v0 = warp_sum(f_acc0 * sc), v1 = warp_sum(f_acc1 * sc * sc);
+        if (lane == 0) { s_fred[warp][0] = (double)v0; s_fred[warp][1] = (double)v1; }
+        __syncthreads();
+        if (tid == 0) {
+            double t0 = 0, t1 = 0;
+#pragma unroll
+            for (int w = 0; w < kK3Warps; ++w) { t0 += s_fred[w][0]; t1 += s_fred[w][1]; }
+            double* out = a.fk.parts + (int64_t)blockIdx.x * 3;
+            out[0] = (double)bmax; out[1] = t0; out[2] = t1;
+        }
+    }
 
     // ---- per-CTA post-resample moment partials (+ the fused finish in the last CTA to arrive) ----
     if (NM > 0 && a.mom_parts) {
@@ -1537,6 +1705,15 @@ k3_resample(K3Args<real> a) {
         if (s_last) {
             __threadfence();
             finish_body(ctrl, a.fin, s_mom, s_m);
+            if constexpr (FUSED) {
+                // ... then the finalize of step t from the records every CTA has just written
+                __shared__ double s_fout[32];
+                __shared__ double s_ftmp[kWarps];
+                __syncthreads();
+                K2Args f2 = a.fk.fin;
+                f2.ctrl = ctrl; f2.parts = a.fk.parts; f2.n_parts = (int)gridDim.x;
+                finalize_body(f2, s_fout, s_ftmp);
+            }
             if (tid == 0) *a.ticket = 0u;
         }
     } else if (a.shard.mail) {
@@ -2001,20 +2178,28 @@ inline int k3_occupancy(int dtype, int nxf) {
     if (dtype == SMC_F32) return nxf <= 1 ? 4 : (nxf == 2 ? 3 : 2);
     return nxf <= 1 ? 3 : 2;
 }
-inline int64_t k3_grid(int64_t n_tiles, int dtype, int nxf) {
-    const int64_t g = (int64_t)sm_count() * k3_occupancy(dtype, nxf);
+inline int64_t k3_grid(int64_t n_tiles, int dtype, int nxf, bool fused = false) {
+    int occ = k3_occupancy(dtype, nxf);
+    if (fused) occ = occ > 2 ? occ - 1 : 2;
+    const int64_t g = (int64_t)sm_count() * occ;
     return n_tiles < g ? n_tiles : g;
 }
+// number of pre-pass ranges: a common multiple of all resampler grids when the problem is large enough
+// (then plain and fused resamplers share a pre-pass), else one range per CTA of the plain grid
+inline int64_t k3_ranges(int64_t n_tiles, int dtype, int nxf) {
+    const int64_t big = (int64_t)sm_count() * 12;
+    return n_tiles >= big ? big : k3_grid(n_tiles, dtype, nxf);
+}
 
-template <typename real, int NXF, bool LIN>
-int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
+template <typename real, int NXF, bool LIN, class FM = NoFuse>
+int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles, FM fm = FM()) {
     using G = K3Geom<real>;
-    static_assert(K3Occ<real, NXF>::value >= 1, "occupancy table");
+
     constexpr int PADROW = G::THREADS + 2 * (G::THREADS / G::IPT);
     constexpr size_t ids_bytes = (size_t)(8 + (G::IPT + 2) * PADROW + 8) * 2;   // guard + window + tail, u16 slots
     static_assert(ids_bytes % 16 == 0, "marker window must be a whole number of 16-byte units");
     const size_t smem = sizeof(real) * G::THREADS * G::IPT * (1 + NXF) + ids_bytes;
-    auto kern = k3_resample<real, NXF, LIN>;
+    auto kern = k3_resample<real, NXF, LIN, FM>;
     static bool attr_set = false;   // one flag per template instantiation
     if (!attr_set) {
         SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2023,9 +2208,15 @@ int launch_k3_t(const Launch& l, K3Args<real>& a, int64_t n_tiles) {
         attr_set = true;
     }
     a.n_tiles = n_tiles;
-    const int64_t grid = k3_grid(n_tiles, sizeof(real) == 4 ? SMC_F32 : SMC_F64, NXF);
+    constexpr bool kFused = FM::NX > 0;
+    const int dt = sizeof(real) == 4 ? SMC_F32 : SMC_F64;
+    const int64_t grid = k3_grid(n_tiles, dt, NXF, kFused);
+    const int64_t ranges = k3_ranges(n_tiles, dt, NXF);
+    SMC_REQUIRE(ranges % grid == 0, "smc: resampler grid %lld does not divide the %lld pre-pass ranges (population too small "
+                "for this variant)", (long long)grid, (long long)ranges);
+    a.ranges_per_cta = (int32_t)(ranges / grid);
     if (a.fuse_finish) a.fin.n_mom_parts = (int)grid;
-    SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, G::THREADS, smem, l.st, a));
+    SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, G::THREADS, smem, l.st, a, fm));
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -2035,7 +2226,7 @@ int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, in
                    const ShardCtx* shard = nullptr) {
     const smc_sir_desc* d = l.d;
     unsigned long long* rtot = l.agg();
-    const unsigned grid = (unsigned)k3_grid(l.L.n_tiles, d->dtype, nxf) * kPreSplit;   // refines the resampler's partition
+    const unsigned grid = (unsigned)k3_ranges(l.L.n_tiles, d->dtype, nxf);   // refines every resampler partition
     const Ctrl* ctrl = l.ctrl();
     const real* w = static_cast<const real*>(wsrc);
     ShardCtx sc;
@@ -2057,14 +2248,10 @@ int launch_prepass(const Launch& l, bool linear_w, const void* wsrc, int nxf, in
 }
 
 template <typename real>
-int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
-              void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
-              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr, const ShardCtx* shard = nullptr) {
+void fill_k3_args(const Launch& l, K3Args<real>& a, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
+                  void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals, int rank,
+                  const FinishArgs* fin, const ShardCtx* shard) {
     const smc_sir_desc* d = l.d;
-    if (run_prepass) {
-        if (int rc = launch_prepass<real>(l, linear_w, wsrc, nxf, force, nullptr)) return rc;
-    }
-    K3Args<real> a;
     a.ctrl = l.ctrl();
     a.wsrc = static_cast<const real*>(wsrc);
     a.x0 = static_cast<const real*>(d->x0_dev);
@@ -2093,6 +2280,18 @@ int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigne
     }
     memset(&a.shard, 0, sizeof(a.shard));
     if (shard) a.shard = *shard;
+    memset(&a.fk, 0, sizeof(a.fk));
+}
+
+template <typename real>
+int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
+              void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
+              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr, const ShardCtx* shard = nullptr) {
+    if (run_prepass) {
+        if (int rc = launch_prepass<real>(l, linear_w, wsrc, nxf, force, nullptr)) return rc;
+    }
+    K3Args<real> a;
+    fill_k3_args<real>(l, a, wsrc, nxf, cdf_offset, force, peer, n_shards, want_moments, totals, rank, fin, shard);
     const int64_t nt = l.L.n_tiles;
     if (linear_w) {
         SMC_REQUIRE(nxf == 0, "smc: linear-weight resampling is ancestors-only");
@@ -2133,6 +2332,34 @@ int launch_syrk_t(const Launch& l, double* stats_row_dev) {
 }
 template <typename real> int launch_syrk(const Launch& l, double* stats_row_dev) {
     return l.d->nx <= 40 ? launch_syrk_t<real, 5>(l, stats_row_dev) : launch_syrk_t<real, 8>(l, stats_row_dev);
+}
+
+// ---- fused resample(t-1) -> propagate + weigh(t) (run() pipeline of bootstrap filters, fp32) ------------
+template <class Model>
+int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const double* z_dev, double resample_thresh,
+                 uint64_t seed, int64_t t, double* stats_prev_dev, double* stats_row_dev, int phases) {
+    const smc_sir_desc* d = l.d;
+    if (!(phases & 1)) return launch_prepass<float>(l, false, logw_out_dev, d->nx, 0, nullptr);
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.stats = stats_prev_dev; f.nx = d->nx; f.inline_moments = 1;
+    f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+    K3Args<float> a;
+    fill_k3_args<float>(l, a, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, !(d->flags & SMC_FLAG_NO_MOMENTS), nullptr, 0, &f,
+                        nullptr);
+    a.fk.lw_out = static_cast<float*>(logw_out_dev);
+    a.fk.z = z_dev;
+    a.fk.keys = philox_expand(seed);
+    a.fk.t = (uint32_t)t;
+    a.fk.parts = l.k1_parts();            // <= 592 records of 3 doubles: fits the K1 partial area
+    memset(&a.fk.fin, 0, sizeof(a.fk.fin));
+    a.fk.fin.stats = stats_row_dev; a.fk.fin.n_global = d->n_global; a.fk.fin.nx = d->nx;
+    a.fk.fin.inline_moments = 0; a.fk.fin.f32 = 1;
+    a.fk.fin.thresh = resample_thresh; a.fk.fin.u_host = -1.0; a.fk.fin.seed = seed; a.fk.fin.t = (uint32_t)t;
+    if (int rc = launch_k3_t<float, Model::NX, false, Model>(l, a, l.L.n_tiles, m)) return rc;
+    if (!(phases & 2)) return 0;
+    // pre-pass of step t on the weights just written
+    return launch_prepass<float>(l, false, logw_out_dev, d->nx, 0, nullptr);
 }
 
 }  // namespace
@@ -2474,6 +2701,40 @@ int smc_sir_step_resample(const smc_sir_desc* d, int32_t phases, double* stats_r
                    : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f);
     }
     return 0;
+}
+
+int smc_sir_step_fused(const smc_sir_desc* d, void* logw_out_dev, int32_t model_id, const double* params_host,
+                       int32_t n_params, const double* z_dev, double resample_thresh, uint64_t seed, int64_t t,
+                       double* stats_prev_dev, double* stats_row_dev, int32_t phases, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    SMC_REQUIRE(phases >= 1 && phases <= 3, "smc: phases must be 1 (fused kernel), 2 (pre-pass of step t) or 3");
+    SMC_REQUIRE(d->dtype == SMC_F32 && d->n == d->n_global && d->offset == 0,
+                "smc: the fused step is the single-GPU fp32 throughput path");
+    SMC_REQUIRE(resample_thresh > 1.0, "smc: the fused step is for filters that resample every step (thresh > 1)");
+    SMC_REQUIRE(inline_moments(d) && !(d->flags & (SMC_FLAG_POST_MOMENTS_GENERIC | SMC_FLAG_WRITE_ANCESTORS)),
+                "smc: the fused step needs inline moments and no ancestor trace");
+    SMC_REQUIRE(logw_out_dev && logw_out_dev != d->logw_dev && z_dev && params_host, "smc: fused step: bad buffers");
+    SMC_REQUIRE(k3_grid(l.L.n_tiles, d->dtype, d->nx, true) <= kK1MaxBlocks, "smc: partial area too small");
+    SMC_REQUIRE(l.L.n_tiles >= (int64_t)sm_count() * 12, "smc: the fused step needs at least %d tiles", sm_count() * 12);
+    const double* p = params_host;
+    if (model_id == SMC_MODEL_STOCH_VOL) {
+        SMC_REQUIRE(n_params == 4 && d->nx == 1 && d->nz == 1, "smc: STOCH_VOL needs 4 params and nx = nz = 1");
+        StochVolModel<float> m;
+        m.alpha = (float)p[0]; m.lq = (float)p[1]; m.beta = (float)p[2]; m.rinv = (float)(1.0 / p[3]);
+        return launch_fused(l, m, logw_out_dev, z_dev, resample_thresh, seed, t, stats_prev_dev, stats_row_dev, phases);
+    }
+    if (model_id == SMC_MODEL_LINEAR_GAUSSIAN && d->nx == 2 && d->nz == 2) {
+        SMC_REQUIRE(n_params == 16, "smc: LINEAR_GAUSSIAN (2,2) needs 16 params");
+        LinGaussModel<float, 2, 2> m;
+        const double* q = p;
+        for (int i = 0; i < 4; ++i) m.A[i] = (float)*q++;
+        for (int i = 0; i < 4; ++i) m.Lq[i] = (float)*q++;
+        for (int i = 0; i < 4; ++i) m.H[i] = (float)*q++;
+        for (int i = 0; i < 4; ++i) m.LRinv[i] = (float)*q++;
+        return launch_fused(l, m, logw_out_dev, z_dev, resample_thresh, seed, t, stats_prev_dev, stats_row_dev, phases);
+    }
+    SMC_REQUIRE(false, "smc: the fused step is compiled for STOCH_VOL and LINEAR_GAUSSIAN (2,2)");
 }
 
 // ---- multi-GPU: whole sharded step with mailbox exchanges (no collective calls) ----------------

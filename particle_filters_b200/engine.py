@@ -216,16 +216,72 @@ class SirEngine:
         self.torch.cuda.current_stream(self.device).synchronize()
         return self._row_pin.numpy().copy()
 
-    def run(self, model_id: int, params, Z: np.ndarray, thresh: float, seed: int, t0: int = 0) -> np.ndarray:
+    def run(self, model_id: int, params, Z: np.ndarray, thresh: float, seed: int, t0: int = 0,
+            fused: Optional[bool] = None) -> np.ndarray:
         """Enqueue ``len(Z)`` SIR steps without any host synchronisation and return
-        the statistic rows ``(T, stats_stride)`` (one D2H at the end)."""
+        the statistic rows ``(T, stats_stride)`` (one D2H at the end).
+
+        Filters that resample every step (``thresh > 1``) take the fused pipeline when the
+        configuration allows it (``fused=None``): the resampler of step t-1 hands its output
+        straight to the propagate + likelihood functor of step t (two launches per step,
+        20 B per particle-update); ``fused=False`` forces the three-launch step."""
         torch = self.torch
         T = self.set_observations(Z)
         if self.trace.shape[0] < T:
             self.trace = torch.zeros((T, self.stride), dtype=torch.float64, device=self.device)
-        for k in range(T):
-            self.step(model_id, params, thresh, z_index=k, seed=seed, t=t0 + k, row=k)
+        self.enqueue(model_id, params, T, thresh, seed, t0=t0, fused=fused)
         return self.trace[:T].cpu().numpy()
+
+    def enqueue(self, model_id: int, params, T: int, thresh: float, seed: int, t0: int = 0, z0: int = 0,
+                row0: int = 0, fused: Optional[bool] = None):
+        """Enqueue T steps (observations ``z0 .. z0+T-1`` of the staged block, statistics rows
+        ``row0 .. row0+T-1``, Philox steps ``t0 ..``) on the current stream; no synchronisation."""
+        if fused is None:
+            fused = self.can_fuse(model_id, thresh) and T >= 2
+        if fused:
+            self._run_fused(model_id, params, T, thresh, seed, t0, z0, row0)
+        else:
+            for k in range(T):
+                self.step(model_id, params, thresh, z_index=z0 + k, seed=seed, t=t0 + k, row=row0 + k)
+        return fused
+
+    def can_fuse(self, model_id: int, thresh: float) -> bool:
+        """Whether ``smc_sir_step_fused`` serves this configuration (include/smc.h)."""
+        ok_model = (model_id == _lib.SMC_MODEL_STOCH_VOL and self.nx == 1) or \
+            (model_id == _lib.SMC_MODEL_LINEAR_GAUSSIAN and self.nx == 2 and self.nz == 2)
+        n_tiles = -(-self.n // 4096)
+        return bool(ok_model and thresh > 1.0 and self.dtype_code == _lib.SMC_F32 and self.n == self.n_global
+                    and self.offset == 0 and self.ancestors is None and not self.generic_moments
+                    and not (self.desc.flags & _lib.SMC_FLAG_POST_MOMENTS_GENERIC) and n_tiles >= 148 * 12)
+
+    def _run_fused(self, model_id, params, T, thresh, seed, t0, z0=0, row0=0, events=None):
+        """``events``: optional callable(tag) invoked between launch groups (bench.py's per-kernel timing)."""
+        torch = self.torch
+        if getattr(self, "logw2", None) is None:
+            self.logw2 = torch.zeros_like(self.logw)
+        kp, pp = _lib.as_doubles(params)
+        cur, alt = self.logw, self.logw2
+        desc = SirDesc.from_buffer_copy(self.desc)
+        dref = C.byref(desc)
+        check(self.lib.smc_sir_step_weight(dref, model_id, pp, kp.size, self._zptr(z0), None, float(thresh), -1.0,
+                                           C.c_uint64(seed), t0, self._row(row0), self.stream))
+        check(self.lib.smc_sir_step_resample(dref, 1, self._row(row0), self.stream))
+        for k in range(1, T):
+            desc.logw_dev = cur.data_ptr()
+            for ph in ((1, 2) if events else (3,)):
+                if events:
+                    events("fused" if ph == 1 else "prepass")
+                check(self.lib.smc_sir_step_fused(dref, C.c_void_p(alt.data_ptr()), model_id, pp, kp.size,
+                                                  self._zptr(z0 + k), float(thresh), C.c_uint64(seed), t0 + k,
+                                                  self._row(row0 + k - 1), self._row(row0 + k), ph, self.stream))
+            if events:
+                events("end")
+            cur, alt = alt, cur
+        desc.logw_dev = cur.data_ptr()
+        check(self.lib.smc_sir_step_resample(dref, 2, self._row(row0 + T - 1), self.stream))
+        # the engine's canonical log-weight array is the one written last
+        self.logw, self.logw2 = cur, alt
+        self.desc.logw_dev = self.logw.data_ptr()
 
     # ------------------------------------------------------------------ bridge (host callbacks)
     def bridge_predict(self, gx: Optional[np.ndarray], noise: np.ndarray, Lq: np.ndarray, scale: float = 1.0,

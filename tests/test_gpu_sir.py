@@ -297,3 +297,39 @@ def test_sharded_step_matches_single_gpu_when_two_gpus_are_visible():
                           "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(here, "sharded_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "[sharded_check] PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["sv", "lgssm"])
+def test_fused_resample_propagate_pipeline_matches_three_launch_step(kind):
+    """run() of a bootstrap filter through smc_sir_step_fused (resampler of step t-1 feeding the functor
+    of step t) against the three-launch step from the same seed: same Philox blocks, same functor
+    arithmetic -> the statistics agree to the reduction-order level and virtually all particles are
+    bit-identical (a last-bit difference of a normaliser may move a handful of resampling boundaries)."""
+    from particle_filters_b200 import LinearGaussianSSM, StochVolSSM
+    from particle_filters_b200.engine import SirEngine
+
+    N, T, seed = (1 << 23) + 4096 * 3 + 1237, 6, 11
+    if kind == "sv":
+        mid, params = StochVolSSM(0.95, 1.0).device_functor(np.array([[0.04]]), np.array([[1.0]]))
+        nx, nz, Z = 1, 1, np.random.default_rng(1).standard_normal((T, 1))
+        mean0, L0 = np.zeros(1), np.array([[0.6]])
+    else:
+        m = LGSSMModel()
+        mid, params = LinearGaussianSSM(m.A, m.C).device_functor(m.Q, m.R)
+        nx, nz, Z = 2, 2, m.simulate(T, seed=3)[1]
+        mean0, L0 = np.zeros(2), np.eye(2)
+    rows, parts = [], []
+    for fused in (False, True):
+        eng = SirEngine(N, nx, nz, dtype="f32", trace_len=T)
+        assert eng.can_fuse(mid, 2.0)
+        eng.init_gaussian(mean0, L0, seed)
+        rows.append(eng.run(mid, params, Z, 2.0, seed, fused=fused))
+        parts.append(eng.get_particles())
+    a, b = rows
+    assert np.all(a[:, 2] == 1.0) and np.all(b[:, 2] == 1.0)
+    np.testing.assert_allclose(b[:, 0], a[:, 0], rtol=0, atol=1e-6)             # log normaliser
+    np.testing.assert_allclose(b[:, 1], a[:, 1], rtol=1e-6)                     # ESS
+    np.testing.assert_array_equal(b[:, 3], a[:, 3])                             # resampling uniforms
+    np.testing.assert_allclose(b[:, 4:], a[:, 4:], rtol=0, atol=2e-5)           # mean, covariance
+    same = np.mean(np.all(parts[0] == parts[1], axis=1))
+    assert same > 0.999, same
