@@ -258,6 +258,9 @@ def run_gpu_arm(args):
             elif tag == "prepass":
                 acc[phases[1]] += e_a.elapsed_time(e_b) / NB
         dom, alg_bytes = phases[0], 16.0 * N      # fused kernel: R logw, R x, W x, W logw (fp32, nx = 1)
+        # dram__bytes_read + write of this kernel from the committed ncu --set full capture
+        # (profiles/r1_ncu_full_summary.txt: 537.2 MB + 500.8 MB per launch at N = 2^26)
+        traffic = 1038.0e6 * (N / float(1 << 26))
     else:
         phases = ("k1_propagate_weight+finalize", "k3a_range_totals", "k3_resample+finish")
         acc = {p: 0.0 for p in phases}
@@ -276,6 +279,8 @@ def run_gpu_arm(args):
                 acc[p] += evs[i].elapsed_time(evs[i + 1]) / NB
         dom = max((phases[0], phases[2]), key=lambda p: acc[p])
         alg_bytes = 12.0 * N          # K1: R x, W x, W logw ; K3: R logw, R x, W x   (fp32, nx = 1)
+        # profiles/r1_ncu_full_summary.txt: K3 537 MB + 242 MB, K1 268 MB + 479 MB per launch at N = 2^26
+        traffic = (779.0e6 if dom == phases[2] else 747.5e6) * (N / float(1 << 26))
     clk = clocks.stop()
     rows = eng.trace[: W + K].cpu().numpy()
     assert np.all(np.isfinite(rows[:, :5])), "non-finite filter statistics"
@@ -325,7 +330,8 @@ def run_gpu_arm(args):
         "pipeline": ("fused resample->propagate (2 launches per step, 20 B per particle-update)" if fused_used
                      else "three launches per step (28 B per particle-update)"),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "B per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": acc[dom]},
         "roofline_step": {"alg_bytes_per_particle_update": step_alg,
                           "achieved": step_alg * value / 1e9, "peak": peak, "unit": "GB/s",

@@ -1024,7 +1024,10 @@ template <> __device__ __forceinline__ double lds_real<double>(uint32_t saddr) {
 // Resident CTAs per SM of the resampler (shared memory: (1 + NXF) tiles + the id window)
 template <typename real, int NXF, bool FUSED = false> struct K3Occ {
     static constexpr int plain = (sizeof(real) == 4) ? (NXF <= 1 ? 4 : (NXF == 2 ? 3 : 2)) : (NXF <= 1 ? 3 : 2);
-    static constexpr int value = FUSED ? (plain > 2 ? plain - 1 : 2) : plain;   // the fused functor needs the registers
+#ifndef SMC_FUSED_OCC_DROP
+#define SMC_FUSED_OCC_DROP 1
+#endif
+    static constexpr int value = FUSED ? (plain > 2 ? plain - SMC_FUSED_OCC_DROP : 2) : plain;   // the fused functor needs the registers
 };
 
 // K3 proper.  Persistent grid: CTA b owns the contiguous tiles [b T / G, (b + 1) T / G) (static
@@ -2180,7 +2183,7 @@ inline int k3_occupancy(int dtype, int nxf) {
 }
 inline int64_t k3_grid(int64_t n_tiles, int dtype, int nxf, bool fused = false) {
     int occ = k3_occupancy(dtype, nxf);
-    if (fused) occ = occ > 2 ? occ - 1 : 2;
+    if (fused) occ = occ > 2 ? occ - SMC_FUSED_OCC_DROP : 2;
     const int64_t g = (int64_t)sm_count() * occ;
     return n_tiles < g ? n_tiles : g;
 }
