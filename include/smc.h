@@ -126,6 +126,13 @@ int smc_bridge_predict(const smc_sir_desc *d, const void *gx_dev, const void *no
 int smc_bridge_loglik(const smc_sir_desc *d, const void *zpred_dev, const double *z_host,
                       const double *LRinv_host, const void *wprev_dev, void *stream);
 
+/* Post-resample regularisation on chip (particle_filter.py:212-218): x += n (scale Lq)^T with
+ * n ~ N(0, I) from the Philox jitter stream (seed, t), applied to the buffer K3 has just filled iff
+ * the control block says the step resampled.  Call between smc_sir_resample and smc_sir_finish_step
+ * on a descriptor with SMC_FLAG_POST_MOMENTS_GENERIC (the moments are then taken after the jitter). */
+int smc_sir_jitter(const smc_sir_desc *d, const double *Lq_host, double scale, uint64_t seed, int64_t t,
+                   void *stream);
+
 /* K2: combine block partials -> log normaliser, ESS, weighted mean/cov; decide
  * resampling (ESS < resample_thresh * n_global, particle_filter.py:203-204);
  * fix the systematic uniform u (u_host in [0,1) = caller's draw for

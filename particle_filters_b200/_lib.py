@@ -68,6 +68,7 @@ _SIG = {
                                            _P, _P, C.c_uint64, C.c_int64, _P]),
     "smc_bridge_predict": (C.c_int, [C.POINTER(SirDesc), _P, _P, _D, C.c_double, C.c_int32, _P]),
     "smc_bridge_loglik": (C.c_int, [C.POINTER(SirDesc), _P, _D, _D, _P, _P]),
+    "smc_sir_jitter": (C.c_int, [C.POINTER(SirDesc), _D, C.c_double, C.c_uint64, C.c_int64, _P]),
     "smc_sir_finalize": (C.c_int, [C.POINTER(SirDesc), C.c_double, C.c_double, C.c_uint64, C.c_int64,
                                    _P, _P, C.c_int32, _P]),
     "smc_sir_set_uniform": (C.c_int, [C.POINTER(SirDesc), C.c_double, _P]),

@@ -61,9 +61,10 @@ __device__ __forceinline__ void l96_rk4(real (&x)[NX], real F, real dt) {
 
 // the standard normal that draw_normals() hands to particle `gidx`, dimension d (same Philox block,
 // same Box-Muller lane), so results do not depend on which kernel propagates the particle
-__device__ inline float normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, float) {
+__device__ inline float normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, float,
+                                   uint32_t stream = kStreamProcess) {
     uint32_t r[4];
-    philox_quad_keys(keys, gidx >> 2, t, kStreamProcess | (d << 8), r);
+    philox_quad_keys(keys, gidx >> 2, t, stream | (d << 8), r);
     const int j = (int)(gidx & 3), p = j >> 1;
     const float k2pow32inv = 2.3283064365386963e-10f, k2pi = 6.2831853071795865f;
     const float u1 = fmaf((float)(p ? r[2] : r[0]), k2pow32inv, 0.5f * k2pow32inv);
@@ -73,10 +74,11 @@ __device__ inline float normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32
     __sincosf(u2, &s, &c);
     return (j & 1) ? rad * s : rad * c;
 }
-__device__ inline double normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, double) {
+__device__ inline double normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, double,
+                                    uint32_t stream = kStreamProcess) {
     uint32_t r[4];
     const int j = (int)(gidx & 3), h = j >> 1;
-    philox_quad_keys(keys, gidx >> 2, t, kStreamProcess | (d << 8) | ((uint32_t)h << 16), r);
+    philox_quad_keys(keys, gidx >> 2, t, stream | (d << 8) | ((uint32_t)h << 16), r);
     double z2[2];
     normals2_f64(r, z2);
     return z2[j & 1];
@@ -288,6 +290,28 @@ __global__ void __launch_bounds__(256) k_moments_syrk_finish(const Ctrl* ctrl, c
         cov[e] = tot[1 + nx + e] / W - (tot[1 + a] / W) * (tot[1 + b] / W);
     }
     for (int a = threadIdx.x; a < nx; a += 256) mean[a] = (a < kMaxNx ? ctrl->shift[a] : 0.0) + tot[1 + a] / W;
+}
+
+// ==============================================================================================
+// Post-resample regularisation on chip (particle_filter.py:212-218): x += n (scale Lq)^T with
+// n ~ N(0, I) from the Philox jitter stream, applied to the resampling destination iff the control
+// block says the step resampled.  Thread per particle; nx <= 64.
+// ==============================================================================================
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_jitter(const Ctrl* ctrl, real* x0, real* x1, const double* Lq, double scale,
+                                                     int64_t n, int64_t offset, int64_t ld, int nx, PhiloxKeys keys,
+                                                     uint32_t t) {
+    if (!ctrl->do_resample) return;
+    real* x = ctrl->cur ? x0 : x1;                      // the buffer K3 has just filled
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    real z[kMaxNx];
+    for (int d = 0; d < nx; ++d) z[d] = normal_one(keys, (uint64_t)(offset + i), t, (uint32_t)d, real(0), kStreamJitter);
+    for (int d = nx - 1; d >= 0; --d) {
+        double acc = 0;
+        for (int k = 0; k <= d; ++k) acc = fma((double)z[k], Lq[d * nx + k] * scale, acc);
+        x[d * ld + i] = (real)((double)x[d * ld + i] + acc);
+    }
 }
 
 }  // namespace smc

@@ -2454,6 +2454,25 @@ int smc_bridge_predict(const smc_sir_desc* d, const void* gx_dev, const void* no
     return 0;
 }
 
+int smc_sir_jitter(const smc_sir_desc* d, const double* Lq_host, double scale, uint64_t seed, int64_t t, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    const int nx = d->nx;
+    SMC_REQUIRE(Lq_host && nx <= kMaxNx, "smc: jitter needs Lq and nx <= %d", kMaxNx);
+    double* lq_dev;
+    if (int rc = stage(l, 1, Lq_host, nx * nx, &lq_dev)) return rc;
+    const unsigned grid = (unsigned)cdiv64(d->n, kThreads);
+    const PhiloxKeys keys = philox_expand(seed);
+    if (d->dtype == SMC_F32)
+        k_jitter<float><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (float*)d->x0_dev, (float*)d->x1_dev, lq_dev, scale, d->n,
+                                                    d->offset, d->ld, nx, keys, (uint32_t)t);
+    else
+        k_jitter<double><<<grid, kThreads, 0, l.st>>>(l.ctrl(), (double*)d->x0_dev, (double*)d->x1_dev, lq_dev, scale, d->n,
+                                                     d->offset, d->ld, nx, keys, (uint32_t)t);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int smc_bridge_loglik(const smc_sir_desc* d, const void* zpred_dev, const double* z_host, const double* LRinv_host,
                       const void* wprev_dev, void* stream) {
     Launch l;

@@ -184,6 +184,11 @@ class SirEngine:
             self._d, C.c_uint64(cdf_offset), self._row(row),
             C.c_void_p(peers.data_ptr()) if peers is not None else None, n_shards, self.stream))
 
+    def jitter(self, Lq: np.ndarray, scale: float, seed: int, t: int):
+        """On-chip post-resample regularisation (no-op on the device when the step did not resample)."""
+        kl, pl = _lib.as_doubles(Lq)
+        check(self.lib.smc_sir_jitter(self._d, pl, float(scale), C.c_uint64(seed), t, self.stream))
+
     def finish_step(self, row: int = 0, mom_parts=None, n_mom_parts: int = 0):
         check(self.lib.smc_sir_finish_step(
             self._d, self._row(row),

@@ -318,9 +318,8 @@ class ParticleFilter:
         self._generation += 1
         mid, params = self._functor
         eng.set_observation(z, 0)
-        host_rng = self._noise == "reference" or self.resample_method != "systematic" \
-            or self.regularize_after_resample
-        if not host_rng and mode == _lib.SMC_MODE_STEP:
+        host_rng = self._noise == "reference" or self.resample_method != "systematic"
+        if not host_rng and mode == _lib.SMC_MODE_STEP and not self.regularize_after_resample:
             # whole step on the device clock: K1 (+ finalize), range pre-pass, K3 (+ finish)
             eng.step(mid, params, self.resample_thresh, z_index=0, seed=self._seed, t=self._t_phil)
             return self._publish_device_state(eng, t_next)
@@ -344,6 +343,8 @@ class ParticleFilter:
             eng.finalize(self.resample_thresh, u=-1.0, seed=self._seed, t=self._t_phil)
             if self.resample_thresh > 0:
                 eng.resample()
+                if self.regularize_after_resample:      # on chip, decided by the device's own resampling flag
+                    eng.jitter(self._chol_Q(1e-12), 0.001, self._seed, self._t_phil)
         eng.finish_step()
         return self._publish_device_state(eng, t_next)
 

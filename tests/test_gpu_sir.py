@@ -333,3 +333,38 @@ def test_fused_resample_propagate_pipeline_matches_three_launch_step(kind):
     np.testing.assert_allclose(b[:, 4:], a[:, 4:], rtol=0, atol=2e-5)           # mean, covariance
     same = np.mean(np.all(parts[0] == parts[1], axis=1))
     assert same > 0.999, same
+
+
+def test_on_chip_regularisation_jitter_in_philox_mode():
+    """regularize_after_resample with noise='philox': the 0.001 Lq jitter (particle_filter.py:212-218) is drawn
+    on the device from the Philox jitter stream -- no host synchronisation for it -- only in steps that
+    resample; same seed gives the same particles, and the jitter has the reference's scale."""
+    from particle_filters_b200 import LinearGaussianSSM, ParticleFilter
+
+    m = LGSSMModel()
+    X, Y = m.simulate(4, seed=8)
+    spec = LinearGaussianSSM(m.A, m.C)
+    N = 1 << 16
+    outs = {}
+    for reg in (False, True, True):
+        pf = ParticleFilter(spec.g, spec.h, m.Q, m.R, Np=N, resample_thresh=2.0, regularize_after_resample=reg,
+                            dtype="f64", noise="philox", seed=21)
+        pf.initialize(np.zeros(2), np.eye(2))
+        for t in range(3):
+            st = pf.step(Y[t])
+            assert pf.last_resampled
+        outs.setdefault(reg, []).append((st.particles.copy(), st.mean.copy(), st.cov.copy()))
+    plain, (reg_a, reg_b) = outs[False][0], outs[True]
+    np.testing.assert_array_equal(reg_a[0], reg_b[0])                     # deterministic in the seed
+    # after three regularised steps the clouds differ by accumulated jitter; the moments barely move
+    np.testing.assert_allclose(reg_a[1], plain[1], atol=5e-3)
+    # one more step from IDENTICAL particles isolates one jitter draw
+    pf0 = ParticleFilter(spec.g, spec.h, m.Q, m.R, Np=N, resample_thresh=2.0, dtype="f64", noise="philox", seed=5)
+    pf1 = ParticleFilter(spec.g, spec.h, m.Q, m.R, Np=N, resample_thresh=2.0, regularize_after_resample=True,
+                         dtype="f64", noise="philox", seed=5)
+    for pf in (pf0, pf1):
+        pf.initialize(np.zeros(2), np.eye(2))
+    d = pf1.step(Y[0]).particles - pf0.step(Y[0]).particles
+    Lq = np.linalg.cholesky(m.Q)
+    np.testing.assert_allclose(np.cov(d.T), 1e-6 * (Lq @ Lq.T), rtol=0.05, atol=1e-9)
+    assert abs(d.mean()) < 1e-4
