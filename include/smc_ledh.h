@@ -86,6 +86,15 @@ int smc_ledh_weights(const struct smc_sir_desc *d, const double *wprev_dev, cons
 int smc_weighted_moments(const struct smc_sir_desc *d, const double *w_dev, double *stats_row_dev,
                          void *stream);
 
+/* EDH flow (models/EDH_particle_filter.py:218-275).  The EDH flow field A(lambda) x + b(lambda) is
+ * evaluated at the tracker's mean path, not per particle, so the caller composes the L Euler / RK4
+ * pseudo-time sub-steps into one affine map (M, c) on the host (nx x nx, tiny) and this call applies
+ * x <- M x + c to all n particles in place (SoA x[d * ld + i], dtype as in smc.h, fp64 arithmetic).
+ * Weights, ESS, resampling and moments of the EDH step run on smc_ledh_weights (theta = 0) and the
+ * SIR kernels. */
+int smc_affine_map(void *x_dev, const double *M_host, const double *c_host, int64_t n, int64_t ld,
+                   int32_t nx, int32_t dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,7 @@ _LEDH_SIG = {
     "smc_ledh_gauss_terms": (C.c_int, [C.POINTER(LedhDesc), _P, _D, _D, _D, _D, C.c_int32, _D, C.c_int32, _P, _P]),
     "smc_ledh_weights": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P, _P]),
     "smc_weighted_moments": (C.c_int, [C.POINTER(SirDesc), _P, _P, _P]),
+    "smc_affine_map": (C.c_int, [_P, _D, _D, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
 }
 SMC_LEDH_H_LINEAR, SMC_LEDH_H_ACOUSTIC, SMC_LEDH_H_EXP = 1, 2, 3
 

@@ -299,6 +299,31 @@ __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a
 }
 
 
+// ---- EDH flow: the pseudo-time integration is ONE affine map for every particle -------------------
+// (models/EDH_particle_filter.py:218-275: A(lambda), b(lambda) are evaluated at the tracker's mean
+// path, not per particle, so the L Euler / RK4 sub-steps compose to x <- M x + c on the host and the
+// particle update is a streaming kernel: thread per particle, M and c in shared memory, fp64 math)
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_affine_map(real* x, const double* M, const double* c, int64_t n,
+                                                         int64_t ld, int nx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sM = reinterpret_cast<double*>(smem_raw);
+    double* sc = sM + nx * nx;
+    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) sM[i] = M[i];
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) sc[i] = c[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double xi[kLedhMaxDim], yi[kLedhMaxDim];
+    for (int d = 0; d < nx; ++d) xi[d] = (double)x[d * ld + i];
+    for (int r = 0; r < nx; ++r) {
+        double acc = sc[r];
+        for (int d = 0; d < nx; ++d) acc = fma(sM[r * nx + d], xi[d], acc);
+        yi[r] = acc;
+    }
+    for (int d = 0; d < nx; ++d) x[d * ld + i] = (real)yi[d];
+}
+
 }  // namespace smc
 #include "ledh_fast.cuh"
 namespace smc {
@@ -623,6 +648,31 @@ int smc_ledh_flow_step_supplied(const smc_ledh_desc* d, const double* P_host, co
     return d->dtype == SMC_F32
                ? launch_flow<float>(d, P_host, R_host, z_host, 0, nullptr, 0, H_dev, h_dev, lam, dlam, step_index, 1, st)
                : launch_flow<double>(d, P_host, R_host, z_host, 0, nullptr, 0, H_dev, h_dev, lam, dlam, step_index, 1, st);
+}
+
+int smc_affine_map(void* x_dev, const double* M_host, const double* c_host, int64_t n, int64_t ld, int32_t nx,
+                   int32_t dtype, void* stream) {
+    SMC_REQUIRE(x_dev && M_host && c_host && n > 0 && ld >= n, "smc_affine_map: bad arguments");
+    SMC_REQUIRE(nx >= 1 && nx <= kLedhMaxDim, "smc_affine_map: nx must be in [1, %d]", kLedhMaxDim);
+    SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_affine_map: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t cnt = (size_t)nx * nx + nx;
+    std::vector<double> host(cnt);
+    memcpy(host.data(), M_host, sizeof(double) * nx * nx);
+    memcpy(host.data() + nx * nx, c_host, sizeof(double) * nx);
+    double* dev = nullptr;
+    SMC_CHECK_CUDA(cudaMallocAsync(&dev, cnt * sizeof(double), st));
+    SMC_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    SMC_CHECK_CUDA(cudaStreamSynchronize(st));   // `host` leaves scope; the copy is tiny
+    const unsigned grid = (unsigned)cdiv64(n, kThreads);
+    const size_t smem = cnt * sizeof(double);
+    if (dtype == SMC_F32)
+        k_affine_map<float><<<grid, kThreads, smem, st>>>((float*)x_dev, dev, dev + nx * nx, n, ld, nx);
+    else
+        k_affine_map<double><<<grid, kThreads, smem, st>>>((double*)x_dev, dev, dev + nx * nx, n, ld, nx);
+    SMC_CHECK_CUDA(cudaGetLastError());
+    SMC_CHECK_CUDA(cudaFreeAsync(dev, st));
+    return 0;
 }
 
 int smc_ledh_propagate_linear(const smc_ledh_desc* d, const void* x_dev, const double* F_host, const double* Lq_host,

@@ -45,6 +45,7 @@ ref_ledh = load_ref("models/LEDH_particle_filter.py", "ref_ledh_particle_filter"
 ref_sv = load_ref("simulator/simulator_sto_volatility_model.py", "ref_sim_sv")
 ref_lgssm = load_ref("simulator/simulator_LGSSM.py", "ref_sim_lgssm")
 ref_l96 = load_ref("simulator/simulator_Lorenz_96.py", "ref_sim_l96")
+ref_edh = load_ref("models/EDH_particle_filter.py", "ref_edh_particle_filter")
 
 
 class FixedU:
@@ -296,6 +297,87 @@ def gen_ledh():
         x_true0=np.array([12.5, 13.0, 0.6, -0.2, 29.0, 26.0, -0.5, 0.3]), with_noise=False)
 
 
+class ScriptedMeanTracker(ScriptedTracker):
+    """ScriptedTracker that also replays scripted past means (EDH uses get_past_mean, :213)."""
+
+    def __init__(self, Ps, means, nx):
+        super().__init__(Ps, nx)
+        self.means = means
+
+    def get_past_mean(self):
+        return self.means[self.k - 1]
+
+
+class RecordingRng:
+    """Wraps a Generator and records every ``random()`` (the resampling uniforms)."""
+
+    def __init__(self, rng):
+        self._r, self.us = rng, []
+
+    def random(self):
+        u = self._r.random()
+        self.us.append(u)
+        return u
+
+    def __getattr__(self, name):
+        return getattr(self._r, name)
+
+
+def gen_edh():
+    """EDHFlowPF steps of the unmodified reference (Euler and RK4 pseudo-time
+    integrators, ESS-triggered resampling), scripted tracker covariances and past means."""
+    def run(tag, model, *, N, L, T, ess_ratio, integrator, seed, mean0, cov0, x_true0):
+        rng = np.random.default_rng(seed)
+        nx, nz = model.nx, model.nz
+        Ps, means = [], []
+        Pk = np.array(cov0, float)
+        x = np.asarray(x_true0, float)
+        for k in range(T):
+            G = rng.standard_normal((nx, nx)) * 0.02
+            Pk = 0.8 * Pk + model.Q + G @ G.T
+            Ps.append(Pk + 1e-9 * np.triu(np.ones((nx, nx)), 1))
+            means.append(x + 0.1 * rng.standard_normal(nx))
+            x = model.g(x, None, None)
+        rec = RecordingRng(np.random.default_rng(seed + 1))
+        cfg = ref_edh.EDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=ess_ratio,
+                                flow_integrator=integrator, rng=rec)
+        f = ref_edh.EDHFlowPF(ScriptedMeanTracker(Ps, means, nx), model.g, model.h, model.jac_h,
+                              model.log_trans_pdf, model.log_like_pdf, model.R, cfg)
+        st = f.init_from_gaussian(np.asarray(mean0, float), np.asarray(cov0, float))
+        Lq = np.linalg.cholesky(model.Q)
+        x = np.asarray(x_true0, float)
+        out = dict(N=np.array(N), L=np.array(L), T=np.array(T), ess_ratio=np.array(ess_ratio),
+                   integrator=np.array(integrator), seed=np.array(seed), Ps=np.array(Ps), means=np.array(means),
+                   Q=model.Q, R=model.R, particles0=st.particles.copy(), weights0=st.weights.copy())
+        Z, V, U = [], [], []
+        for k in range(T):
+            x = model.g(x, None, Lq @ rng.standard_normal(nx))
+            z = model.h(x) + np.linalg.cholesky(model.R) @ rng.standard_normal(nz)
+            v = rng.standard_normal((N, nx)) @ Lq.T
+            n_before = len(rec.us)
+            st = f.step(st, z, None, lambda n_, d_, v=v: v)
+            U.append(rec.us[-1] if len(rec.us) > n_before else -1.0)
+            Z.append(z)
+            V.append(v)
+            out[f"particles_{k}"] = st.particles.copy()
+            out[f"weights_{k}"] = st.weights.copy()
+            out[f"mean_{k}"] = st.mean.copy()
+            out[f"cov_{k}"] = st.cov.copy()
+            out[f"cond_{k}"] = np.array(st.diagnostics["condition_numbers"])
+        out["Z"], out["V"], out["U"] = np.array(Z), np.array(V), np.array(U)
+        np.savez_compressed(os.path.join(HERE, f"edh_{tag}.npz"), **out)
+        print(f"edh_{tag}: resampled {int(np.sum(np.array(U) >= 0))}/{T}, final ESS {1.0 / np.sum(st.weights ** 2):.1f}")
+
+    run("linear1d_euler", Linear1DModel(), N=64, L=8, T=6, ess_ratio=0.5, integrator="euler", seed=21,
+        mean0=np.array([0.5]), cov0=np.array([[0.3]]), x_true0=np.array([0.4]))
+    run("linear1d_rk4", Linear1DModel(), N=50, L=4, T=6, ess_ratio=0.9, integrator="rk4", seed=22,
+        mean0=np.array([0.5]), cov0=np.array([[0.3]]), x_true0=np.array([0.4]))
+    ac = AcousticCVModel(n_targets=1, grid=(3, 3))
+    run("acoustic1_rk4", ac, N=40, L=6, T=4, ess_ratio=0.5, integrator="rk4", seed=23,
+        mean0=np.array([12.0, 14.0, 0.5, -0.3]), cov0=np.diag([4.0, 4.0, 0.25, 0.25]),
+        x_true0=np.array([12.5, 13.0, 0.6, -0.2]))
+
+
 def gen_rng_checksum():
     r = np.random.default_rng(42)
     a = r.standard_normal((4, 3))
@@ -310,4 +392,5 @@ if __name__ == "__main__":
     gen_sir()
     gen_l96()
     gen_ledh()
+    gen_edh()
     gen_rng_checksum()
