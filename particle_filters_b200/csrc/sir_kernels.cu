@@ -824,8 +824,13 @@ __host__ __device__ inline int64_t k3_range_begin(int64_t b, int64_t n_tiles, in
 // for grids of 148 x {4, 3, 2} CTAs): CTA b of a grid of G owns ranges [b R / G, (b + 1) R / G), whose
 // first tile is floor(b T / G) -- the plain and the fused resampler can consume the same pre-pass.
 
+// (1776 ranges = exactly three waves of 4 resident CTAs on 148 SMs; measured at N = 2^26: 2 -> 0.139 ms,
+// 3 -> 0.091, 4 -> 0.061, 5 -> 0.067, 6 -> 0.069)
+#ifndef SMC_K3A_OCC
+#define SMC_K3A_OCC 4
+#endif
 template <typename real, bool LINEAR_W>
-__global__ void __launch_bounds__(K3Geom<real>::THREADS) k3a_range_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
+__global__ void __launch_bounds__(K3Geom<real>::THREADS, sizeof(real) == 4 ? SMC_K3A_OCC : 3) k3a_range_totals(const Ctrl* ctrl, const real* wsrc, int64_t n,
                                                                          int64_t n_global, int64_t n_tiles,
                                                                          unsigned long long* rtot, int force,
                                                                          ShardCtx shard, unsigned int* ticket) {
