@@ -58,12 +58,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(STAMP) as f:
             if f.read().strip() == fp:
                 return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(res.stderr)
+    # one nvcc process per translation unit (they share no device code), then one link step
+    from concurrent.futures import ThreadPoolExecutor
+
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    objs = [os.path.join(OUT_DIR, os.path.splitext(os.path.basename(src))[0] + ".o") for src in _sources()]
+
+    def compile_one(pair):
+        src, obj = pair
+        return subprocess.run([_nvcc()] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(objs)) as pool:
+        results = list(pool.map(compile_one, zip(_sources(), objs)))
+    for res in results:
+        if verbose:
+            sys.stderr.write(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    for obj in objs:
+        os.remove(obj)
     with open(STAMP, "w") as f:
         f.write(fp)
     return LIB
