@@ -1365,6 +1365,9 @@ k3_resample(K3Args<real> a, FM fm) {
             if (j0 + IPT >= a.n_global) {
 #pragma unroll
                 for (int k = 0; k < IPT; ++k) if (j0 + k >= a.n_global - 1) e[k] = fs.n_global;
+                // a thread that holds padding only starts where the last particle's range ends -- otherwise a
+                // quantised total slightly below N 2^F would give its first padding item the tail outputs too
+                if (j0 >= a.n_global) e_start = fs.n_global;
             }
             // the quantised total may exceed N 2^F by round-off: no boundary may pass N
             // (boundaries are monotone, so one test per thread suffices)
