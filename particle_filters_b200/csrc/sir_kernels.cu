@@ -716,7 +716,7 @@ template <typename real> struct K3Args {
     double* mom_parts;          // nullable
     unsigned long long cdf_offset;
     const unsigned long long* totals;   // nullable: per-shard weight totals (offset = sum over lower ranks)
-    int32_t rank;
+    int32_t rank, n_totals;
     int64_t n, n_global, offset, ld, shard_n;
     int32_t force;              // ignore ctrl->do_resample (stand-alone use)
     int64_t n_tiles;
@@ -752,17 +752,24 @@ __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; 
 //  2^-F index units does not accumulate over a run of tiny weights.
 template <typename real> struct Quant;
 template <> struct Quant<float> {
-    float fscale, kshift;
+    float fscale, kshift, corr;
     __device__ inline void init(int F, double lw_ref) {
         fscale = __uint_as_float((127u + (uint32_t)F) << 23);                 // 2^F
-        kshift = (float)((double)F - lw_ref * 1.4426950408889634);          // N w 2^F = 2^(lw log2e + kshift)
+        // N w 2^F = 2^((lw - lw_ref) log2e + F).  Two systematic errors would each move the CDF total by
+        // ~1e-6 N index units (and push that many outputs onto / off the last particles): the fp32
+        // rounding of the shift and of log2(e).  The shift is therefore formed with the fp32 constant the
+        // FMA really multiplies by (so its error only scales log(N w) = O(1)), and its fp32 rounding
+        // remainder is applied as a factor 2^(k - fl(k)) after the exponential.
+        const double k = (double)F - lw_ref * (double)1.4426950408889634f;
+        kshift = (float)k;
+        corr = (float)exp2(k - (double)kshift);
     }
     __device__ inline unsigned long long add(unsigned long long run, float v, double&) const {
         return run + __float2ull_rn(v * fscale);
     }
     // log-weight -> fixed point in one FFMA + FMNMX + MUFU.EX2 + F2I (NaN-free input, see K1)
     __device__ inline unsigned long long add_logw(unsigned long long run, float lw, double&) const {
-        const float p = ex2_approx(fminf(fmaf(lw, 1.4426950408889634f, kshift), 62.5f));
+        const float p = ex2_approx(fminf(fmaf(lw, 1.4426950408889634f, kshift), 62.5f)) * corr;
         unsigned long long q;
         asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
         return run + q;
@@ -1079,6 +1086,7 @@ k3_resample(K3Args<real> a, FM fm) {
     unsigned short* ids_raw = reinterpret_cast<unsigned short*>(smem_raw + sizeof(real) * TILE * (1 + NXF));
     unsigned short* ids = ids_raw + GUARD;
     __shared__ unsigned long long s_warp_tot[kK3Warps];
+    __shared__ unsigned long long s_warp_all[kK3Warps];
     __shared__ uint32_t s_E[4];
     __shared__ int s_wmax[kK3Warps];
     __shared__ double s_mom[kK3Warps][16];
@@ -1153,7 +1161,7 @@ k3_resample(K3Args<real> a, FM fm) {
 
     // exclusive CDF prefix of the first tile: the lower shards' totals (multi-GPU) and the totals of
     // the ranges below this CTA's
-    unsigned long long prefix;
+    unsigned long long prefix, cdf_total;
     {
         const unsigned long long* totals = a.totals;
         if (a.shard.mail) {   // every rank's weight total of this step must have arrived in the own mailbox
@@ -1161,16 +1169,42 @@ k3_resample(K3Args<real> a, FM fm) {
             mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp);
             totals = own->tot;
         }
-        unsigned long long part = 0;
-        for (int i = tid; i < (int)blockIdx.x * a.ranges_per_cta; i += kK3Threads) part += a.rtot[i];
-        if (totals) for (int r = tid; r < a.rank; r += kK3Threads) part += __ldcg(totals + r);
+        unsigned long long part = 0, all = 0;
+        const int n_ranges = (int)gridDim.x * a.ranges_per_cta;
+        for (int i = tid; i < n_ranges; i += kK3Threads) {
+            const unsigned long long v = a.rtot[i];
+            if (i < (int)blockIdx.x * a.ranges_per_cta) part += v;
+            all += v;
+        }
+        if (totals) {
+            all = 0;                                             // the global total is the sum over ALL shards
+            const int ns = a.shard.mail ? a.shard.n_shards : a.n_totals;
+            for (int r = tid; r < ns; r += kK3Threads) {
+                const unsigned long long v = __ldcg(totals + r);
+                if (r < a.rank) part += v;
+                all += v;
+            }
+        }
         part = warp_sum(part);
-        if (lane == 0) s_warp_tot[warp] = part;
+        all = warp_sum(all);
+        if (lane == 0) { s_warp_tot[warp] = part; s_warp_all[warp] = all; }
         __syncthreads();
         prefix = a.cdf_offset;
+        cdf_total = 0;
 #pragma unroll
-        for (int w = 0; w < kK3Warps; ++w) prefix += s_warp_tot[w];
+        for (int w = 0; w < kK3Warps; ++w) { prefix += s_warp_tot[w]; cdf_total += s_warp_all[w]; }
         __syncthreads();
+    }
+    // fp32 mode: the stratified positions are laid over the ACTUAL fixed-point total T instead of over
+    // N 2^32 (boundaries are taken at C rho, rho = N 2^32 / T = 1 + eps): the fp32 round-off of the
+    // normaliser then moves no boundary -- a relative error delta of the normaliser rescales every
+    // weight and T alike -- so the three-launch step, the fused pipeline and any shard count select the
+    // same ancestors, and nothing is left over for (or missing from) the last particles.
+    long long rho_eps = 0;                                       // round(eps 2^64)
+    if (sizeof(real) == 4 && cdf_total > 0ull) {
+        const double want = (double)a.n_global * 4294967296.0;
+        const double eps = (want - (double)cdf_total) / (double)cdf_total;
+        if (fabs(eps) < 0.25) rho_eps = (long long)(eps * 18446744073709551616.0);
     }
 
     real shift[NXF > 0 ? NXF : 1];
@@ -1317,13 +1351,22 @@ k3_resample(K3Args<real> a, FM fm) {
 
         // ---- phase C: output boundaries (32-bit) -------------------------------------------------
         // e[k] = number of outputs whose stratified position lies below the CDF value after item k
-        const unsigned long long base_b = tile_prefix + warp_excl + (incl_w - run) + fs.bias;   // + bias folded in
+        const unsigned long long base_raw = tile_prefix + warp_excl + (incl_w - run);
+        const unsigned long long base_b = base_raw + fs.bias;                                    // + bias folded in
         uint32_t e_start, e[IPT];
         if constexpr (sizeof(real) == 4) {
-            // F = 32: the count is the high word of the biased CDF value
-            e_start = (uint32_t)(base_b >> 32);
+            // F = 32: the count is the high word of the biased CDF value.  The thread's first and last
+            // boundary are taken at the rescaled values C rho (see rho_eps above); the items in between use
+            // the thread-local increments as they are (an error below 2^-7 index units, absorbed by the
+            // thread's last item), clamped so that consecutive threads tile the outputs exactly.
+            const unsigned long long end_raw = base_raw + run;
+            const unsigned long long bs = base_b + (unsigned long long)__mul64hi((long long)base_raw, rho_eps);
+            const unsigned long long be = end_raw + fs.bias + (unsigned long long)__mul64hi((long long)end_raw, rho_eps);
+            e_start = (uint32_t)(bs >> 32);
+            const uint32_t e_end = (uint32_t)(be >> 32);
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) e[k] = (uint32_t)((base_b + c[k]) >> 32);
+            for (int k = 0; k < IPT - 1; ++k) e[k] = umin(umax((uint32_t)((bs + c[k]) >> 32), e_start), e_end);
+            e[IPT - 1] = e_end;
         } else
         {
             uint32_t near = 0;
@@ -2278,7 +2321,7 @@ void fill_k3_args(const Launch& l, K3Args<real>& a, const void* wsrc, int nxf, u
     a.rtot = l.agg();
     a.mom_parts = want_moments ? l.mom_parts() : nullptr;
     a.cdf_offset = cdf_offset;
-    a.totals = totals; a.rank = rank;
+    a.totals = totals; a.rank = rank; a.n_totals = n_shards;
     a.n = d->n; a.n_global = d->n_global; a.offset = d->offset; a.ld = d->ld;
     a.shard_n = n_shards > 0 ? d->n_global / n_shards : d->n_global;
     a.force = force;
