@@ -169,9 +169,12 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SV SIR bootstrap filter, systematic resampling every step; CPU arm on a "
-                               "bounded sample (particle-updates/s is flat in N for this path)",
-                   "n_particles_timed": n_cpu, "n_particles_workload": 1 << args.log2n},
+        "config": {"workload": f"SV SIR bootstrap filter N=2^{args.log2n}, systematic resampling every step "
+                               "(BASELINE.json configs[2] / SURVEY 8d C3)",
+                   "n_particles": 1 << args.log2n, "nx": 1, "nz": 1, "resample": "every step",
+                   "noise": "numpy Generator (PCG64)",
+                   "sample": f"each step is timed on N_cpu = 2^22 particles with {threads} host threads "
+                             "(particle-updates/s is flat in N for this path)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
