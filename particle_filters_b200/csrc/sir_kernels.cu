@@ -1489,8 +1489,11 @@ k3_resample(K3Args<real> a, FM fm) {
                     const uint32_t p23 = *reinterpret_cast<const uint32_t*>(ids + sl + 2);
                     uint32_t m[4] = {p01 & 0xffffu, p01 >> 16, p23 & 0xffffu, p23 >> 16};
                     if (m[0] == 0u && w0 > s0) {                          // ancestor of the slots before this quad
-                        uint32_t qq = w0;
-                        do { --qq; m[0] = ids[slot(qq)]; } while (m[0] == 0u && qq > 0u);
+                        m[0] = ids[sl - ((w0 & (uint32_t)(IPT - 1)) ? 1u : 3u)];   // the slot just before (one step covers most)
+                        if (m[0] == 0u) {
+                            uint32_t qq = w0 - 1u;
+                            do { --qq; m[0] = ids[slot(qq)]; } while (m[0] == 0u && qq > 0u);
+                        }
                     }
 #pragma unroll
                     for (int j = 1; j < 4; ++j) m[j] = m[j] ? m[j] : m[j - 1];
