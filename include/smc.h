@@ -87,7 +87,7 @@ int smc_abi_version(void);
 const char *smc_last_error(void);
 uint64_t smc_sizeof_sir_desc(void);
 
-/* Workspace size for a shard (control block, block partials, scan tile state). */
+/* Workspace size for a shard (control block, block partials, pre-pass range totals, moment partials). */
 uint64_t smc_sir_workspace_bytes(int64_t n, int32_t nx, int32_t dtype);
 
 /* Reset the control block: current buffer = x0, weights uniform, moment shift =
@@ -155,10 +155,12 @@ int64_t smc_partial_stride(int32_t nx);
 int smc_sir_reduce_partials(const smc_sir_desc *d, double *out_dev, void *stream);
 
 /* K3: systematic resampling (particle_filter.py:146-171 + gather :209-210;
- * LEDH_particle_filter.py:25-37).  One pass: fixed-point decoupled-look-back
- * scan of the normalised weights, closed-form search of the stratified
- * positions with exact tie handling, shared-memory-staged ancestor gather into
- * the other ping-pong buffer, post-resample moments.  A no-op when the control
+ * LEDH_particle_filter.py:25-37).  A range pre-pass sums the 64-bit fixed-point weights of contiguous
+ * tile ranges; the persistent resampler then carries the exact CDF prefix from tile to tile, finds the
+ * output boundaries in closed form (fp64 mode: exact tie handling against NumPy's rounding of
+ * (u + i) / N; fp32 mode: positions laid over the actual fixed-point total), expands them through a
+ * shared-memory marker window and gathers the payload into the other ping-pong buffer, accumulating
+ * the post-resample moments.  A no-op when the control
  * block says "do not resample".  cdf_offset_fix / total are used by sharded
  * runs (exclusive prefix of lower ranks' weight totals in 2^-32 index units,
  * see smc_sir_shard_weight_total); pass 0 for a single shard.  peer_x_dev:
@@ -206,7 +208,7 @@ int smc_sir_step(const smc_sir_desc *d, int32_t model_id, const double *params_h
 
 /* The two halves of smc_sir_step, for callers that want to time or interleave them:
  *  _weight  : K1 with the K2 finalize folded into its last CTA (one launch);
- *  _resample: phases bit 1 = tile pre-pass + tile scan, bit 2 = K3 with the finish step folded
+ *  _resample: phases bit 1 = range pre-pass, bit 2 = K3 with the finish step folded
  *             into its last CTA; a no-op on the data when the control block says "do not resample". */
 int smc_sir_step_weight(const smc_sir_desc *d, int32_t model_id, const double *params_host,
                         int32_t n_params, const double *z_dev, const void *noise_dev,

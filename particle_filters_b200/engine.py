@@ -212,7 +212,7 @@ class SirEngine:
             float(thresh), float(u), C.c_uint64(seed), t, self._row(row), self.stream))
 
     def step_resample(self, phases: int = 3, row: int = 0):
-        """Second half of ``step``: 1 = tile pre-pass + scan, 2 = K3 with the fused finish, 3 = both."""
+        """Second half of ``step``: 1 = range pre-pass, 2 = K3 with the fused finish, 3 = both."""
         check(self.lib.smc_sir_step_resample(self._d, int(phases), self._row(row), self.stream))
 
     def read_row(self, row: int = 0) -> np.ndarray:
