@@ -257,6 +257,17 @@ int smc_sir_step_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_
  * w_dev = n normalised fp64 weights, ancestors_dev = n int32 out. */
 int smc_systematic_ancestors(const double *w_dev, int64_t n, double u, int32_t *ancestors_dev,
                              void *ws_dev, uint64_t ws_bytes, void *stream);
+/* ParticleFilter._multinomial_resample(weights) (particle_filter.py:173-186), i.e. NumPy's
+ * rng.choice(n, size=n_out, p=w) = searchsorted(cumsum(w)/sum(w), u, side='right'):
+ * ancestors[i] = #{ j : cdf_j <= u_i }.  w_dev = n fp64 probabilities (16-byte aligned); u_dev =
+ * n_out fp64 uniforms in [0,1) (the host's rng.random(n_out): reference-noise mode) or NULL for
+ * on-chip Philox uniforms keyed by (seed, t, i).  The CDF is an exact 2^-62 fixed-point prefix
+ * sum and the comparison is exact (128-bit), so results do not depend on the launch shape.
+ * ws_dev: smc_multinomial_workspace_bytes(n) bytes, 256-byte aligned. */
+uint64_t smc_multinomial_workspace_bytes(int64_t n);
+int smc_multinomial_ancestors(const double *w_dev, int64_t n, int64_t n_out, const double *u_dev,
+                              uint64_t seed, int64_t t, int32_t *ancestors_dev, void *ws_dev,
+                              uint64_t ws_bytes, void *stream);
 /* particles[idx] (particle_filter.py:209): dst[d*ld+i] = src[d*ld+idx[i]]. */
 int smc_gather(const void *src_dev, void *dst_dev, const int32_t *idx_dev, int64_t n, int64_t ld,
                int32_t nx, int32_t dtype, void *stream);

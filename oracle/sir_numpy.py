@@ -124,6 +124,16 @@ def multinomial_ancestors(weights: Array, rng) -> Array:
     return rng.choice(n, size=n, p=weights)
 
 
+def multinomial_ancestors_from_uniforms(weights: Array, u: Array) -> Array:
+    """What ``rng.choice(N, size=len(u), p=w)`` computes from its uniforms ``u = rng.random(len(u))``
+    (NumPy 2.3 ``Generator.choice``, replace=True with ``p``: ``cdf = p.cumsum(); cdf /= cdf[-1];
+    cdf.searchsorted(uniform_samples, side='right')``); checked against ``rng.choice`` itself in
+    tests/test_oracle_golden.py.  This is the checker of the device multinomial resampler."""
+    cdf = np.cumsum(np.asarray(weights, float))
+    cdf /= cdf[-1]
+    return np.searchsorted(cdf, np.asarray(u, float), side="right").astype(np.int64)
+
+
 def normalize_log_weights(logw: Array) -> Tuple[Array, float]:
     """Stable normalisation, reference ``particle_filter.py:262-263``.
 

@@ -95,6 +95,9 @@ _SIG = {
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_systematic_ancestors": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_uint64, _P]),
+    "smc_multinomial_workspace_bytes": (C.c_uint64, [C.c_int64]),
+    "smc_multinomial_ancestors": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_uint64, C.c_int64, _P, _P,
+                                            C.c_uint64, _P]),
     "smc_gather": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P]),
     "smc_sir_export_weights": (C.c_int, [C.POINTER(SirDesc), _P, _P]),
     "smc_sir_current_buffer": (C.c_int, [C.POINTER(SirDesc), C.POINTER(C.c_int32), _P]),

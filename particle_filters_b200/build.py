@@ -19,7 +19,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libsmc.so")
 STAMP = os.path.join(OUT_DIR, "libsmc.stamp")
 
-SOURCES = ["sir_kernels.cu", "ledh_kernels.cu"]
+SOURCES = ["sir_kernels.cu", "ledh_kernels.cu", "multinomial.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -38,10 +38,9 @@ def _sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def _fingerprint() -> str:
+def _hash(names) -> str:
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + ["../../include/smc.h", "../../include/smc_ledh.h"]
-    for name in files:
+    for name in names:
         p = os.path.normpath(os.path.join(CSRC, name))
         if os.path.isfile(p):
             with open(p, "rb") as f:
@@ -51,6 +50,14 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def _headers():
+    return sorted(n for n in os.listdir(CSRC) if not n.endswith(".cu")) + ["../../include/smc.h", "../../include/smc_ledh.h"]
+
+
+def _fingerprint() -> str:
+    return _hash(sorted(n for n in os.listdir(CSRC) if n.endswith(".cu")) + _headers())
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     fp = _fingerprint()
@@ -58,28 +65,44 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(STAMP) as f:
             if f.read().strip() == fp:
                 return LIB
-    # one nvcc process per translation unit (they share no device code), then one link step
+    # one nvcc process per translation unit (they share no device code), then one link step; an
+    # object whose source and headers are unchanged since it was compiled is reused
     from concurrent.futures import ThreadPoolExecutor
 
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
-    objs = [os.path.join(OUT_DIR, os.path.splitext(os.path.basename(src))[0] + ".o") for src in _sources()]
+    jobs = []
+    objs = []
+    for src in _sources():
+        stem = os.path.splitext(os.path.basename(src))[0]
+        obj, ostamp = os.path.join(OUT_DIR, stem + ".o"), os.path.join(OUT_DIR, stem + ".ostamp")
+        ofp = _hash([os.path.basename(src)] + _headers())
+        objs.append(obj)
+        fresh = False
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(ostamp):
+            with open(ostamp) as f:
+                fresh = f.read().strip() == ofp
+        if not fresh:
+            jobs.append((src, obj, ostamp, ofp))
 
-    def compile_one(pair):
-        src, obj = pair
+    def compile_one(job):
+        src, obj, ostamp, ofp = job
+        if os.path.exists(ostamp):
+            os.remove(ostamp)
         return subprocess.run([_nvcc()] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
 
-    with ThreadPoolExecutor(max_workers=len(objs)) as pool:
-        results = list(pool.map(compile_one, zip(_sources(), objs)))
-    for res in results:
-        if verbose:
-            sys.stderr.write(res.stderr)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            results = list(pool.map(compile_one, jobs))
+        for job, res in zip(jobs, results):
+            if verbose:
+                sys.stderr.write(res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            with open(job[2], "w") as f:
+                f.write(job[3])
     res = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-    for obj in objs:
-        os.remove(obj)
     with open(STAMP, "w") as f:
         f.write(fp)
     return LIB

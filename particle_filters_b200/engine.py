@@ -189,6 +189,32 @@ class SirEngine:
         kl, pl = _lib.as_doubles(Lq)
         check(self.lib.smc_sir_jitter(self._d, pl, float(scale), C.c_uint64(seed), t, self.stream))
 
+    def resample_multinomial(self, u: Optional[np.ndarray] = None, seed: int = 0, t: int = 0):
+        """Multinomial resampling of the current weighted set, all on the device: export the fp64
+        weights, draw ancestors (``u`` = the host's ``rng.random(n)`` in reference-noise mode, else
+        on-chip Philox), gather into the other ping-pong buffer.  ``finish_step`` flips the buffers."""
+        torch = self.torch
+        assert self.n == self.n_global, "multinomial resampling is single-shard"
+        if getattr(self, "_mn_ws", None) is None:
+            self._mn_w = torch.empty((self.n,), dtype=torch.float64, device=self.device)
+            self._mn_bytes = int(self.lib.smc_multinomial_workspace_bytes(self.n))
+            self._mn_ws = torch.empty((self._mn_bytes,), dtype=torch.uint8, device=self.device)
+            self._mn_anc = self.ancestors if self.ancestors is not None else \
+                torch.empty((self.n,), dtype=torch.int32, device=self.device)
+        ud = None
+        if u is not None:
+            ud = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64).reshape(-1)).to(self.device)
+            assert ud.numel() == self.n
+        check(self.lib.smc_sir_export_weights(self._d, C.c_void_p(self._mn_w.data_ptr()), self.stream))
+        check(self.lib.smc_multinomial_ancestors(
+            C.c_void_p(self._mn_w.data_ptr()), self.n, self.n, C.c_void_p(ud.data_ptr()) if ud is not None else None,
+            C.c_uint64(seed), int(t), C.c_void_p(self._mn_anc.data_ptr()), C.c_void_p(self._mn_ws.data_ptr()),
+            C.c_uint64(self._mn_bytes), self.stream))
+        cur = self.current_buffer()
+        check(self.lib.smc_gather(C.c_void_p(self.x[cur].data_ptr()), C.c_void_p(self.x[cur ^ 1].data_ptr()),
+                                  C.c_void_p(self._mn_anc.data_ptr()), self.n, self.ld, self.nx, self.dtype_code,
+                                  self.stream))
+
     def finish_step(self, row: int = 0, mom_parts=None, n_mom_parts: int = 0):
         check(self.lib.smc_sir_finish_step(
             self._d, self._row(row),
@@ -332,6 +358,34 @@ def systematic_ancestors(weights: np.ndarray, u: float, device=None) -> np.ndarr
     check(lib.smc_systematic_ancestors(C.c_void_p(wd.data_ptr()), n, float(u), C.c_void_p(anc.data_ptr()),
                                        C.c_void_p(ws.data_ptr()), C.c_uint64(ws_bytes), st))
     return anc[:n].cpu().numpy().astype(np.int64)
+
+
+def multinomial_ancestors(weights: np.ndarray, u: Optional[np.ndarray] = None, size: Optional[int] = None,
+                          seed: int = 0, t: int = 0, device=None) -> np.ndarray:
+    """GPU multinomial resampling of fp64 probabilities -> int64 ancestors (reference
+    ``ParticleFilter._multinomial_resample``, particle_filter.py:173-186, i.e. ``rng.choice(N, size, p=w)``).
+    ``u``: the uniforms ``rng.random(size)`` that ``choice`` would have drawn (reference-noise mode);
+    ``None`` draws them on chip from Philox ``(seed, t)``."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    w = np.ascontiguousarray(weights, dtype=np.float64).reshape(-1)
+    n = w.shape[0]
+    n_out = int(size) if size is not None else (n if u is None else int(np.size(u)))
+    wd = torch.from_numpy(w).to(dev)
+    ud = None
+    if u is not None:
+        ud = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64).reshape(-1)).to(dev)
+        assert ud.numel() == n_out
+    anc = torch.empty((n_out,), dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.smc_multinomial_workspace_bytes(n))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.smc_multinomial_ancestors(C.c_void_p(wd.data_ptr()), n, n_out,
+                                        C.c_void_p(ud.data_ptr()) if ud is not None else None,
+                                        C.c_uint64(seed), int(t), C.c_void_p(anc.data_ptr()),
+                                        C.c_void_p(ws.data_ptr()), C.c_uint64(ws_bytes), st))
+    return anc.cpu().numpy().astype(np.int64)
 
 
 def gather_rows(particles: np.ndarray, idx: np.ndarray, device=None) -> np.ndarray:

@@ -222,9 +222,19 @@ class ParticleFilter:
         return systematic_ancestors(np.asarray(weights, float), self.rng.random(), device=self._device)
 
     def _multinomial_resample(self, weights: Array) -> Array:
-        """Multinomial resampling indices (reference :173-186).  The draw itself is
-        ``rng.choice`` so that the caller's NumPy stream stays the reference's."""
-        return self.rng.choice(len(weights), size=len(weights), p=weights)
+        """Multinomial resampling indices (reference :173-186) from the GPU resampler.  The caller's
+        NumPy stream is consumed exactly as ``rng.choice(N, size=N, p=weights)`` consumes it (one
+        ``rng.random(N)``), and the same arguments are rejected with the same ``ValueError``."""
+        from .engine import multinomial_ancestors
+
+        p = np.asarray(weights, float).reshape(-1)
+        if np.isnan(p).any():
+            raise ValueError("probabilities contain NaN")
+        if (p < 0).any():
+            raise ValueError("probabilities are not non-negative")
+        if abs(float(np.sum(p)) - 1.0) > np.sqrt(np.finfo(np.float64).eps):
+            raise ValueError("probabilities do not sum to 1")
+        return multinomial_ancestors(p, self.rng.random(len(p)), device=self._device)
 
     def _resample(self, particles: Array, weights: Array) -> Tuple[Array, Array]:
         """Resample when Neff < resample_thresh * Np (reference :188-220)."""
@@ -245,14 +255,7 @@ class ParticleFilter:
             eng.set_uniform(self.rng.random())
             eng.resample()
         else:
-            w = eng.weights() if w_norm is None else w_norm
-            idx = self._multinomial_resample(w)
-            import ctypes as C
-
-            ix = eng.torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(eng.device)
-            cur = eng.current_buffer()
-            _lib.check(eng.lib.smc_gather(C.c_void_p(eng.x[cur].data_ptr()), C.c_void_p(eng.x[cur ^ 1].data_ptr()),
-                                          C.c_void_p(ix.data_ptr()), n, eng.ld, self.nx, eng.dtype_code, eng.stream))
+            eng.resample_multinomial(u=self.rng.random(n))
         if self.regularize_after_resample:
             Lq = self._chol_Q(1e-12)
             jitter = self.rng.standard_normal((n, self.nx))
@@ -361,13 +364,12 @@ class ParticleFilter:
         return self.state
 
     def _device_multinomial(self, eng):
-        import ctypes as C
-
-        idx = self._multinomial_resample(eng.weights())
-        ix = eng.torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(eng.device)
-        cur = eng.current_buffer()
-        _lib.check(eng.lib.smc_gather(C.c_void_p(eng.x[cur].data_ptr()), C.c_void_p(eng.x[cur ^ 1].data_ptr()),
-                                      C.c_void_p(ix.data_ptr()), eng.n, eng.ld, self.nx, eng.dtype_code, eng.stream))
+        """Ancestors + gather on the device; only the uniforms come from the host, and only in
+        reference-noise mode (so that ``self.rng`` advances as the reference's ``rng.choice`` does)."""
+        if self._noise == "reference":
+            eng.resample_multinomial(u=self.rng.random(eng.n))
+        else:
+            eng.resample_multinomial(seed=self._seed, t=self._t_phil)
 
     def step(self, z: Array, u: Optional[Array] = None) -> PFState:
         """One PF step: predict then update (reference :271-287); fused into a single

@@ -137,3 +137,22 @@ class _FixedUFromRef:
 
     def random(self):
         return self.r.random()
+
+
+def test_multinomial_restatement_equals_rng_choice():
+    """oracle.multinomial_ancestors_from_uniforms is what rng.choice(N, size=N, p=w) computes from
+    rng.random(N) (reference particle_filter.py:173-186 delegates to it); both generators end in
+    the same state."""
+    from oracle.sir_numpy import multinomial_ancestors_from_uniforms
+
+    for n in (1, 7, 1000, 4097):
+        w = np.random.default_rng(n).random(n)
+        if n > 5:
+            w[::5] = 0.0
+        w /= w.sum()
+        r1, r2 = np.random.default_rng(5), np.random.default_rng(5)
+        want = r1.choice(n, size=n, p=w)
+        got = multinomial_ancestors_from_uniforms(w, r2.random(n))
+        np.testing.assert_array_equal(got, want)
+        assert got.dtype == want.dtype
+        assert r1.random() == r2.random()
