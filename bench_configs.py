@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Timing lines for the other BASELINE.json configurations (bench.py measures the headline C3):
 
-    python bench_configs.py [--configs c2,c4,c5] [--steps K]
+    python bench_configs.py [--configs c2,c3ess,c4,c5] [--steps K]
 
   c2  2-D LGSSM SIR filter vs the exact Kalman filter, N = 2^24 (README A/B/C/D model)
+  c3ess  C3 (SV, N = 2^26) with ESS-triggered resampling (resample_thresh = 0.5)
   c4  Lorenz-96 (d = 40, 20 RK4 sub-steps, every 4th variable observed), ESS-triggered resampling, N = 2^22
   c5  LEDH particle flow, 4-target acoustic tracking (16-D state, 25 sensors), N = 2^20
 
@@ -70,6 +71,36 @@ def run_c2(K, log2n=24):
                                                       "achieved": alg * v / 1e9, "peak": peak_hbm(), "unit": "GB/s",
                                                       "frac": alg * v / 1e9 / peak_hbm()},
             "check": {"max_abs_mean_error_vs_kalman": err, "posterior_std": float(np.sqrt(P[0, 0]))}}
+
+
+def run_c3ess(K, log2n=26):
+    """C3's model and size with the reference's default trigger (resample_thresh = 0.5): the device decides
+    per step; B_alg is the mix of 32 B (resampling step) and 16 B."""
+    import torch
+    from particle_filters_b200 import ParticleFilter, StochVolSSM
+
+    alpha, sigma, beta = 0.95, 0.2, 1.0
+    rng = np.random.default_rng(42)
+    x, Y = rng.standard_normal() * sigma / np.sqrt(1 - alpha ** 2), np.empty(K + 5)
+    for t in range(K + 5):
+        x = alpha * x + sigma * rng.standard_normal()
+        Y[t] = beta * np.exp(0.5 * x) * rng.standard_normal()
+    N = 1 << log2n
+    spec = StochVolSSM(alpha, beta)
+    pf = ParticleFilter(spec.g, spec.h, np.array([[sigma ** 2]]), np.array([[beta ** 2]]), Np=N, resample_thresh=0.5,
+                        dtype="f32", noise="philox", seed=42)
+    pf.initialize(np.zeros(1), np.array([[sigma ** 2 / (1 - alpha ** 2)]]))
+    pf.run(Y[:5].reshape(-1, 1))
+    out, ms = timed(lambda: pf.run(Y[5:].reshape(-1, 1)), torch)
+    v = N * K / (ms * 1e-3)
+    f = float(np.mean(out["resampled"]))
+    alg = 32 * f + 16 * (1 - f)
+    return {"config": "c3ess", "metric": "particle-updates/s (SIR, SV model, N=2^%d, resample_thresh=0.5)" % log2n,
+            "value": v, "ms_per_step": ms / K, "steps": K, "dtype": "f32",
+            "roofline": {"bound": "hbm", "alg_bytes_per_particle_update": alg, "achieved": alg * v / 1e9,
+                         "peak": peak_hbm(), "unit": "GB/s", "frac": alg * v / 1e9 / peak_hbm()},
+            "check": {"resampled_fraction": f, "ess_over_n_min": float(np.min(out["ess"]) / N),
+                      "mean_finite": bool(np.isfinite(out["mean"]).all())}}
 
 
 def run_c4(K, log2n=22):
@@ -181,7 +212,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=0)
     args = ap.parse_args()
     for c in args.configs.split(","):
-        fn = {"c2": run_c2, "c4": run_c4, "c5": run_c5}[c.strip()]
+        fn = {"c2": run_c2, "c3ess": run_c3ess, "c4": run_c4, "c5": run_c5}[c.strip()]
         kw = {"log2n": args.log2n} if args.log2n else {}
         print(json.dumps(fn(args.steps, **kw)), flush=True)
 

@@ -11,8 +11,11 @@
 // deviations from the reference are where the reference's own sequential fp64 cumsum rounds a CDF
 // value across a uniform (the same "cumulative-weight tie" rule as the systematic resampler).
 //
-// Four launches: tile totals -> one-CTA scan of the totals -> tile scans (write C) -> search.
-// All HBM traffic is streaming except the search, whose upper levels stay in L2.
+// Five launches: tile totals -> one-CTA scan of the totals -> tile scans (write C) -> guide table ->
+// search.  The guide table (cut-point method) holds, for 2^L ~ N/8 equal cells of the CDF's value
+// range, how many CDF entries lie below the cell: it is built by coherent (neighbouring threads ->
+// neighbouring thresholds) binary searches, stays L2-resident (N/2 bytes), and leaves each of the N
+// random-order outputs a search over ~8 adjacent CDF entries instead of log2 N scattered HBM probes.
 #include "smc_common.cuh"
 
 #include <string.h>
@@ -26,17 +29,27 @@ constexpr int kMnScanThreads = 1024;
 constexpr uint32_t kStreamMultinomial = 4;      // Philox stream of the on-chip uniforms
 
 struct MnLayout {
-    size_t cdf, tile_off, total;
+    size_t cdf, tile_off, guide, total;
     int64_t n_tiles;
+    int log2_cells;
 };
 inline MnLayout mn_layout(int64_t n) {
     MnLayout L;
     L.n_tiles = cdiv64(n, kMnTile);
+    L.log2_cells = 0;
+    while ((int64_t(8) << L.log2_cells) < n) ++L.log2_cells;     // 2^L cells ~ n / 8
     size_t off = 0;
     L.cdf = off;      off = align256(off + size_t(n) * 8);
     L.tile_off = off; off = align256(off + size_t(L.n_tiles + 1) * 8);
+    L.guide = off;    off = align256(off + ((size_t(1) << L.log2_cells) + 2) * 4);
     L.total = off;
     return L;
+}
+
+// cell of a CDF value q < T: q >> s, with s such that T >> s < 2^L
+__device__ __forceinline__ int guide_shift(unsigned long long T, int log2_cells) {
+    const int bits = 64 - __clzll((long long)T);
+    return bits > log2_cells ? bits - log2_cells : 0;
 }
 
 __device__ __forceinline__ unsigned long long quantise62(double w) {
@@ -174,11 +187,25 @@ __device__ __forceinline__ int64_t upper_bound_u64(const unsigned long long* C, 
     return lo;
 }
 
+// guide[b] = #{ j : C_j < b 2^s } for b = 0 .. (T >> s) + 1: the answer for any q in cell b lies in
+// [guide[b], guide[b + 1]]
+__global__ void __launch_bounds__(kThreads) k_mn_guide(const unsigned long long* cdf, const unsigned long long* tile_off,
+                                                       int64_t n_tiles, int64_t n, int log2_cells, int32_t* guide) {
+    const unsigned long long T = tile_off[n_tiles];
+    const int s = guide_shift(T, log2_cells);
+    const unsigned long long cells = (T >> s) + 1;
+    const unsigned long long b = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+    if (b > cells) return;
+    guide[b] = b == 0 ? 0 : (int32_t)upper_bound_u64(cdf, n, (b << s) - 1);
+}
+
 // two outputs per thread: one Philox block yields both uniforms in on-chip mode
 __global__ void __launch_bounds__(kThreads) k_mn_search(const unsigned long long* cdf, const unsigned long long* tile_off,
                                                         int64_t n_tiles, int64_t n, int64_t n_out, const double* u_dev,
-                                                        PhiloxKeys keys, uint32_t t, int32_t* ancestors) {
+                                                        PhiloxKeys keys, uint32_t t, int log2_cells,
+                                                        const int32_t* guide, int32_t* ancestors) {
     const unsigned long long T = tile_off[n_tiles];
+    const int s = guide_shift(T, log2_cells);
     const int64_t pair = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t i0 = pair * 2;
     if (i0 >= n_out) return;
@@ -195,7 +222,13 @@ __global__ void __launch_bounds__(kThreads) k_mn_search(const unsigned long long
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         if (i0 + k >= n_out) break;
-        int64_t a = T ? upper_bound_u64(cdf, n, scale_uniform(u[k], T)) : 0;
+        int64_t a = 0;
+        if (T) {
+            const unsigned long long q = scale_uniform(u[k], T);
+            const unsigned long long b = q >> s;
+            const int64_t lo = __ldg(guide + b), hi = __ldg(guide + b + 1);
+            a = lo + upper_bound_u64(cdf + lo, hi - lo, q);
+        }
         ancestors[i0 + k] = (int32_t)(a < n ? a : n - 1);
     }
 }
@@ -228,9 +261,13 @@ int smc_multinomial_ancestors(const double* w_dev, int64_t n, int64_t n_out, con
     SMC_CHECK_CUDA(cudaGetLastError());
     k_mn_scan_write<<<grid, kThreads, 0, st>>>(w_dev, n, tile_off, cdf);
     SMC_CHECK_CUDA(cudaGetLastError());
+    int32_t* guide = reinterpret_cast<int32_t*>(ws + L.guide);
+    const unsigned ggrid = (unsigned)cdiv64((int64_t(1) << L.log2_cells) + 1, kThreads);
+    k_mn_guide<<<ggrid, kThreads, 0, st>>>(cdf, tile_off, L.n_tiles, n, L.log2_cells, guide);
+    SMC_CHECK_CUDA(cudaGetLastError());
     const unsigned sgrid = (unsigned)cdiv64(cdiv64(n_out, 2), kThreads);
     k_mn_search<<<sgrid, kThreads, 0, st>>>(cdf, tile_off, L.n_tiles, n, n_out, u_dev, philox_expand(seed), (uint32_t)t,
-                                            ancestors_dev);
+                                            L.log2_cells, guide, ancestors_dev);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
