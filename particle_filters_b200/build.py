@@ -54,6 +54,22 @@ def _headers():
     return sorted(n for n in os.listdir(CSRC) if not n.endswith(".cu")) + ["../../include/smc.h", "../../include/smc_ledh.h"]
 
 
+def _deps(name, seen=None):
+    """``name`` plus the quoted includes it reaches (paths relative to csrc/)."""
+    import re
+
+    seen = [] if seen is None else seen
+    if name in seen:
+        return seen
+    seen.append(name)
+    path = os.path.normpath(os.path.join(CSRC, name))
+    if os.path.isfile(path):
+        with open(path) as f:
+            for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', f.read(), flags=re.M):
+                _deps(os.path.normpath(os.path.join(os.path.dirname(name), inc)), seen)
+    return seen
+
+
 def _fingerprint() -> str:
     return _hash(sorted(n for n in os.listdir(CSRC) if n.endswith(".cu")) + _headers())
 
@@ -75,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in _sources():
         stem = os.path.splitext(os.path.basename(src))[0]
         obj, ostamp = os.path.join(OUT_DIR, stem + ".o"), os.path.join(OUT_DIR, stem + ".ostamp")
-        ofp = _hash([os.path.basename(src)] + _headers())
+        ofp = _hash(_deps(os.path.basename(src)))
         objs.append(obj)
         fresh = False
         if not force and not verbose and os.path.exists(obj) and os.path.exists(ostamp):

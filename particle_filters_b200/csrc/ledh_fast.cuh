@@ -31,6 +31,21 @@ template <int NP> __device__ __forceinline__ void ld_row(const float* p, float (
         out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
     }
 }
+// 16-byte stores of the first N entries of a register row into a padded scratch row (pad lanes get 0)
+template <int NP, int N> __device__ __forceinline__ void st_row(float* p, const float (&v)[N]) {
+#pragma unroll
+    for (int q = 0; q < NP / 4; ++q)
+        reinterpret_cast<float4*>(p)[q] = make_float4(4 * q < N ? v[4 * q < N ? 4 * q : 0] : 0.f,
+                                                      4 * q + 1 < N ? v[4 * q + 1 < N ? 4 * q + 1 : 0] : 0.f,
+                                                      4 * q + 2 < N ? v[4 * q + 2 < N ? 4 * q + 2 : 0] : 0.f,
+                                                      4 * q + 3 < N ? v[4 * q + 3 < N ? 4 * q + 3 : 0] : 0.f);
+}
+template <int NP, int N> __device__ __forceinline__ void st_row(double* p, const double (&v)[N]) {
+#pragma unroll
+    for (int q = 0; q < NP / 2; ++q)
+        reinterpret_cast<double2*>(p)[q] = make_double2(2 * q < N ? v[2 * q < N ? 2 * q : 0] : 0.0,
+                                                        2 * q + 1 < N ? v[2 * q + 1 < N ? 2 * q + 1 : 0] : 0.0);
+}
 template <int NP> __device__ __forceinline__ void ld_row(const double* p, double (&out)[NP]) {
 #pragma unroll
     for (int q = 0; q < NP / 2; ++q) {
@@ -42,6 +57,11 @@ __device__ __forceinline__ float log_abs_acc(float v) { return logf(fabsf(v)); }
 __device__ __forceinline__ double log_abs_acc(double v) { return log(fabs(v)); }
 
 constexpr int kLedhFastWarps = 4;
+#ifndef SMC_LEDH_FAST_MINB
+#define SMC_LEDH_FAST_MINB 3        // fp32: resident CTAs per SM the register allocation is held to.  Measured C5 step
+                                   // (N=2^20, L=8): 1 (254 regs, 2 CTAs) 299 ms, 3 (168 regs) 163 ms, 4 (128) 165 ms,
+                                   // 5 (96) 296 ms, 6 (80) 174 ms -- the kernel is latency bound, not issue bound
+#endif
 
 template <typename real, int NX, int NZ> struct LedhFastSmem {
     static constexpr int NXP = Pad4<NX>::value, NZP = Pad4<NZ>::value;
@@ -54,7 +74,7 @@ template <typename real, int NX, int NZ> struct LedhFastSmem {
 };
 
 template <typename real, int NX, int NZ>
-__global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArgs<real> a) {
+__global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_LEDH_FAST_MINB : 1) k4_ledh_flow_fast(LedhArgs<real> a) {
     static_assert(NX <= 32 && NZ <= 32, "lane = row layout needs nx, nz <= 32");
     constexpr int NXP = Pad4<NX>::value, NZP = Pad4<NZ>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -136,10 +156,7 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArg
 #pragma unroll
             for (int t = 0; t < NX; ++t) Hr[t] = (t == lz) ? real(0.5) * v : real(0);
         }
-        if (rz) {
-#pragma unroll
-            for (int t = 0; t < NX; ++t) Hs[lane * NXP + t] = Hr[t];
-        }
+        if (rz) st_row<NXP>(Hs + lane * NXP, Hr);
         real innov = sz[lz] - hx;                 // z - e = z - (h - H eta)
 #pragma unroll
         for (int t = 0; t < NX; ++t) innov = fma(Hr[t], eta[t], innov);
@@ -176,16 +193,17 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArg
             const real d = sqrt_real(shfl_real(Sr[c], c));
             if (lane == c) Sr[c] = d;
             else if (lane > c) Sr[c] = Sr[c] / d;
+            // constant trip count (the triangular bound is a compile-time predicate after unrolling):
+            // with `k = c + 1` as the lower bound Sr[] was left in local memory (ncu: 930 LDL/STL
+            // per particle-substep, profiles/r1_ledh_notes.txt)
 #pragma unroll
-            for (int k = c + 1; k < NZ; ++k) {
+            for (int k = 0; k < NZ; ++k) {
+                if (k <= c) continue;
                 const real lkc = shfl_real(Sr[c], k);
                 if (lane >= k) Sr[k] = fma(-Sr[c], lkc, Sr[k]);
             }
         }
-        if (rz) {
-#pragma unroll
-            for (int c = 0; c < NZ; ++c) Ls[lane * NZP + c] = Sr[c];
-        }
+        if (rz) st_row<NZP>(Ls + lane * NZP, Sr);
         // ---- 4. X = S^-1 H: forward and backward substitution, one row per lane ------------------------
         real Yr[NX];
 #pragma unroll
@@ -195,7 +213,8 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArg
             if (lane == k) {
                 const real inv = real(1) / Sr[k];
 #pragma unroll
-                for (int t = 0; t < NX; ++t) { Yr[t] *= inv; Xs[k * NXP + t] = Yr[t]; }
+                for (int t = 0; t < NX; ++t) Yr[t] *= inv;
+                st_row<NXP>(Xs + k * NXP, Yr);
             }
             __syncwarp();
             if (lane > k && rz) {
@@ -211,7 +230,8 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArg
             if (lane == k) {
                 const real inv = real(1) / Sr[k];
 #pragma unroll
-                for (int t = 0; t < NX; ++t) { Yr[t] *= inv; Xs[k * NXP + t] = Yr[t]; }
+                for (int t = 0; t < NX; ++t) Yr[t] *= inv;
+                st_row<NXP>(Xs + k * NXP, Yr);
             }
             __syncwarp();
             if (lane < k) {
@@ -301,7 +321,8 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps) k4_ledh_flow_fast(LedhArg
                 if (lane == arg) { used = true; step_of = c; }
                 const real f = used ? real(0) : Mr[c] / piv;
 #pragma unroll
-                for (int k = c + 1; k < NX; ++k) {
+                for (int k = 0; k < NX; ++k) {
+                    if (k <= c) continue;
                     const real pk = shfl_real(Mr[k], arg);
                     Mr[k] = fma(-f, pk, Mr[k]);
                 }
