@@ -23,6 +23,25 @@ __device__ __forceinline__ double log_abs(double v) { return log(fabs(v)); }
 __device__ __forceinline__ float sqrt_real(float v) { return sqrtf(v); }
 __device__ __forceinline__ double sqrt_real(double v) { return sqrt(v); }
 
+// lane holding the largest |v| among the lanes not yet used as a pivot row (lowest lane on ties)
+__device__ __forceinline__ int pivot_lane(float v, bool used) {
+    // non-negative floats order like their bit patterns: one redux.sync instead of a shuffle tree
+    const unsigned key = used ? 0u : __float_as_uint(fabsf(v));
+    const unsigned top = __reduce_max_sync(0xffffffffu, key);
+    return __ffs(__ballot_sync(0xffffffffu, !used && key == top)) - 1;
+}
+__device__ __forceinline__ int pivot_lane(double v, bool used) {
+    double best = used ? -1.0 : fabs(v);
+    int arg = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    return arg;
+}
+
 // 16-byte broadcast loads of one padded row from the per-warp scratch
 template <int NP> __device__ __forceinline__ void ld_row(const float* p, float (&out)[NP]) {
 #pragma unroll
@@ -56,9 +75,12 @@ template <int NP> __device__ __forceinline__ void ld_row(const double* p, double
 __device__ __forceinline__ float log_abs_acc(float v) { return logf(fabsf(v)); }
 __device__ __forceinline__ double log_abs_acc(double v) { return log(fabs(v)); }
 
-constexpr int kLedhFastWarps = 4;
+#ifndef SMC_LEDH_FAST_WARPS
+#define SMC_LEDH_FAST_WARPS 4
+#endif
+constexpr int kLedhFastWarps = SMC_LEDH_FAST_WARPS;
 #ifndef SMC_LEDH_FAST_MINB
-#define SMC_LEDH_FAST_MINB 3        // fp32: resident CTAs per SM the register allocation is held to.  Measured C5 step
+#define SMC_LEDH_FAST_MINB 4        // fp32: resident CTAs per SM the register allocation is held to.  Measured C5 step
                                    // (N=2^20, L=8): 1 (254 regs, 2 CTAs) 299 ms, 3 (168 regs) 163 ms, 4 (128) 165 ms,
                                    // 5 (96) 296 ms, 6 (80) 174 ms -- the kernel is latency bound, not issue bound
 #endif
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
             for (int k = 0; k < NZ; ++k) {
                 if (k <= c) continue;
                 const real lkc = shfl_real(Sr[c], k);
-                if (lane >= k) Sr[k] = fma(-Sr[c], lkc, Sr[k]);
+                Sr[k] = fma(-Sr[c], lkc, Sr[k]);        // rows above the diagonal (lane < k) are never read
             }
         }
         if (rz) st_row<NZP>(Ls + lane * NZP, Sr);
@@ -306,14 +328,7 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
             ld = 0; sg = 1;
 #pragma unroll
             for (int c = 0; c < NX; ++c) {
-                real best = used ? real(-1) : fabs(Mr[c]);
-                int arg = lane;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const real ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-                    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-                }
+                const int arg = pivot_lane(Mr[c], used);
                 const real piv = shfl_real(Mr[c], arg);
                 if (piv < 0) sg = -sg;
                 if (piv == 0) sg = 0;
