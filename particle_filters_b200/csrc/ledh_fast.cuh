@@ -210,10 +210,11 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
             for (int c = 0; c < NZ; ++c) out[c] = (double)Sr[c];
         }
         // ---- 3. Cholesky S = L L^T in registers, row per lane, broadcasts by shuffle -------------------
+        real diag = 1;                                           // L[lane][lane]
 #pragma unroll
         for (int c = 0; c < NZ; ++c) {
             const real d = sqrt_real(shfl_real(Sr[c], c));
-            if (lane == c) Sr[c] = d;
+            if (lane == c) { Sr[c] = d; diag = d; }
             else if (lane > c) Sr[c] = Sr[c] / d;
             // constant trip count (the triangular bound is a compile-time predicate after unrolling):
             // with `k = c + 1` as the lower bound Sr[] was left in local memory (ncu: 930 LDL/STL
@@ -227,43 +228,46 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
         }
         if (rz) st_row<NZP>(Ls + lane * NZP, Sr);
         // ---- 4. X = S^-1 H: forward and backward substitution, one row per lane ------------------------
+        // Row k is broadcast UNSCALED and the other rows fold 1/L_kk into their own coefficient
+        // (L_rk / L_kk) w_k; every lane scales its own row once at the end of each sweep.  (Scaling
+        // the broadcast row first costs 16 single-lane multiplies and a division per step.)
+        const real invd = real(1) / diag;
         real Yr[NX];
 #pragma unroll
         for (int t = 0; t < NX; ++t) Yr[t] = Hr[t];
 #pragma unroll
         for (int k = 0; k < NZ; ++k) {
-            if (lane == k) {
-                const real inv = real(1) / Sr[k];
-#pragma unroll
-                for (int t = 0; t < NX; ++t) Yr[t] *= inv;
-                st_row<NXP>(Xs + k * NXP, Yr);
-            }
+            if (lane == k) st_row<NXP>(Xs + k * NXP, Yr);
+            const real ik = shfl_real(invd, k);
             __syncwarp();
             if (lane > k && rz) {
+                const real coef = -Sr[k] * ik;
                 real row[NXP];
                 ld_row<NXP>(Xs + k * NXP, row);
 #pragma unroll
-                for (int t = 0; t < NX; ++t) Yr[t] = fma(-Sr[k], row[t], Yr[t]);
+                for (int t = 0; t < NX; ++t) Yr[t] = fma(coef, row[t], Yr[t]);
             }
         }
+#pragma unroll
+        for (int t = 0; t < NX; ++t) Yr[t] *= invd;
         __syncwarp();
 #pragma unroll
         for (int k = NZ - 1; k >= 0; --k) {
-            if (lane == k) {
-                const real inv = real(1) / Sr[k];
-#pragma unroll
-                for (int t = 0; t < NX; ++t) Yr[t] *= inv;
-                st_row<NXP>(Xs + k * NXP, Yr);
-            }
+            if (lane == k) st_row<NXP>(Xs + k * NXP, Yr);
+            const real ik = shfl_real(invd, k);
             __syncwarp();
             if (lane < k) {
-                const real lkr = Ls[k * NZP + lane];           // L[k][r]
+                const real coef = -Ls[k * NZP + lane] * ik;     // L[k][r] / L[k][k]
                 real row[NXP];
                 ld_row<NXP>(Xs + k * NXP, row);
 #pragma unroll
-                for (int t = 0; t < NX; ++t) Yr[t] = fma(-lkr, row[t], Yr[t]);
+                for (int t = 0; t < NX; ++t) Yr[t] = fma(coef, row[t], Yr[t]);
             }
         }
+#pragma unroll
+        for (int t = 0; t < NX; ++t) Yr[t] *= invd;
+        __syncwarp();
+        if (rz) st_row<NXP>(Xs + lane * NXP, Yr);
         __syncwarp();                                           // Xs = S^-1 H, complete
         // ---- 5. rows of P H^T and A = -1/2 P H^T S^-1 H (:158-159) -------------------------------------
         real PHtr[NZ];
