@@ -89,7 +89,7 @@ template <typename real, int NX, int NZ> struct LedhFastSmem {
     static constexpr int NXP = Pad4<NX>::value, NZP = Pad4<NZ>::value;
     // per-CTA constants, then per-warp scratch
     static constexpr int kConst = NX * NXP + 2 * NZ * NZP + NZP + 64;
-    static constexpr int kPerWarp = 2 * NZ * NXP + NZ * NZP + 2 * NZP + 4 * NXP;
+    static constexpr int kPerWarp = 3 * NZ * NXP + NZ * NZP + 2 * NZP + 4 * NXP;
     static constexpr size_t bytes(int n_hp) {
         return sizeof(real) * (size_t)(kConst + (n_hp > 64 ? (n_hp + 3) / 4 * 4 - 64 : 0) + kLedhFastWarps * kPerWarp);
     }
@@ -117,9 +117,10 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
     for (int i = tid; i < a.n_hp; i += blockDim.x) shp[i] = (real)a.hp[i];
     __syncthreads();
     // ---- per-warp scratch ---------------------------------------------------------------------------
-    real* w = sm + warp * (2 * NZ * NXP + NZ * NZP + 2 * NZP + 4 * NXP);
+    real* w = sm + warp * LedhFastSmem<real, NX, NZ>::kPerWarp;
     real* Hs = w;             w += NZ * NXP;      // H rows (broadcast source)
     real* Xs = w;             w += NZ * NXP;      // rows of Y / X as they are finalised
+    real* HPs = w;            w += NZ * NXP;      // rows of H P (P H^T is read from it by columns)
     real* Ls = w;             w += NZ * NZP;      // Cholesky factor (column reads in the backward solve)
     real* vin = w;            w += NZP;           // innov, then R^-1 innov
     real* vz = w;             w += NZP;
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
 #pragma unroll
             for (int k = 0; k < NX; ++k) HPr[k] = fma(Hr[t], row[k], HPr[k]);
         }
+        if (rz) st_row<NXP>(HPs + lane * NXP, HPr);
         real Sr[NZ];
 #pragma unroll
         for (int c = 0; c < NZ; ++c) {
@@ -270,15 +272,11 @@ __global__ void __launch_bounds__(32 * kLedhFastWarps, sizeof(real) == 4 ? SMC_L
         if (rz) st_row<NXP>(Xs + lane * NXP, Yr);
         __syncwarp();                                           // Xs = S^-1 H, complete
         // ---- 5. rows of P H^T and A = -1/2 P H^T S^-1 H (:158-159) -------------------------------------
+        // (P H^T)[r][s] = (H P)[s][r] bit for bit (P is symmetrised by the host, same summation order):
+        // one conflict-free column read per entry instead of a second nx-long dot product
         real PHtr[NZ];
 #pragma unroll
-        for (int s = 0; s < NZ; ++s) {
-            real acc = 0, row[NXP];
-            ld_row<NXP>(Hs + s * NXP, row);
-#pragma unroll
-            for (int k = 0; k < NX; ++k) acc = fma(Pr[k], row[k], acc);
-            PHtr[s] = acc;
-        }
+        for (int s = 0; s < NZ; ++s) PHtr[s] = HPs[s * NXP + lx];
         real Ar[NX];
 #pragma unroll
         for (int c = 0; c < NX; ++c) Ar[c] = 0;
