@@ -39,24 +39,36 @@ __device__ __forceinline__ void l96_rhs_reg(const real (&x)[NX], real F, real (&
         k[i] = l96_term(x[(i + 1) % NX], x[(i + NX - 2) % NX], x[(i + NX - 1) % NX], x[i], F);
 }
 
-// one RK4 step, x <- x + dt/6 (k1 + 2 k2 + 2 k3 + k4)   (rk4_step :78-83, same association)
+// one RK4 step, x <- x + dt/6 (k1 + 2 k2 + 2 k3 + k4)   (rk4_step :78-83, same association).
+// Stages 2 and 3 update the stage state IN PLACE while the stencil walks over it (the two trailing old
+// values ride in scalars, the old first entry is kept for the wrap-around), so only x, the stage state
+// and the k-sum are live: 3 NX registers instead of 4 NX (NX = 40: 128 registers, 4 CTAs per SM; measured
+// time-neutral against 168 registers / 3 CTAs -- the kernel sits on the fp32 pipe, 55 % of its issue rate).
+// Every element sees exactly the operations of the array form, in the same order.
+template <typename real, int NX, int STAGE>
+__device__ __forceinline__ void l96_stage(real (&x)[NX], real (&xt)[NX], real (&acc)[NX], real F, real c) {
+    const real (&src)[NX] = (STAGE == 1) ? x : xt;
+    const real old0 = src[0];
+    real d2 = src[NX - 2], d1 = src[NX - 1];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const real cur = src[i];
+        const real nxt = (i + 1 < NX) ? src[(i + 1) % NX] : old0;
+        const real k = l96_term(nxt, d2, d1, cur, F);
+        if (STAGE == 1) { acc[i] = k; xt[i] = axpy_nc(c, k, x[i]); }
+        else if (STAGE < 4) { acc[i] = axpy_nc(real(2), k, acc[i]); xt[i] = axpy_nc(c, k, x[i]); }
+        else x[i] = axpy_nc(c, acc[i] + k, x[i]);
+        d2 = d1; d1 = cur;
+    }
+}
 template <typename real, int NX>
 __device__ __forceinline__ void l96_rk4(real (&x)[NX], real F, real dt) {
-    real k[NX], xt[NX], acc[NX];
+    real xt[NX], acc[NX];
     const real hdt = real(0.5) * dt;
-    l96_rhs_reg<real, NX>(x, F, k);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xt[i] = axpy_nc(hdt, k[i], x[i]); }
-    l96_rhs_reg<real, NX>(xt, F, k);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) { acc[i] = axpy_nc(real(2), k[i], acc[i]); xt[i] = axpy_nc(hdt, k[i], x[i]); }
-    l96_rhs_reg<real, NX>(xt, F, k);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) { acc[i] = axpy_nc(real(2), k[i], acc[i]); xt[i] = axpy_nc(dt, k[i], x[i]); }
-    l96_rhs_reg<real, NX>(xt, F, k);
-    const real dt6 = dt / real(6);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = axpy_nc(dt6, acc[i] + k[i], x[i]);
+    l96_stage<real, NX, 1>(x, xt, acc, F, hdt);
+    l96_stage<real, NX, 2>(x, xt, acc, F, hdt);
+    l96_stage<real, NX, 3>(x, xt, acc, F, dt);
+    l96_stage<real, NX, 4>(x, xt, acc, F, dt / real(6));
 }
 
 // the standard normal that draw_normals() hands to particle `gidx`, dimension d (same Philox block,
@@ -84,8 +96,11 @@ __device__ inline double normal_one(const PhiloxKeys& keys, uint64_t gidx, uint3
     return z2[j & 1];
 }
 
+#ifndef SMC_L96_MINB
+#define SMC_L96_MINB 4      // fp32: CTAs per SM the register allocation is held to (3 NX live registers per thread)
+#endif
 template <typename real, int NX>
-__global__ void __launch_bounds__(kL96Threads) k1_lorenz96(K1Args<real> a, L96Params<real> p) {
+__global__ void __launch_bounds__(kL96Threads, sizeof(real) == 4 ? SMC_L96_MINB : 1) k1_lorenz96(K1Args<real> a, L96Params<real> p) {
     constexpr int kW = kL96Threads / 32;
     __shared__ real s_z[kL96MaxNx];
     __shared__ real s_max[kW];
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(kL96Threads) k1_lorenz96(K1Args<real> a, L96Pa
 constexpr int kSyrkTile = 128;     // particles staged per iteration
 
 template <typename real, int BS>
-__global__ void __launch_bounds__(256) k_moments_syrk(const Ctrl* ctrl, const real* x0, const real* x1, const real* logw,
+__global__ void __launch_bounds__(256, BS <= 5 ? 2 : 1) k_moments_syrk(const Ctrl* ctrl, const real* x0, const real* x1, const real* logw,
                                                        int64_t n, int64_t ld, int nx, int post_flip, double* parts) {
     constexpr int NP = 8 * BS;            // padded state dimension
     constexpr int LDS = NP + 1;           // row stride (odd: conflict-free column walks)
@@ -189,6 +204,8 @@ __global__ void __launch_bounds__(256) k_moments_syrk(const Ctrl* ctrl, const re
     const bool weighted = !ctrl->do_resample;
     const double log_norm = ctrl->log_norm;
     const int tid = threadIdx.x, grp = tid >> 6, ti = (tid >> 3) & 7, tj = tid & 7;
+    __shared__ real s_shift[NP];
+    if (tid < NP) s_shift[tid] = (real)(tid < kMaxNx ? ctrl->shift[tid] : 0.0);
     double acc[BS][BS], accm[BS], accw = 0;
 #pragma unroll
     for (int a = 0; a < BS; ++a) {
@@ -205,11 +222,27 @@ __global__ void __launch_bounds__(256) k_moments_syrk(const Ctrl* ctrl, const re
             real w = 0;
             if (pl < cnt) w = weighted ? (real)exp((double)logw[base + pl] - log_norm) : real(1);
             if (tid < kSyrkTile) ws[pl] = w;
-            for (int d = tid >> 7; d < NP; d += 2) {
-                real y = 0;
-                if (pl < cnt && d < nx) y = x[(int64_t)d * ld + base + pl] - (real)(d < kMaxNx ? ctrl->shift[d] : 0.0);
-                ys[pl * LDS + d] = y;
-                yw[pl * LDS + d] = w * y;
+            // the thread's loads are issued in batches before the first is consumed (the tile is not
+            // double-buffered, so the staging phase has to cover the HBM latency by itself: with one
+            // load in flight per thread this phase was 85 % of the kernel)
+            constexpr int ND = NP / 2, NB = ND % 10 == 0 ? 10 : 8;
+            const bool live = pl < cnt;
+            const int d0 = tid >> 7;
+#pragma unroll
+            for (int q0 = 0; q0 < ND; q0 += NB) {
+                real v[NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int d = d0 + 2 * (q0 + q);
+                    v[q] = (live && d < nx) ? __ldg(x + (int64_t)d * ld + base + pl) : real(0);
+                }
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    const int d = d0 + 2 * (q0 + q);
+                    const real y = (live && d < nx) ? v[q] - s_shift[d] : real(0);
+                    ys[pl * LDS + d] = y;
+                    yw[pl * LDS + d] = w * y;
+                }
             }
         }
         __syncthreads();
