@@ -303,26 +303,31 @@ __global__ void __launch_bounds__(256, BS <= 5 ? 2 : 1) k_moments_syrk(const Ctr
     }
 }
 
-// combine the per-CTA records (fixed order) into the stats row: mean, covariance
+// combine the per-CTA records (fixed order) into the stats row: mean, covariance.  Each CTA owns a slice of
+// the covariance entries and re-derives the weight total and the mean sums it needs (same order everywhere).
 __global__ void __launch_bounds__(256) k_moments_syrk_finish(const Ctrl* ctrl, const double* parts, int n_parts, int nx,
                                                               double* stats) {
     extern __shared__ __align__(16) unsigned char syrk_smem[];
-    double* tot = reinterpret_cast<double*>(syrk_smem);     // 1 + nx + nx * nx
-    const int rec = 1 + nx + nx * nx;
-    for (int e = threadIdx.x; e < rec; e += 256) {
+    double* tot = reinterpret_cast<double*>(syrk_smem);     // [1 + nx] head, then this CTA's second moments
+    const int rec = 1 + nx + nx * nx, head = 1 + nx;
+    const int per = (nx * nx + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int e0 = (int)blockIdx.x * per, e1 = min(nx * nx, e0 + per);
+    for (int e = threadIdx.x; e < head + (e1 - e0); e += 256) {
+        const int src = e < head ? e : e0 + e;               // head + e0 + (e - head)
         double s = 0;
-        for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * rec + e];
+        for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * rec + src];
         tot[e] = s;
     }
     __syncthreads();
     double* mean = stats + SMC_STATS_HEADER;
     double* cov = mean + nx;
     const double W = tot[0];
-    for (int e = threadIdx.x; e < nx * nx; e += 256) {
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
         const int a = e / nx, b = e % nx;
-        cov[e] = tot[1 + nx + e] / W - (tot[1 + a] / W) * (tot[1 + b] / W);
+        cov[e] = tot[head + e - e0] / W - (tot[1 + a] / W) * (tot[1 + b] / W);
     }
-    for (int a = threadIdx.x; a < nx; a += 256) mean[a] = (a < kMaxNx ? ctrl->shift[a] : 0.0) + tot[1 + a] / W;
+    if (blockIdx.x == 0)
+        for (int a = threadIdx.x; a < nx; a += 256) mean[a] = (a < kMaxNx ? ctrl->shift[a] : 0.0) + tot[1 + a] / W;
 }
 
 // ==============================================================================================

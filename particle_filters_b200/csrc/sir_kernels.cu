@@ -2383,7 +2383,7 @@ int launch_syrk_t(const Launch& l, double* stats_row_dev) {
                                               (const real*)d->logw_dev, d->n, d->ld, d->nx, 0, l.big_parts());
     SMC_CHECK_CUDA(cudaGetLastError());
     const size_t fsm = sizeof(double) * (1 + d->nx + (size_t)d->nx * d->nx);
-    k_moments_syrk_finish<<<1, 256, fsm, l.st>>>(l.ctrl(), l.big_parts(), (int)grid, d->nx, stats_row_dev);
+    k_moments_syrk_finish<<<d->nx > 8 ? 16 : 1, 256, fsm, l.st>>>(l.ctrl(), l.big_parts(), (int)grid, d->nx, stats_row_dev);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
