@@ -1,0 +1,600 @@
+// K5: the fused step of the run() pipeline -- "resample step t-1, propagate + weigh step t" in ONE launch,
+// 16 B per particle-update (R logw, R x, W x, W logw), for filters that resample every step (bootstrap
+// filters; fp32, one shard).  Included by sir_kernels.cu (namespace smc).
+//
+// Reference semantics: models/particle_filter.py:146-171 (systematic resampling), :209-210 (gather, uniform
+// weights), :266-268 (post-resample moments) of step t-1, then :223-237 (predict) and :253-263 (log-weights,
+// normaliser, ESS) of step t.
+//
+// Per 4096-particle tile (four barriers):
+//   B  the tile's log-weights (cp.async, issued one tile ahead) are quantised to fixed point, a = rni(p),
+//      p = 2^(lw log2e + kshift); thread / warp / CTA scan of the exact 64-bit sums
+//   C  the thread's first and last output boundary from the exact CDF (128-bit products with rho, RhoMap)
+//   D  EXPANSION: the thread that owns an item stores the item's PAYLOAD once per offspring into a linear
+//      output window in shared memory (boundaries inside the thread from the fp32 sums of p) -- no markers,
+//      no back-probing, no gather: the window is the resampled tile
+//   E  every thread takes quads of four consecutive outputs (one LDS.128 per dimension, laid out on global
+//      quads), accumulates the post-resample moments of step t-1, draws the quad's Philox block of step t,
+//      runs the model functor and stores x and log-weights of step t with 128-bit stores.
+//   Skewed tiles (a thread with more than 64 outputs, or more outputs than the window holds) take the
+//   marker + max-scan route of k3_resample and run the functor over the written particles in place.
+//
+// No range pre-pass: a bootstrap step's log-weights are bounded a priori (lw <= -log N, the Gaussian
+// constant being omitted as in the reference), so phase E quantises the weights it writes against that
+// bound -- with the very instructions phase B of the NEXT launch will use -- and adds them, exactly, into the
+// per-range totals the next launch's CTAs take their CDF prefixes from (64-bit integer atomics: the result
+// does not depend on the order).  The last CTA decides (finalize_body) whether the bound left the weights
+// enough resolution; if not -- an observation that costs the whole cloud more than ~11 nats -- it says so in
+// the control block and the (otherwise empty) pre-pass launch that follows re-quantises against the
+// normaliser.
+#pragma once
+
+namespace smc {
+
+// Resident CTAs per SM: shared memory = (1 + NX) tiles + NX windows (51 KB at NX = 1)
+#ifndef SMC_K5_OCC
+#define SMC_K5_OCC 4
+#endif
+template <int NX> struct K5Occ { static constexpr int value = NX <= 1 ? SMC_K5_OCC : 2; };
+constexpr int kK5Tile = 4096;
+constexpr int kK5Window = 256 * 18;          // output slots per tile handled by the expansion route
+constexpr int kK5WinStride = kK5Window + 8;  // + the quad offset of the first output; a multiple of 4
+template <int NX> constexpr size_t k5_smem_bytes() {
+    return sizeof(float) * ((size_t)kK5Tile * (1 + NX) + (size_t)kK5WinStride * NX);
+}
+
+template <bool B> struct K5Flag { static constexpr bool value = B; };
+
+struct K5Args {
+    Ctrl* ctrl;
+    const float* lw_in;        // log-weights of step t-1
+    float* lw_out;             // log-weights of step t (a second array: other CTAs still read step t-1's)
+    const float* x0;
+    const float* x1;
+    float* dst0;               // destination when ctrl->cur == 1 (buffer 0)
+    float* dst1;
+    unsigned long long* rsum;  // two buffers of kRsumStride range totals (ctrl->rsum_sel: the one to read)
+    double* mom_parts;         // per-CTA post-resample moment records of step t-1 (nullable)
+    double* parts;             // per-CTA (max, sum e, sum e^2) records of step t
+    const double* z;           // observation of step t (device)
+    PhiloxKeys keys;
+    uint32_t t;
+    int64_t n, ld, n_tiles;
+    int32_t n_ranges, ranges_per_cta;
+    float kshift_bound;        // quantisation shift of the a-priori bound (K2Args::kshift_bound)
+    unsigned int* ticket;
+    FinishArgs fin;            // finish of step t-1
+    K2Args fin2;               // finalize of step t
+};
+
+template <int NX, class Model>
+__global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K5Args a, Model fm) {
+    static_assert(Model::NX == NX, "functor / payload mismatch");
+    constexpr int THREADS = 256, WARPS = 8, IPT = 16, UPT = 4, TILE = kK5Tile;
+    constexpr int W = kK5Window, WIN = kK5WinStride, CH = IPT + 2;
+    constexpr uint32_t MAXD = 4 * IPT;
+    constexpr int NZ = Model::NZ;
+    constexpr int NM = NX + NX * (NX + 1) / 2;
+    static_assert(W == THREADS * CH && WIN % 4 == 0, "window geometry");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* lw_s = reinterpret_cast<float4*>(smem_raw);                                   // TILE floats, units swizzled
+    float* x_s = reinterpret_cast<float*>(smem_raw + sizeof(float) * TILE);               // NX x TILE, same swizzle
+    float* win = reinterpret_cast<float*>(smem_raw + sizeof(float) * TILE * (1 + NX));    // NX x WIN
+    unsigned short* ids = reinterpret_cast<unsigned short*>(win);                         // skewed route only (aliases win)
+    __shared__ unsigned long long s_warp_tot[WARPS];
+    __shared__ unsigned long long s_warp_all[WARPS];
+    __shared__ uint32_t s_E[2];
+    __shared__ int s_wmax[WARPS];
+    __shared__ double s_mom[WARPS][16];
+    __shared__ double s_m[16];
+    __shared__ int s_last;
+
+    Ctrl* ctrl = a.ctrl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
+    pdl_trigger();
+    if (!ctrl->do_resample) {
+        // (only a filter whose weights have all vanished gets here) nothing to resample: moment-shift refresh
+        if (blockIdx.x == 0 && tid == 0 && a.fin.stats && !a.fin.no_moments)
+            for (int d = 0; d < a.fin.nx && d < kMaxNx; ++d) ctrl->shift[d] = a.fin.stats[SMC_STATS_HEADER + d];
+        return;
+    }
+    const int cur = ctrl->cur;
+    const float* xsrc = cur ? a.x1 : a.x0;
+    float* xdst = cur ? a.dst0 : a.dst1;
+    const int sel = ctrl->rsum_sel;
+    const unsigned long long* rin = a.rsum + (size_t)sel * kRsumStride;
+    unsigned long long* rout = a.rsum + (size_t)(sel ^ 1) * kRsumStride;
+    const float kshift_in = ctrl->kshift;
+    const uint32_t Nn = (uint32_t)a.n;
+
+    const int64_t t_begin = k3_range_begin(blockIdx.x, a.n_tiles, gridDim.x);
+    const int64_t t_end = k3_range_begin(blockIdx.x + 1, a.n_tiles, gridDim.x);
+    auto swz = [](int f) -> int { return f ^ ((f >> 3) & (UPT - 1)); };
+
+    // log-weights and particles of one tile -> shared memory (cp.async; a guarded copy of the ragged last tile)
+    auto fetch = [&](int64_t tile) {
+        const int64_t tb = tile * TILE;
+        if (tb + TILE <= a.n) {
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * THREADS + tid, fs = swz(f);
+                const unsigned dl = (unsigned)__cvta_generic_to_shared(&lw_s[fs]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dl), "l"(a.lw_in + tb + (int64_t)f * 4) : "memory");
+#pragma unroll
+                for (int d = 0; d < NX; ++d) {
+                    const unsigned dx = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + fs * 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dx),
+                                 "l"(xsrc + d * a.ld + tb + (int64_t)f * 4) : "memory");
+                }
+            }
+        } else {
+            const int n_in = (int)(a.n - tb);
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * THREADS + tid, fs = swz(f);
+                float tmp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (f * 4 < n_in) {
+                    load4<float>(a.lw_in + tb + f * 4, tmp);              // rows are padded to a multiple of 4
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (f * 4 + j >= n_in) tmp[j] = -INFINITY;
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) {
+                        const unsigned dx = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + fs * 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dx),
+                                     "l"(xsrc + d * a.ld + tb + (int64_t)f * 4) : "memory");
+                    }
+                }
+                lw_s[fs] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (t_begin < t_end) fetch(t_begin);
+
+    // exclusive CDF prefix of this CTA's first tile and the CDF total, from the range totals
+    unsigned long long prefix, cdf_total;
+    {
+        unsigned long long part = 0, all = 0;
+        const int mine = (int)blockIdx.x * a.ranges_per_cta;
+        for (int i = tid; i < a.n_ranges; i += THREADS) {
+            const unsigned long long v = __ldcg(rin + i);
+            if (i < mine) part += v;
+            all += v;
+        }
+        part = warp_sum(part);
+        all = warp_sum(all);
+        if (lane == 0) { s_warp_tot[warp] = part; s_warp_all[warp] = all; }
+        __syncthreads();
+        prefix = 0; cdf_total = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { prefix += s_warp_tot[w]; cdf_total += s_warp_all[w]; }
+        __syncthreads();
+    }
+    const RhoMap rm = make_rho(cdf_total, a.n, 0xffffffffull - ctrl->uq);
+
+    float shift[NX];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) shift[d] = (float)ctrl->shift[d];
+    double macc_d[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) macc_d[k] = 0.0;
+
+    // ---- step t: observation, online (max, sum e, sum e^2) of its log-weights, range totals of its CDF ----
+    float fz[NZ];
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) fz[k] = (float)a.z[k];
+    float f_tm = -INFINITY, f_acc0 = 0.f, f_acc1 = 0.f;
+    const float f_lw_uniform = (float)(-log((double)a.n));
+    // range cursor: the pre-pass range (k3_range_begin over n_ranges) that holds the thread's current quad
+    const uint32_t cR = (uint32_t)a.n_ranges, cTd = (uint32_t)(a.n_tiles / a.n_ranges), cTm = (uint32_t)(a.n_tiles % a.n_ranges);
+    uint32_t cur_r = 0xffffffffu, cur_bnd = 0u, cur_rem = 0u;
+    unsigned long long cur_acc = 0ull;
+    auto cursor_slow = [&](const uint32_t gi0) {
+        if (cur_r == 0xffffffffu) {                                  // first quad of this thread: locate its range
+            const unsigned long long tile = gi0 >> 12;
+            const unsigned long long r = ((tile + 1ull) * cR - 1ull) / (unsigned long long)a.n_tiles;
+            const unsigned long long base = r * (unsigned long long)a.n_tiles;
+            const uint32_t beg = (uint32_t)(base / cR), rem = (uint32_t)(base % cR);
+            const uint32_t s = rem + cTm, c = s >= cR ? 1u : 0u;
+            cur_r = (uint32_t)r; cur_rem = s - (c ? cR : 0u); cur_bnd = (beg + cTd + c) << 12;
+        } else {
+            do {
+                if (cur_acc) atomicAdd(rout + cur_r, cur_acc);
+                cur_acc = 0ull;
+                ++cur_r;
+                const uint32_t s = cur_rem + cTm, c = s >= cR ? 1u : 0u;
+                cur_rem = s - (c ? cR : 0u); cur_bnd += (cTd + c) << 12;
+            } while (gi0 >= cur_bnd);
+        }
+    };
+    // one quad of resampled particles (global indices gi0 .. gi0 + 3, gi0 % 4 == 0; `mask` = the lanes that
+    // belong to this tile): exactly k1_chunk's arithmetic on exactly its Philox blocks, so the particles are
+    // bit-identical to the three-launch step's
+    auto process_quad = [&](auto full_tag, float (&xt)[NX][4], const uint32_t gi0, const unsigned mask) {
+        constexpr bool FULL = decltype(full_tag)::value;           // all four lanes belong to this tile
+        if (gi0 >= cur_bnd) cursor_slow(gi0);
+        float nrm[NX][4];
+        Draw<NX>::run(a.keys, (uint64_t)(gi0 >> 2), a.t, nrm);
+        float lwq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float xv[NX], nv[NX];
+#pragma unroll
+            for (int d = 0; d < NX; ++d) { xv[d] = xt[d][j]; nv[d] = nrm[d][j]; }
+            fm.propagate(xv, nv);
+#pragma unroll
+            for (int d = 0; d < NX; ++d) xt[d][j] = xv[d];
+            float v = f_lw_uniform + fm.loglik(xv, fz);
+            v = fmaxf(v, -INFINITY);                                 // NaN -> -inf (zero weight)
+            lwq[j] = (FULL || ((mask >> j) & 1u)) ? v : -INFINITY;
+        }
+        if (FULL) {
+#pragma unroll
+            for (int d = 0; d < NX; ++d) store4<float>(xdst + d * a.ld + gi0, xt[d]);
+            store4<float>(a.lw_out + gi0, lwq);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((mask >> j) & 1u) {
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xdst[d * a.ld + gi0 + j] = xt[d][j];
+                    a.lw_out[gi0 + j] = lwq[j];
+                }
+        }
+        const float cmax = fmaxf(fmaxf(lwq[0], lwq[1]), fmaxf(lwq[2], lwq[3]));
+        if (cmax > f_tm) {
+            const float sc = fast_exp(f_tm - cmax);                  // f_tm = -inf -> 0
+            f_acc0 *= sc; f_acc1 *= sc * sc; f_tm = cmax;
+        }
+        if (f_tm != -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float e = fast_exp(lwq[j] - f_tm);             // masked lanes: exp(-inf) = 0
+                f_acc0 += e; f_acc1 = fmaf(e, e, f_acc1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur_acc += quant_a(quant_p(lwq[j], a.kshift_bound));   // masked lanes: 0
+    };
+    using FullQuad = K5Flag<true>;
+    using PartQuad = K5Flag<false>;
+
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+        const int64_t tile_base = tile * TILE;
+        const unsigned long long tile_prefix = prefix;
+
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();   // S1: lw_s, x_s complete; every thread has left the previous tile's phase E (window free)
+
+        // ---- phase B: fixed-point weights, thread / warp / CTA scan ------------------------------------
+        float p[IPT];
+        unsigned long long run = 0;
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+            const float4 u = lw_s[swz(UPT * tid + k)];
+            p[4 * k + 0] = quant_p(u.x, kshift_in); p[4 * k + 1] = quant_p(u.y, kshift_in);
+            p[4 * k + 2] = quant_p(u.z, kshift_in); p[4 * k + 3] = quant_p(u.w, kshift_in);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) run += quant_a(p[4 * k + j]);
+        }
+        unsigned long long incl_w = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl_w, o);
+            if (lane >= o) incl_w += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl_w;
+        __syncthreads();   // S2
+        unsigned long long warp_excl = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const unsigned long long t = s_warp_tot[w];
+            if (w < warp) warp_excl += t;
+            tile_total += t;
+        }
+        prefix = tile_prefix + tile_total;
+
+        // ---- phase C: the thread's exact first / last boundary ---------------------------------------
+        const unsigned long long base_raw = tile_prefix + warp_excl + (incl_w - run);
+        const unsigned long long Ps = map_pos(base_raw, rm), Pe = map_pos(base_raw + run, rm);
+        uint32_t e_start = umin((uint32_t)(Ps >> 32), Nn), e_end = umin((uint32_t)(Pe >> 32), Nn);
+        int klast = IPT;               // first local item that owns the tail: cumsum[-1] = 1 (particle_filter.py:163)
+        if (tile_base + TILE >= a.n) { // the last tile
+            const int64_t j0 = tile_base + (int64_t)tid * IPT;
+            if (j0 + IPT >= a.n) {
+                e_end = Nn;
+                klast = j0 >= a.n - 1 ? 0 : (int)(a.n - 1 - j0);
+                if (j0 >= a.n) e_start = Nn;   // a thread that holds padding only starts where the last particle's range ends
+            }
+        }
+        if (tid == 0) s_E[0] = e_start;
+        if (tid == THREADS - 1) s_E[1] = e_end;
+        const int heavy = __syncthreads_or(e_end - e_start > MAXD);   // S3
+        const uint32_t E0 = s_E[0], E1 = s_E[1];
+        const bool sane = E0 <= E1 && E1 <= Nn;
+        const uint32_t count = sane ? E1 - E0 : 0u;
+        const uint32_t s0 = E0 & 3u;                   // the window is laid out on global quads
+        const bool direct = !heavy && count + s0 <= (uint32_t)W;
+
+        float macc[NM];
+#pragma unroll
+        for (int k = 0; k < NM; ++k) macc[k] = 0.f;
+        auto add_moments = [&](const float (&xv)[NX]) {
+            float xc[NX];
+            int k = 0;
+#pragma unroll
+            for (int d = 0; d < NX; ++d) { xc[d] = xv[d] - shift[d]; macc[k] += xc[d]; ++k; }
+#pragma unroll
+            for (int d = 0; d < NX; ++d)
+#pragma unroll
+                for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fmaf(xc[d], xc[d2], macc[k]); ++k; }
+        };
+
+        if (direct) {
+            // ---- phase D: expansion -- one payload store per offspring ------------------------------
+            if (count > 0u) {
+                uint32_t e[IPT];
+                f32_boundaries<IPT>(p, Ps, e_end, rm.rho_f, e);
+                if (klast < IPT) {
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) if (k >= klast) e[k] = Nn;
+                }
+                // byte address of output index 0 in the window (boundaries are monotone and lie in [E0, E1], so
+                // every store below falls into [s0, s0 + count))
+                const uint32_t wb = (uint32_t)__cvta_generic_to_shared(win) + 4u * s0 - 4u * E0;
+                uint32_t a0 = wb + 4u * e_start, most = 0u;
+#pragma unroll
+                for (int k4 = 0; k4 < UPT; ++k4) {
+                    float xk[NX][4];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) {
+                        const float4 u = reinterpret_cast<const float4*>(x_s + d * TILE)[swz(UPT * tid + k4)];
+                        xk[d][0] = u.x; xk[d][1] = u.y; xk[d][2] = u.z; xk[d][3] = u.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t a1 = wb + 4u * e[4 * k4 + j];
+                        const uint32_t nb = a1 - a0;                  // 4 x offspring count of this item
+                        most = umax(most, nb);
+#pragma unroll
+                        for (int d = 0; d < NX; ++d)                   // first and second offspring: predicated stores
+                            asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                                         "setp.ge.u32 p1, %0, 4;\n\tsetp.ge.u32 p2, %0, 8;\n\t"
+                                         "@p1 st.shared.f32 [%1], %2;\n\t@p2 st.shared.f32 [%1+4], %2;\n\t}"
+                                         :: "r"(nb), "r"(a0 + (uint32_t)(d * WIN * 4)), "f"(xk[d][j]) : "memory");
+                        a0 = a1;
+                    }
+                }
+                if (most >= 12u) {                                     // some item has three or more offspring (rare)
+                    uint32_t b0 = wb + 4u * e_start;
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        const uint32_t b1 = wb + 4u * e[k];
+                        if (b1 - b0 >= 12u) {
+#pragma unroll
+                            for (int d = 0; d < NX; ++d) {
+                                const int li = IPT * tid + k;
+                                const float xv = x_s[d * TILE + swz(li >> 2) * 4 + (li & 3)];
+#pragma unroll 1
+                                for (uint32_t bb = b0 + 8u; bb < b1; bb += 4u)
+                                    asm volatile("st.shared.f32 [%0], %1;" :: "r"(bb + (uint32_t)(d * WIN * 4)), "f"(xv) : "memory");
+                            }
+                        }
+                        b0 = b1;
+                    }
+                }
+            }
+            __syncthreads();   // S4: the window holds the resampled tile; lw_s / x_s are dead
+            if (tile + 1 < t_end) fetch(tile + 1);             // the next tile travels during phase E
+
+            // ---- phase E: quads of outputs -> moments of step t-1, functor of step t, stores ------------
+            const uint32_t wend = s0 + count;                  // valid window positions [s0, wend)
+            const uint32_t nquad = (wend + 3u) >> 2;
+            const uint32_t gw0 = E0 - s0;                      // global index of window position 0
+            const uint32_t win_sa = (uint32_t)__cvta_generic_to_shared(win);
+            for (uint32_t q = tid; q < nquad; q += THREADS) {
+                const uint32_t w0 = 4u * q;
+                float xt[NX][4];
+#pragma unroll
+                for (int d = 0; d < NX; ++d)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(xt[d][0]), "=f"(xt[d][1]), "=f"(xt[d][2]), "=f"(xt[d][3])
+                                 : "r"(win_sa + (uint32_t)(d * WIN * 4) + 16u * q) : "memory");
+                if (w0 >= s0 && w0 + 4u <= wend) {
+                    // post-resample moments of step t-1 (the gathered, not yet propagated, particles)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float xv[NX];
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
+                        add_moments(xv);
+                    }
+                    process_quad(FullQuad(), xt, gw0 + w0, 15u);
+                } else {                                       // first / last quad of the tile: partial
+                    unsigned mask = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool valid = w0 + j >= s0 && w0 + j < wend;
+                        if (valid) mask |= 1u << j;
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xt[d][j] = valid ? xt[d][j] : 0.f;
+                        if (valid) {
+                            float xv[NX];
+#pragma unroll
+                            for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
+                            add_moments(xv);
+                        }
+                    }
+                    process_quad(PartQuad(), xt, gw0 + w0, mask);
+                }
+            }
+        } else {
+            // ---- skewed tile: exact boundaries, head markers + max-scan fill, window by window ------------
+            uint32_t e[IPT];
+            exact_boundaries<IPT>(p, base_raw, rm, e);
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) e[k] = umin(k >= klast ? Nn : e[k], e_end);
+            auto x_of = [&](const int d, const int li) -> float {      // item li of the (swizzled) particle tile
+                return x_s[d * TILE + swz(li >> 2) * 4 + (li & 3)];
+            };
+            for (uint32_t wbase = 0; wbase < count; wbase += W) {
+                {
+                    uint4* o4 = reinterpret_cast<uint4*>(ids);
+                    for (int i = tid; i < W * 2 / 16; i += THREADS) o4[i] = make_uint4(0, 0, 0, 0);
+                }
+                __syncthreads();
+                {   // head markers (local index + 1) at the first output of every item with offspring
+                    uint32_t r0 = umax(e_start, E0) - E0;
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        const uint32_t r1 = umin(umax(e[k], E0) - E0, count);
+                        if (r1 > r0 && r1 > wbase && r0 < wbase + W) {
+                            const uint32_t pos = (r0 > wbase ? r0 : wbase) - wbase;
+                            ids[pos] = (unsigned short)(tid * IPT + k + 1);
+                        }
+                        r0 = r1;
+                    }
+                }
+                __syncthreads();
+                {   // forward fill = inclusive max-scan (markers increase with position)
+                    uint32_t* o32 = reinterpret_cast<uint32_t*>(ids) + tid * (CH / 2);
+                    uint32_t wv[CH / 2];
+                    int tmax = 0;
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) {
+                        wv[k] = o32[k];
+                        const int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                        tmax = max(tmax, max(lo, hi));
+                    }
+                    int inc = tmax;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc = max(inc, t);
+                    }
+                    int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+                    if (lane == 0) excl = 0;
+                    if (lane == 31) s_wmax[warp] = inc;
+                    __syncthreads();
+                    int carry = excl;
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) if (w < warp) carry = max(carry, s_wmax[w]);
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) {
+                        int lo = wv[k] & 0xffff, hi = wv[k] >> 16;
+                        lo = max(lo, carry); carry = lo;
+                        hi = max(hi, carry); carry = hi;
+                        o32[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+                    }
+                }
+                __syncthreads();
+                {
+                    const uint32_t rem = count - wbase;
+                    const int cnt = rem < (uint32_t)W ? (int)rem : W;
+                    const uint32_t g0 = E0 + wbase;                          // global index of window slot 0
+                    for (int i = tid; i < cnt; i += THREADS) {
+                        int li1 = (int)ids[i];
+                        if (li1 == 0) li1 = 1;                               // (only on inconsistent input)
+                        float xv[NX];
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) {
+                            xv[d] = x_of(d, li1 - 1);
+                            xdst[d * a.ld + g0 + i] = xv[d];
+                        }
+                        add_moments(xv);
+                    }
+                }
+                __syncthreads();
+            }
+            // the window loop has written the resampled particles of this tile to the destination buffer (block-
+            // visible after the barrier): run the functor over them in place
+            if (count > 0u) {
+                const uint32_t gq0 = E0 & ~3u;
+                const uint32_t nq = ((E1 + 3u) >> 2) - (gq0 >> 2);
+                for (uint32_t q = tid; q < nq; q += THREADS) {
+                    const uint32_t gi0 = gq0 + 4u * q;
+                    unsigned mask = 0;
+                    float xt[NX][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t gi = gi0 + j;
+                        const bool valid = gi >= E0 && gi < E1;
+                        if (valid) mask |= 1u << j;
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xt[d][j] = valid ? xdst[d * a.ld + gi] : 0.f;
+                    }
+                    process_quad(PartQuad(), xt, gi0, mask);
+                }
+            }
+            __syncthreads();
+            if (tile + 1 < t_end) fetch(tile + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < NM; ++k) macc_d[k] += (double)macc[k];
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    if (cur_r != 0xffffffffu && cur_acc) atomicAdd(rout + cur_r, cur_acc);
+
+    {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
+        __shared__ float s_fmax[WARPS];
+        __shared__ double s_fred[WARPS][2];
+        const float wmax = warp_max(f_tm);
+        if (lane == 0) s_fmax[warp] = wmax;
+        __syncthreads();
+        float bmax = s_fmax[0];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) bmax = s_fmax[w] > bmax ? s_fmax[w] : bmax;
+        const float sc = (f_tm == -INFINITY) ? 0.f : fast_exp(f_tm - bmax);
+        const float v0 = warp_sum(f_acc0 * sc), v1 = warp_sum(f_acc1 * sc * sc);
+        if (lane == 0) { s_fred[warp][0] = (double)v0; s_fred[warp][1] = (double)v1; }
+        __syncthreads();
+        if (tid == 0) {
+            double t0 = 0, t1 = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { t0 += s_fred[w][0]; t1 += s_fred[w][1]; }
+            double* out = a.parts + (int64_t)blockIdx.x * 3;
+            out[0] = (double)bmax; out[1] = t0; out[2] = t1;
+        }
+    }
+    // per-CTA post-resample moment partials of step t-1
+    if (a.mom_parts) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+            const double v = warp_sum(macc_d[k]);
+            if (lane == 0) s_mom[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < NM) {
+            double s = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s += s_mom[w][tid];
+            a.mom_parts[(int64_t)blockIdx.x * NM + tid] = s;
+        }
+    }
+    // the last CTA to arrive: finish of step t-1 (moments, buffer flip, shift refresh), hand-over of the
+    // range-total buffers, finalize of step t (normaliser, ESS, decision, u, quantisation reference)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        finish_body(ctrl, a.fin, s_mom, s_m);
+        // every CTA has read the totals of step t-1: clear them for the launch after the next, and make the
+        // buffer this launch has accumulated into the current one
+        for (int i = tid; i < kRsumStride; i += THREADS) a.rsum[(size_t)sel * kRsumStride + i] = 0ull;
+        if (tid == 0) ctrl->rsum_sel = sel ^ 1;
+        __shared__ double s_fout[32];
+        __shared__ double s_ftmp[kWarps];
+        __syncthreads();
+        K2Args f2 = a.fin2;
+        f2.ctrl = ctrl; f2.parts = a.parts; f2.n_parts = (int)gridDim.x;
+        finalize_body(f2, s_fout, s_ftmp);
+        if (tid == 0) *a.ticket = 0u;
+    }
+}
+
+}  // namespace smc

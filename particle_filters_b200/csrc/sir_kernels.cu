@@ -6,6 +6,7 @@
 #include "smc_common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace smc {
@@ -112,6 +113,22 @@ __device__ inline void mailbox_wait(const volatile unsigned long long* flags, in
     __syncthreads();
 }
 
+// Fractional bits Fa of the fp32 mode's fixed-point weights: 2^Fa N must stay below 2^62
+__host__ __device__ inline int fa_bits_for(int64_t n_global) {
+    int lg = 0;
+    while ((1ll << lg) < n_global) ++lg;
+    const int F = 62 - lg;
+    return F > 36 ? 36 : F;          // n_global <= 2^30 -> F >= 32
+}
+constexpr float kLog2eF = 1.4426950408889634f;
+// a-priori bound of a bootstrap step's log-weights (the fp32 value K1 / the fused functor add the
+// log-likelihood to) and the quantisation shift that goes with it
+inline void quant_bound_for(int64_t n_global, double* lw_bound, float* kshift_bound) {
+    const float lw_uniform = (float)(-log((double)n_global));
+    *lw_bound = (double)lw_uniform;
+    *kshift_bound = (float)((double)fa_bits_for(n_global) - (double)lw_uniform * (double)kLog2eF);
+}
+
 struct K2Args {
     Ctrl* ctrl;
     const double* parts;
@@ -122,6 +139,11 @@ struct K2Args {
     double thresh, u_host;
     uint64_t seed;
     uint32_t t;
+    // fp32 CDF (see below): the a-priori bound on the log-weights of a bootstrap step and its quantisation shift,
+    // computed once on the host so that every kernel quantises with the very same constant
+    double lw_bound;
+    float kshift_bound;
+    int32_t producer_rsum;   // the calling kernel accumulated the range totals against the bound
 };
 
 __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp);   // defined with K2
@@ -549,6 +571,24 @@ __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_t
     c->do_resample = do_res;
     c->uniform = 0;
     ctrl_prepare_search(c, a.n_global, a.f32 != 0);
+    if (a.f32) {
+        // fp32 CDF: fixed-point weights a_i = rni(2^Fa exp(lw_i - lw_ref)).  Any reference lw_ref >= max lw_i
+        // that leaves the mean weight enough resolution will do, because the stratified positions are laid
+        // over the ACTUAL total (see RhoMap).  A bootstrap step knows such a reference before it has seen a
+        // single weight -- lw_i = -log N - quad_i / 2 <= -log N -- which is what lets the kernel that WRITES
+        // the log-weights also deliver the range totals of the resampler's CDF (no pre-pass over them).
+        const int Fa = fa_bits_for(a.n_global);
+        const double log_mean = log_norm - a.lw_bound - log((double)a.n_global);   // log of the mean of exp(lw - bound)
+        const bool bound_ok = M <= a.lw_bound && log_mean >= -(double)(Fa - 20) * 0.6931471805599453;
+        if (bound_ok) {
+            c->lw_ref = a.lw_bound;
+            c->kshift = a.kshift_bound;
+            c->rsum_valid = a.producer_rsum ? 1 : 0;
+        } else {                                            // N w_i = exp(lw_i - lw_ref), as in fp64 mode
+            c->kshift = (float)((double)Fa - c->lw_ref * (double)kLog2eF);
+            c->rsum_valid = 0;
+        }
+    }
     if (a.stats) {
         a.stats[0] = log_norm;
         a.stats[1] = ess;
@@ -747,37 +787,42 @@ __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; 
 
 
 // Per-item quantisation of the weights.
-//  fp32 mode: each weight carries 24 significant bits, so it is converted on its own (one F2I);
+//  fp32 mode: every weight is converted on its own, a = rni(p), p = 2^(lw log2e + kshift) (one FFMA, FMNMX,
+//  MUFU.EX2 and F2I); the same three instructions run wherever a log-weight is quantised -- the kernel that
+//  writes it, the range pre-pass, the resampler -- so all of them see the same integers and every sum of
+//  them is exact and order-independent;
 //  fp64 mode (parity): the thread's fp64 running sum is quantised instead, so the round-off of
 //  2^-F index units does not accumulate over a run of tiny weights.
+__device__ __forceinline__ float quant_p(float lw, float kshift) {
+    return ex2_approx(fminf(fmaf(lw, kLog2eF, kshift), 62.5f));       // NaN-free input (see K1)
+}
+__device__ __forceinline__ unsigned long long quant_a(float p) {
+    unsigned long long q;
+    asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
+    return q;
+}
 template <typename real> struct Quant;
 template <> struct Quant<float> {
-    float fscale, kshift, corr;
-    __device__ inline void init(int F, double lw_ref) {
-        fscale = __uint_as_float((127u + (uint32_t)F) << 23);                 // 2^F
-        // N w 2^F = 2^((lw - lw_ref) log2e + F).  Two systematic errors would each move the CDF total by
-        // ~1e-6 N index units (and push that many outputs onto / off the last particles): the fp32
-        // rounding of the shift and of log2(e).  The shift is therefore formed with the fp32 constant the
-        // FMA really multiplies by (so its error only scales log(N w) = O(1)), and its fp32 rounding
-        // remainder is applied as a factor 2^(k - fl(k)) after the exponential.
-        const double k = (double)F - lw_ref * (double)1.4426950408889634f;
-        kshift = (float)k;
-        corr = (float)exp2(k - (double)kshift);
+    float fscale, kshift;
+    __device__ inline void init(const Ctrl* c, int64_t n_global, bool) {
+        fscale = __uint_as_float((127u + (uint32_t)fa_bits_for(n_global)) << 23);   // 2^Fa (linear weights)
+        kshift = c->kshift;
     }
+    __device__ inline float p_logw(float lw) const { return quant_p(lw, kshift); }
+    __device__ inline float p_lin(float v) const { return v * fscale; }           // v = N w, clamped to [0, N]
     __device__ inline unsigned long long add(unsigned long long run, float v, double&) const {
-        return run + __float2ull_rn(v * fscale);
+        return run + quant_a(p_lin(v));
     }
-    // log-weight -> fixed point in one FFMA + FMNMX + MUFU.EX2 + F2I (NaN-free input, see K1)
     __device__ inline unsigned long long add_logw(unsigned long long run, float lw, double&) const {
-        const float p = ex2_approx(fminf(fmaf(lw, 1.4426950408889634f, kshift), 62.5f)) * corr;
-        unsigned long long q;
-        asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
-        return run + q;
+        return run + quant_a(p_logw(lw));
     }
 };
 template <> struct Quant<double> {
     double fscale, lw_ref, nmax;
-    __device__ inline void init(int F, double lw_ref_) { fscale = ldexp(1.0, F); lw_ref = lw_ref_; nmax = ldexp(1.0, 62 - F); }
+    __device__ inline void init(const Ctrl* c, int64_t, bool linear_w) {
+        const int F = c->frac_bits;
+        fscale = ldexp(1.0, F); lw_ref = linear_w ? 0.0 : c->lw_ref; nmax = ldexp(1.0, 62 - F);
+    }
     __device__ inline unsigned long long add(unsigned long long, double v, double& runf) const {
         runf += v;
         return __double2ull_rn(runf * fscale);
@@ -788,6 +833,66 @@ template <> struct Quant<double> {
         return add(run, v, runf);
     }
 };
+
+// fp32 CDF: the stratified positions are laid over the ACTUAL fixed-point total A of the weights instead of
+// over a nominal one: the output boundary of a CDF value C (in the weights' own units) is taken at
+// C rho, rho = N 2^32 / A, in 2^-32 index units.  Whatever reference the weights were quantised against,
+// nothing is then left over for, or missing from, the last particles, and neither the round-off of a
+// normaliser nor the order of any floating-point sum can move a boundary: the three-launch step, the
+// fused pipeline and any shard count select the same ancestors.  rho = R 2^-sh with R normalised to 64 bits.
+struct RhoMap {
+    unsigned long long R, bias;    // bias = 2^32 - 1 - floor(u 2^32): e(C) = (floor(C rho) + bias) >> 32
+    int sh;                        // C rho = mulhi64(C << sh, R): the total, shifted, fills 63 bits
+    float rho_f;                   // rho 2^-32: thread-local weight sums (fp32) -> index units
+};
+__device__ inline RhoMap make_rho(unsigned long long total, int64_t n_global, unsigned long long bias) {
+    RhoMap m;
+    m.bias = bias; m.R = 0ull; m.sh = 0; m.rho_f = 0.f;
+    if (total > 0ull && total < (1ull << 63)) {
+        m.sh = __clzll((long long)total) - 1;                                // total << sh in [2^62, 2^63)
+        const double r = (double)n_global / (double)(total << m.sh);         // correctly rounded: same on every CTA
+        m.R = __double2ull_rz(fmin(ldexp(r, 96), 18446744073709549568.0));   // rho 2^(64 - sh) <= N 2^34 <= 2^64
+        m.rho_f = (float)((double)n_global / (double)total);
+    }
+    return m;
+}
+// floor(C rho) + bias, monotone in C (C <= total, so the result stays below N 2^32 + 2^32)
+__device__ __forceinline__ unsigned long long map_pos(unsigned long long C, const RhoMap& m) {
+    return __umul64hi(C << m.sh, m.R) + m.bias;
+}
+// Thread-local boundaries of IPT consecutive items from their fp32 weights p[] (the values the fixed-point
+// weights were rounded from) between the thread's exact first and last boundary: e[k] = e_start +
+// trunc(frac(start) + rho sum_{j<=k} p_j), clamped to e_end; the item that carries the thread's last weight
+// takes e_end (so that an item of zero weight never receives an output).  Used where no thread has more
+// than a few dozen outputs (error < 2^-17 index units); skewed tiles take the exact form below.
+template <int IPT>
+__device__ __forceinline__ void f32_boundaries(const float (&p)[IPT], unsigned long long Ps, uint32_t e_end, float rho_f,
+                                               uint32_t (&e)[IPT]) {
+    const uint32_t e_start = (uint32_t)(Ps >> 32);
+    const float fr = __uint2float_rz((uint32_t)Ps) * 2.3283064365386963e-10f;    // < 1
+    float ftot = 0.f;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) ftot = __fadd_rn(ftot, p[k]);
+    float fk = 0.f;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        fk = __fadd_rn(fk, p[k]);
+        const uint32_t ek = umin(e_start + __float2uint_rz(__fmaf_rn(fk, rho_f, fr)), e_end);
+        e[k] = fk < ftot ? ek : e_end;
+    }
+}
+template <int IPT>
+__device__ __forceinline__ void exact_boundaries(const float (&p)[IPT], unsigned long long base_raw, const RhoMap& rm,
+                                                 uint32_t (&e)[IPT]) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        unsigned long long q;   // (volatile: recomputed here rather than kept live across the hot path)
+        asm volatile("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p[k]));
+        c += q;
+        e[k] = (uint32_t)(map_pos(base_raw + c, rm) >> 32);
+    }
+}
 
 // Fast boundary search in 32-bit arithmetic.  With C' = C + (2^F - 1 - uq):
 //   e(C) = C' >> F           (number of stratified positions below the CDF value C)
@@ -849,9 +954,12 @@ __global__ void __launch_bounds__(K3Geom<real>::THREADS, sizeof(real) == 4 ? SMC
     pdl_wait();
     pdl_trigger();
     if (!force && !ctrl->do_resample) return;
+    // fp32 bootstrap steps: the kernel that wrote the log-weights has already delivered these totals
+    if (!force && sizeof(real) == 4 && !LINEAR_W && ctrl->rsum_valid) return;
+    rtot += (size_t)ctrl->rsum_sel * kRsumStride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Quant<real> quant;
-    quant.init(ctrl->frac_bits, LINEAR_W ? 0.0 : ctrl->lw_ref);
+    quant.init(ctrl, n_global, LINEAR_W);
     const real n_real = (real)n_global;
     const real fill = LINEAR_W ? real(0) : real(-INFINITY);
     const int64_t t0 = k3_range_begin(blockIdx.x, n_tiles, gridDim.x), t1 = k3_range_begin(blockIdx.x + 1, n_tiles, gridDim.x);
@@ -1118,7 +1226,7 @@ k3_resample(K3Args<real> a, FM fm) {
     fs.m32 = (uint32_t)(sp.margin >> fs.sh) + 2u;
     fs.n_global = (uint32_t)a.n_global;
     Quant<real> quant;
-    quant.init(sp.F, LINEAR_W ? 0.0 : ctrl->lw_ref);      // weight N w = exp(lw - (log_norm - log N))
+    quant.init(ctrl, a.n_global, LINEAR_W);
     const real n_real = (real)a.n_global;
     const real fill = LINEAR_W ? real(0) : real(-INFINITY);
 
@@ -1171,8 +1279,9 @@ k3_resample(K3Args<real> a, FM fm) {
         }
         unsigned long long part = 0, all = 0;
         const int n_ranges = (int)gridDim.x * a.ranges_per_cta;
+        const unsigned long long* rtot = a.rtot + (size_t)ctrl->rsum_sel * kRsumStride;
         for (int i = tid; i < n_ranges; i += kK3Threads) {
-            const unsigned long long v = a.rtot[i];
+            const unsigned long long v = __ldcg(rtot + i);
             if (i < (int)blockIdx.x * a.ranges_per_cta) part += v;
             all += v;
         }
@@ -1195,17 +1304,8 @@ k3_resample(K3Args<real> a, FM fm) {
         for (int w = 0; w < kK3Warps; ++w) { prefix += s_warp_tot[w]; cdf_total += s_warp_all[w]; }
         __syncthreads();
     }
-    // fp32 mode: the stratified positions are laid over the ACTUAL fixed-point total T instead of over
-    // N 2^32 (boundaries are taken at C rho, rho = N 2^32 / T = 1 + eps): the fp32 round-off of the
-    // normaliser then moves no boundary -- a relative error delta of the normaliser rescales every
-    // weight and T alike -- so the three-launch step, the fused pipeline and any shard count select the
-    // same ancestors, and nothing is left over for (or missing from) the last particles.
-    long long rho_eps = 0;                                       // round(eps 2^64)
-    if (sizeof(real) == 4 && cdf_total > 0ull) {
-        const double want = (double)a.n_global * 4294967296.0;
-        const double eps = (want - (double)cdf_total) / (double)cdf_total;
-        if (fabs(eps) < 0.25) rho_eps = (long long)(eps * 18446744073709551616.0);
-    }
+    // fp32 mode: the stratified positions are laid over the actual fixed-point total (see RhoMap)
+    const RhoMap rm = make_rho(cdf_total, a.n_global, fs.bias);
 
     real shift[NXF > 0 ? NXF : 1];
 #pragma unroll
@@ -1311,7 +1411,8 @@ k3_resample(K3Args<real> a, FM fm) {
         }
 
         // ---- phase B: fixed-point weights, thread / warp / CTA scan -------------------------------
-        unsigned long long c[IPT];
+        unsigned long long c[IPT];                               // fp64: inclusive fixed-point CDF within the thread
+        float pf[IPT];                                           // fp32: the weights the fixed-point values are rounded from
         unsigned long long run = 0;
         {
             double runf = 0.0;
@@ -1322,13 +1423,20 @@ k3_resample(K3Args<real> a, FM fm) {
                 unit_to_array(lw_s[g ^ ((g >> 3) & (UPT - 1))], tmp);
 #pragma unroll
                 for (int j = 0; j < EPU; ++j) {
-                    if (LINEAR_W) {
-                        real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);   // NaN / negative -> 0, cap at N
-                        run = quant.add(run, v, runf);
+                    if constexpr (sizeof(real) == 4) {
+                        const float pv = LINEAR_W ? quant.p_lin(fminf(fmaxf(tmp[j] * n_real, 0.f), n_real))   // NaN / negative -> 0
+                                                  : quant.p_logw(tmp[j]);
+                        pf[k * EPU + j] = pv;
+                        run += quant_a(pv);
                     } else {
-                        run = quant.add_logw(run, tmp[j], runf);
+                        if (LINEAR_W) {
+                            real v = fmin(fmax(tmp[j] * n_real, real(0)), n_real);   // NaN / negative -> 0, cap at N
+                            run = quant.add(run, v, runf);
+                        } else {
+                            run = quant.add_logw(run, tmp[j], runf);
+                        }
+                        c[k * EPU + j] = run;                    // inclusive within thread
                     }
-                    c[k * EPU + j] = run;                        // inclusive within thread
                 }
             }
         }
@@ -1355,18 +1463,12 @@ k3_resample(K3Args<real> a, FM fm) {
         const unsigned long long base_b = base_raw + fs.bias;                                    // + bias folded in
         uint32_t e_start, e[IPT];
         if constexpr (sizeof(real) == 4) {
-            // F = 32: the count is the high word of the biased CDF value.  The thread's first and last
-            // boundary are taken at the rescaled values C rho (see rho_eps above); the items in between use
-            // the thread-local increments as they are (an error below 2^-7 index units, absorbed by the
-            // thread's last item), clamped so that consecutive threads tile the outputs exactly.
-            const unsigned long long end_raw = base_raw + run;
-            const unsigned long long bs = base_b + (unsigned long long)__mul64hi((long long)base_raw, rho_eps);
-            const unsigned long long be = end_raw + fs.bias + (unsigned long long)__mul64hi((long long)end_raw, rho_eps);
-            e_start = (uint32_t)(bs >> 32);
-            const uint32_t e_end = (uint32_t)(be >> 32);
-#pragma unroll
-            for (int k = 0; k < IPT - 1; ++k) e[k] = umin(umax((uint32_t)((bs + c[k]) >> 32), e_start), e_end);
-            e[IPT - 1] = e_end;
+            // The thread's first and last boundary are exact (64 x 64 -> 128 bit products of the global CDF
+            // values with rho), so consecutive threads, tiles, CTAs and shards tile the outputs exactly; the
+            // items in between follow the thread-local fp32 sums (skewed tiles: exact, after S3).
+            const unsigned long long Ps = map_pos(base_raw, rm), Pe = map_pos(base_raw + run, rm);
+            e_start = (uint32_t)(Ps >> 32);
+            f32_boundaries<IPT>(pf, Ps, (uint32_t)(Pe >> 32), rm.rho_f, e);
         } else
         {
             uint32_t near = 0;
@@ -1403,7 +1505,7 @@ k3_resample(K3Args<real> a, FM fm) {
                 }
             }
         }
-        {   // cumsum[-1] = 1.0 clamp (particle_filter.py:163): the globally last particle owns the tail
+        auto tail_clamps = [&]() {   // cumsum[-1] = 1.0 clamp (particle_filter.py:163): the globally last particle owns the tail
             const int64_t j0 = a.offset + tile_base + (int64_t)tid * IPT;
             if (j0 + IPT >= a.n_global) {
 #pragma unroll
@@ -1419,7 +1521,8 @@ k3_resample(K3Args<real> a, FM fm) {
 #pragma unroll
                 for (int k = 0; k < IPT; ++k) e[k] = e[k] < fs.n_global ? e[k] : fs.n_global;
             }
-        }
+        };
+        tail_clamps();
         // (padding items beyond the shard carry zero weight, hence no outputs of their own)
         if (tid == 0) {
             s_E[0] = e_start;
@@ -1432,6 +1535,12 @@ k3_resample(K3Args<real> a, FM fm) {
         if (NXF > 0) asm volatile("cp.async.wait_all;\n" ::: "memory");
         const int heavy = __syncthreads_or(e[IPT - 1] - e_start > MAXD);   // S3: publishes s_E, x_s and the cleared window;
                                                            //     nobody reads lw_s any more
+        if constexpr (sizeof(real) == 4) {
+            if (heavy) {   // skewed tile: a thread-local fp32 sum no longer resolves single outputs -> exact boundaries
+                exact_boundaries<IPT>(pf, base_raw, rm, e);
+                tail_clamps();
+            }
+        }
         if (tile + 1 < t_end) fetch_lw(tile + 1);          // next tile's log-weights travel during D / E
         const uint32_t E0 = s_E[0], E1 = s_E[1];
         // Memory safety on inconsistent input (weights that do not sum to one can wrap the 64-bit
@@ -1912,6 +2021,7 @@ __global__ void k_reset_ctrl(Ctrl* c, const double* shift, int nx) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         c->log_norm = 0.0; c->ess = 0.0; c->u = 0.0; c->cur = 0; c->uniform = 1; c->do_resample = 0;
         c->frac_bits = 32; c->lw_ref = 0.0; c->uq = 0ull; c->margin = 0ull;
+        c->kshift = 0.f; c->rsum_valid = 0;      // (rsum_sel stays: the buffer it does NOT name is all zero, always)
         for (int d = 0; d < kMaxNx; ++d) c->shift[d] = (shift && d < nx) ? shift[d] : 0.0;
     }
 }
@@ -2043,6 +2153,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_step(const Ctrl* ctrl, cons
 
 }  // namespace smc
 
+#include "fused_step.cuh"
 #include "big_state.cuh"
 
 // ================================================================================================
@@ -2392,30 +2503,84 @@ template <typename real> int launch_syrk(const Launch& l, double* stats_row_dev)
 }
 
 // ---- fused resample(t-1) -> propagate + weigh(t) (run() pipeline of bootstrap filters, fp32) ------------
+// K5 (fused_step.cuh): one launch per step plus the conditional range pre-pass (a no-op unless the last CTA
+// of K5 found the a-priori bound too loose for this step's weights).  SMC_FUSED_LEGACY=1 in the environment
+// selects round 1's pipeline (k3_resample with the functor in its copy-out + an unconditional pre-pass) for
+// A/B measurements.
+inline bool fused_legacy() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SMC_FUSED_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+inline int64_t k5_grid(int nx) { return (int64_t)sm_count() * (nx <= 1 ? SMC_K5_OCC : 2); }
+
 template <class Model>
 int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const double* z_dev, double resample_thresh,
                  uint64_t seed, int64_t t, double* stats_prev_dev, double* stats_row_dev, int phases) {
     const smc_sir_desc* d = l.d;
-    if (!(phases & 1)) return launch_prepass<float>(l, false, logw_out_dev, d->nx, 0, nullptr);
-    FinishArgs f;
-    memset(&f, 0, sizeof(f));
-    f.stats = stats_prev_dev; f.nx = d->nx; f.inline_moments = 1;
-    f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
-    K3Args<float> a;
-    fill_k3_args<float>(l, a, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, !(d->flags & SMC_FLAG_NO_MOMENTS), nullptr, 0, &f,
-                        nullptr);
-    a.fk.lw_out = static_cast<float*>(logw_out_dev);
-    a.fk.z = z_dev;
-    a.fk.keys = philox_expand(seed);
-    a.fk.t = (uint32_t)t;
-    a.fk.parts = l.k1_parts();            // <= 592 records of 3 doubles: fits the K1 partial area
-    memset(&a.fk.fin, 0, sizeof(a.fk.fin));
-    a.fk.fin.stats = stats_row_dev; a.fk.fin.n_global = d->n_global; a.fk.fin.nx = d->nx;
-    a.fk.fin.inline_moments = 0; a.fk.fin.f32 = 1;
-    a.fk.fin.thresh = resample_thresh; a.fk.fin.u_host = -1.0; a.fk.fin.seed = seed; a.fk.fin.t = (uint32_t)t;
-    if (int rc = launch_k3_t<float, Model::NX, false, Model>(l, a, l.L.n_tiles, m)) return rc;
+    const bool legacy = fused_legacy();
+    if (phases & 1) {
+        FinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.stats = stats_prev_dev; f.nx = d->nx; f.inline_moments = 1;
+        f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+        K2Args fin2;
+        memset(&fin2, 0, sizeof(fin2));
+        fin2.stats = stats_row_dev; fin2.n_global = d->n_global; fin2.nx = d->nx;
+        fin2.inline_moments = 0; fin2.f32 = 1;
+        fin2.thresh = resample_thresh; fin2.u_host = -1.0; fin2.seed = seed; fin2.t = (uint32_t)t;
+        quant_bound_for(d->n_global, &fin2.lw_bound, &fin2.kshift_bound);
+        if (legacy) {
+            K3Args<float> a;
+            fill_k3_args<float>(l, a, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, !(d->flags & SMC_FLAG_NO_MOMENTS), nullptr, 0,
+                                &f, nullptr);
+            a.fk.lw_out = static_cast<float*>(logw_out_dev);
+            a.fk.z = z_dev;
+            a.fk.keys = philox_expand(seed);
+            a.fk.t = (uint32_t)t;
+            a.fk.parts = l.k1_parts();            // <= 592 records of 3 doubles: fits the K1 partial area
+            a.fk.fin = fin2;
+            if (int rc = launch_k3_t<float, Model::NX, false, Model>(l, a, l.L.n_tiles, m)) return rc;
+        } else {
+            constexpr int NX = Model::NX;
+            K5Args a;
+            memset(&a, 0, sizeof(a));
+            a.ctrl = l.ctrl();
+            a.lw_in = static_cast<const float*>(d->logw_dev);
+            a.lw_out = static_cast<float*>(logw_out_dev);
+            a.x0 = static_cast<const float*>(d->x0_dev); a.x1 = static_cast<const float*>(d->x1_dev);
+            a.dst0 = static_cast<float*>(d->x0_dev); a.dst1 = static_cast<float*>(d->x1_dev);
+            a.rsum = l.agg();
+            a.mom_parts = (d->flags & SMC_FLAG_NO_MOMENTS) ? nullptr : l.mom_parts();
+            a.parts = l.k1_parts();
+            a.z = z_dev;
+            a.keys = philox_expand(seed);
+            a.t = (uint32_t)t;
+            a.n = d->n; a.ld = d->ld; a.n_tiles = l.L.n_tiles;
+            const int64_t grid = k5_grid(NX);
+            const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
+            SMC_REQUIRE(ranges % grid == 0 && l.L.n_tiles >= ranges,
+                        "smc: the fused step needs at least %lld tiles", (long long)ranges);
+            a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
+            a.kshift_bound = fin2.kshift_bound;
+            a.ticket = l.ticket() + 1;
+            a.fin = f; a.fin.mom_parts = l.mom_parts(); a.fin.n_mom_parts = (int)grid;
+            a.fin2 = fin2; a.fin2.producer_rsum = 1;
+            auto kern = k5_resample_propagate<NX, Model>;
+            const size_t smem = k5_smem_bytes<NX>();
+            static bool attr_set = false;   // one flag per template instantiation
+            if (!attr_set) {
+                SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    cudaSharedmemCarveoutMaxShared));
+                attr_set = true;
+            }
+            SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, 256u, smem, l.st, a, m));
+            SMC_CHECK_CUDA(cudaGetLastError());
+        }
+    }
     if (!(phases & 2)) return 0;
-    // pre-pass of step t on the weights just written
+    // range pre-pass of step t over the weights just written: returns at once unless ctrl says it is needed
     return launch_prepass<float>(l, false, logw_out_dev, d->nx, 0, nullptr);
 }
 
@@ -2572,6 +2737,7 @@ int smc_sir_finalize(const smc_sir_desc* d, double resample_thresh, double u_hos
     a.nx = d->nx;
     a.inline_moments = inline_moments(d) ? 1 : 0;
     a.f32 = d->dtype == SMC_F32;
+    quant_bound_for(d->n_global, &a.lw_bound, &a.kshift_bound);
     a.thresh = resample_thresh; a.u_host = u_host; a.seed = seed; a.t = (uint32_t)t;
     k2_finalize<<<1, kThreads, 0, l.st>>>(a);
     SMC_CHECK_CUDA(cudaGetLastError());
@@ -2747,6 +2913,7 @@ int smc_sir_step_weight(const smc_sir_desc* d, int32_t model_id, const double* p
     fin.stats = stats_row_dev; fin.n_global = d->n_global; fin.nx = d->nx;
     fin.inline_moments = inline_moments(d) ? 1 : 0;
     fin.f32 = d->dtype == SMC_F32;
+    quant_bound_for(d->n_global, &fin.lw_bound, &fin.kshift_bound);
     fin.thresh = resample_thresh; fin.u_host = u_host; fin.seed = seed; fin.t = (uint32_t)t;
     return sir_propagate_weight_impl(d, model_id, params_host, n_params, mode, z_dev, noise_dev, seed, t, stream, &fin);
 }
@@ -2844,6 +3011,7 @@ int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_
     memset(&fin, 0, sizeof(fin));
     fin.ctrl = l.ctrl(); fin.stats = stats_row_dev; fin.n_global = d->n_global; fin.nx = d->nx;
     fin.inline_moments = 1; fin.f32 = d->dtype == SMC_F32;
+    quant_bound_for(d->n_global, &fin.lw_bound, &fin.kshift_bound);
     fin.thresh = resample_thresh; fin.u_host = -1.0; fin.seed = seed; fin.t = (uint32_t)t;
     k2_finalize_sharded<<<1, kThreads, 0, l.st>>>(fin, sc);
     SMC_CHECK_CUDA(cudaGetLastError());

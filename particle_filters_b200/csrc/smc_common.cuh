@@ -57,6 +57,7 @@ constexpr int kK1MaxBlocks = 148 * SMC_K1_GRID_PER_SM;  // persistent K1 grid: C
 constexpr int kMaxNx = 64;             // control block moment shift capacity
 constexpr int kFusedNxMax = 4;         // K3 moves the payload itself up to this many dims
 constexpr int kSyrkMaxBlocks = 148 * 2;  // grid of the high-dimensional moment kernel
+constexpr int kRsumStride = 2048;        // entries per range-total buffer (two buffers, <= 148 x 12 ranges each)
 
 // Fixed-point CDF: "index units" (N * w) with F = 62 - ceil(log2 N) fractional bits (>= 32);
 // bit 63 of a published tile word is its "valid" flag.
@@ -75,9 +76,13 @@ struct Ctrl {
     int32_t do_resample; // decision of the last finalize
     int32_t frac_bits;   // F of the fixed-point CDF for this population size
     // resampler constants derived once per step from (u, log_norm, N) by the finalize kernel
-    double lw_ref;                 // log_norm - log N : N w = exp(lw - lw_ref)
+    double lw_ref;                 // quantisation reference: fixed-point weight = 2^Fa exp(lw - lw_ref)
     unsigned long long uq;         // floor(u 2^F)
     unsigned long long margin;     // near-tie margin in fraction units
+    // fp32 mode (see "fp32 CDF" in sir_kernels.cu)
+    float kshift;                  // a = rni(2^(lw log2e + kshift)), kshift = Fa - lw_ref log2e
+    int32_t rsum_valid;            // the kernel that wrote the log-weights also delivered the range totals
+    int32_t rsum_sel;              // which of the two range-total buffers belongs to the current log-weights
 };
 static_assert(sizeof(Ctrl) <= 1024, "control block must fit its slot");
 
@@ -117,7 +122,7 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     L.ctrl = off;      off = align256(off + 1024);
     L.params = off;    off = align256(off + size_t(kParamSlots) * kParamSlotDoubles * sizeof(double));
     L.k1_parts = off;  off = align256(off + size_t(L.n_k1_blocks) * partial_stride(nx) * sizeof(double));
-    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16 + 65536);   // range totals of the pre-pass
+    L.tile_agg = off;  off = align256(off + size_t(L.n_tiles) * 16 + 65536);   // 2 x kRsumStride range totals
     L.ticket = off;    off = align256(off + 256);
     L.mom_parts = off; off = align256(off + size_t(L.n_tiles) * moment_stride(nx) * sizeof(double));
     // per-CTA records of the X^T W X moment kernel (nx > kFusedNxMax): (1 + nx + nx^2) doubles each
