@@ -37,8 +37,8 @@ namespace smc {
 #endif
 template <int NX> struct K5Occ { static constexpr int value = NX <= 1 ? SMC_K5_OCC : 2; };
 constexpr int kK5Tile = 4096;
-constexpr int kK5Window = 256 * 18;          // output slots per tile handled by the expansion route
-constexpr int kK5WinStride = kK5Window + 8;  // + the quad offset of the first output; a multiple of 4
+constexpr int kK5Window = 256 * 18;          // u16 marker slots of the skewed route (aliases the output window)
+constexpr int kK5WinStride = 4096 + 1024 + 512;   // output window: carried outputs (< 1027) + one tile's new ones
 template <int NX> constexpr size_t k5_smem_bytes() {
     return sizeof(float) * ((size_t)kK5Tile * (1 + NX) + (size_t)kK5WinStride * NX);
 }
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     constexpr uint32_t MAXD = 4 * IPT;
     constexpr int NZ = Model::NZ;
     constexpr int NM = NX + NX * (NX + 1) / 2;
-    static_assert(W == THREADS * CH && WIN % 4 == 0, "window geometry");
+    static_assert(W == THREADS * CH && WIN % 4 == 0 && 2 * W <= 4 * WIN, "window geometry");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* lw_s = reinterpret_cast<float4*>(smem_raw);                                   // TILE floats, units swizzled
@@ -86,9 +86,14 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     __shared__ unsigned long long s_warp_all[WARPS];
     __shared__ uint32_t s_E[2];
     __shared__ int s_wmax[WARPS];
-    __shared__ double s_mom[WARPS][16];
-    __shared__ double s_m[16];
     __shared__ int s_last;
+    // scratch of the kernel's tail (after the tile loop): aliases the tile buffers
+    double (*s_mom)[16] = reinterpret_cast<double (*)[16]>(smem_raw);             // [WARPS][16]
+    double* s_m = reinterpret_cast<double*>(smem_raw) + WARPS * 16;               // [16]
+    double* s_fout = s_m + 16;                                                    // [32]
+    double* s_ftmp = s_fout + 32;                                                 // [WARPS]
+    double (*s_fred)[2] = reinterpret_cast<double (*)[2]>(s_ftmp + WARPS);        // [WARPS][2]
+    float* s_fmax = reinterpret_cast<float*>(s_ftmp + WARPS + 2 * WARPS);         // [WARPS]
 
     Ctrl* ctrl = a.ctrl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,12 +266,87 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     using FullQuad = K5Flag<true>;
     using PartQuad = K5Flag<false>;
 
+    // ---- output window state (uniform over the CTA): window position i holds the output with global index
+    // g0 + i (g0 % 4 == 0, so window quads are global quads); positions [lead, fill) are valid.  Phase E only
+    // ever runs whole rounds of 256 quads -- every lane of every warp busy -- and leaves what is left over
+    // (< 1024 + 3 outputs) in the window; it is moved to the front at the start of the next tile.
+    uint32_t g0 = 0u, fill = 0u, lead = 0u, done4 = 0u;     // done4 = 4 x quads consumed by the last round (to be compacted)
+    bool restart = true;                                    // the next tile (re)starts the window at its own E0
+    const uint32_t win_sa = (uint32_t)__cvta_generic_to_shared(win);
+    float macc[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) macc[k] = 0.f;
+    auto add_moments = [&](const float (&xv)[NX]) {
+        float xc[NX];
+        int k = 0;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) { xc[d] = xv[d] - shift[d]; macc[k] += xc[d]; ++k; }
+#pragma unroll
+        for (int d = 0; d < NX; ++d)
+#pragma unroll
+            for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fmaf(xc[d], xc[d2], macc[k]); ++k; }
+    };
+    // one round of phase E over window quads [0, nq): moments of step t-1, functor of step t, stores.
+    // `ragged`: quad 0 may start with `lead` foreign lanes and the last quad may be partial (masked path).
+    auto consume = [&](const uint32_t nq, const bool ragged) {
+        for (uint32_t q = tid; q < nq; q += THREADS) {
+            float xt[NX][4];
+#pragma unroll
+            for (int d = 0; d < NX; ++d)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(xt[d][0]), "=f"(xt[d][1]), "=f"(xt[d][2]), "=f"(xt[d][3])
+                             : "r"(win_sa + (uint32_t)(d * WIN * 4) + 16u * q) : "memory");
+            const uint32_t w0 = 4u * q;
+            if (!((q == 0u && lead) || (ragged && w0 + 4u > fill))) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                  // post-resample moments of step t-1
+                    float xv[NX];
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
+                    add_moments(xv);
+                }
+                process_quad(FullQuad(), xt, g0 + w0, 15u);
+            } else {
+                unsigned mask = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool valid = w0 + j >= lead && w0 + j < fill;
+                    if (valid) mask |= 1u << j;
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) xt[d][j] = valid ? xt[d][j] : 0.f;
+                    if (valid) {
+                        float xv[NX];
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
+                        add_moments(xv);
+                    }
+                }
+                if (mask) process_quad(PartQuad(), xt, g0 + w0, mask);
+            }
+        }
+    };
+
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
         const int64_t tile_base = tile * TILE;
         const unsigned long long tile_prefix = prefix;
 
         asm volatile("cp.async.wait_all;\n" ::: "memory");
-        __syncthreads();   // S1: lw_s, x_s complete; every thread has left the previous tile's phase E (window free)
+        __syncthreads();   // S1: lw_s, x_s complete; every thread has left the previous round of phase E
+
+        // ---- compaction: what the last round left over moves to the front of the window ------------------
+        if (done4) {
+            const uint32_t nl4 = (fill - done4 + 3u) >> 2;     // float4 units to move (< 258)
+            for (uint32_t i = tid; i < nl4; i += THREADS) {
+                // (source and destination overlap by at most two floats, which the same thread reads, then writes)
+#pragma unroll
+                for (int d = 0; d < NX; ++d) {
+                    float4* wq = reinterpret_cast<float4*>(win + d * WIN);
+                    const float4 v = wq[(done4 >> 2) + i];
+                    wq[i] = v;
+                }
+            }
+            g0 += done4; fill -= done4; lead = 0u; done4 = 0u;
+        }
 
         // ---- phase B: fixed-point weights, thread / warp / CTA scan ------------------------------------
         float p[IPT];
@@ -315,22 +395,9 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         const uint32_t E0 = s_E[0], E1 = s_E[1];
         const bool sane = E0 <= E1 && E1 <= Nn;
         const uint32_t count = sane ? E1 - E0 : 0u;
-        const uint32_t s0 = E0 & 3u;                   // the window is laid out on global quads
-        const bool direct = !heavy && count + s0 <= (uint32_t)W;
-
-        float macc[NM];
-#pragma unroll
-        for (int k = 0; k < NM; ++k) macc[k] = 0.f;
-        auto add_moments = [&](const float (&xv)[NX]) {
-            float xc[NX];
-            int k = 0;
-#pragma unroll
-            for (int d = 0; d < NX; ++d) { xc[d] = xv[d] - shift[d]; macc[k] += xc[d]; ++k; }
-#pragma unroll
-            for (int d = 0; d < NX; ++d)
-#pragma unroll
-                for (int d2 = 0; d2 <= d; ++d2) { macc[k] = fmaf(xc[d], xc[d2], macc[k]); ++k; }
-        };
+        if (restart) { g0 = E0 & ~3u; lead = E0 & 3u; fill = lead; restart = false; }
+        const bool direct = !heavy && fill + count <= (uint32_t)WIN && E0 == g0 + fill;
+        const bool last = tile + 1 == t_end;
 
         if (direct) {
             // ---- phase D: expansion -- one payload store per offspring ------------------------------
@@ -342,8 +409,8 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                     for (int k = 0; k < IPT; ++k) if (k >= klast) e[k] = Nn;
                 }
                 // byte address of output index 0 in the window (boundaries are monotone and lie in [E0, E1], so
-                // every store below falls into [s0, s0 + count))
-                const uint32_t wb = (uint32_t)__cvta_generic_to_shared(win) + 4u * s0 - 4u * E0;
+                // every store below falls into [fill, fill + count))
+                const uint32_t wb = win_sa - 4u * g0;
                 uint32_t a0 = wb + 4u * e_start, most = 0u;
 #pragma unroll
                 for (int k4 = 0; k4 < UPT; ++k4) {
@@ -386,52 +453,24 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                     }
                 }
             }
-            __syncthreads();   // S4: the window holds the resampled tile; lw_s / x_s are dead
-            if (tile + 1 < t_end) fetch(tile + 1);             // the next tile travels during phase E
+            fill += count;
+            __syncthreads();   // S4: the window holds the resampled outputs; lw_s / x_s are dead
+            if (!last) fetch(tile + 1);                        // the next tile travels during phase E
 
-            // ---- phase E: quads of outputs -> moments of step t-1, functor of step t, stores ------------
-            const uint32_t wend = s0 + count;                  // valid window positions [s0, wend)
-            const uint32_t nquad = (wend + 3u) >> 2;
-            const uint32_t gw0 = E0 - s0;                      // global index of window position 0
-            const uint32_t win_sa = (uint32_t)__cvta_generic_to_shared(win);
-            for (uint32_t q = tid; q < nquad; q += THREADS) {
-                const uint32_t w0 = 4u * q;
-                float xt[NX][4];
-#pragma unroll
-                for (int d = 0; d < NX; ++d)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(xt[d][0]), "=f"(xt[d][1]), "=f"(xt[d][2]), "=f"(xt[d][3])
-                                 : "r"(win_sa + (uint32_t)(d * WIN * 4) + 16u * q) : "memory");
-                if (w0 >= s0 && w0 + 4u <= wend) {
-                    // post-resample moments of step t-1 (the gathered, not yet propagated, particles)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float xv[NX];
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
-                        add_moments(xv);
-                    }
-                    process_quad(FullQuad(), xt, gw0 + w0, 15u);
-                } else {                                       // first / last quad of the tile: partial
-                    unsigned mask = 0u;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool valid = w0 + j >= s0 && w0 + j < wend;
-                        if (valid) mask |= 1u << j;
-#pragma unroll
-                        for (int d = 0; d < NX; ++d) xt[d][j] = valid ? xt[d][j] : 0.f;
-                        if (valid) {
-                            float xv[NX];
-#pragma unroll
-                            for (int d = 0; d < NX; ++d) xv[d] = xt[d][j];
-                            add_moments(xv);
-                        }
-                    }
-                    process_quad(PartQuad(), xt, gw0 + w0, mask);
-                }
+            // ---- phase E: whole rounds of 256 quads (the CTA's last tile: everything that is left) --------
+            if (last) {
+                consume((fill + 3u) >> 2, true);
+            } else {
+                const uint32_t nq = (fill >> 2) & ~255u;
+                if (lead) consume(nq, true); else consume(nq, false);
+                done4 = 4u * nq;
             }
         } else {
-            // ---- skewed tile: exact boundaries, head markers + max-scan fill, window by window ------------
+            // ---- skewed tile: first everything the window still holds (a ragged round), then exact boundaries,
+            // head markers + max-scan fill window by window, straight to the destination buffer --------------
+            if (fill > lead) consume((fill + 3u) >> 2, true);
+            __syncthreads();
+            restart = true; done4 = 0u; fill = 0u; lead = 0u;
             uint32_t e[IPT];
             exact_boundaries<IPT>(p, base_raw, rm, e);
 #pragma unroll
@@ -493,7 +532,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                 {
                     const uint32_t rem = count - wbase;
                     const int cnt = rem < (uint32_t)W ? (int)rem : W;
-                    const uint32_t g0 = E0 + wbase;                          // global index of window slot 0
+                    const uint32_t gb = E0 + wbase;                          // global index of window slot 0
                     for (int i = tid; i < cnt; i += THREADS) {
                         int li1 = (int)ids[i];
                         if (li1 == 0) li1 = 1;                               // (only on inconsistent input)
@@ -501,7 +540,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
 #pragma unroll
                         for (int d = 0; d < NX; ++d) {
                             xv[d] = x_of(d, li1 - 1);
-                            xdst[d * a.ld + g0 + i] = xv[d];
+                            xdst[d * a.ld + gb + i] = xv[d];
                         }
                         add_moments(xv);
                     }
@@ -529,17 +568,16 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                 }
             }
             __syncthreads();
-            if (tile + 1 < t_end) fetch(tile + 1);
+            if (!last) fetch(tile + 1);
         }
 #pragma unroll
-        for (int k = 0; k < NM; ++k) macc_d[k] += (double)macc[k];
+        for (int k = 0; k < NM; ++k) { macc_d[k] += (double)macc[k]; macc[k] = 0.f; }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     if (cur_r != 0xffffffffu && cur_acc) atomicAdd(rout + cur_r, cur_acc);
 
     {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
-        __shared__ float s_fmax[WARPS];
-        __shared__ double s_fred[WARPS][2];
+        __syncthreads();                                     // the tile buffers are dead: reuse them as scratch
         const float wmax = warp_max(f_tm);
         if (lane == 0) s_fmax[warp] = wmax;
         __syncthreads();
@@ -587,8 +625,6 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         // buffer this launch has accumulated into the current one
         for (int i = tid; i < kRsumStride; i += THREADS) a.rsum[(size_t)sel * kRsumStride + i] = 0ull;
         if (tid == 0) ctrl->rsum_sel = sel ^ 1;
-        __shared__ double s_fout[32];
-        __shared__ double s_ftmp[kWarps];
         __syncthreads();
         K2Args f2 = a.fin2;
         f2.ctrl = ctrl; f2.parts = a.parts; f2.n_parts = (int)gridDim.x;
