@@ -45,6 +45,13 @@ template <int NX> constexpr size_t k5_smem_bytes() {
 
 template <bool B> struct K5Flag { static constexpr bool value = B; };
 
+// "No functor": K5 then is the plain fp32 resampler -- gather, uniform weights, post-resample moments, finish
+// (models/particle_filter.py:209-210, :266-268) -- with the same boundaries, hence the same ancestors, as the
+// fused instantiations and as k3_resample (which keeps the fp64 parity mode, the ancestor trace and the shards).
+template <int NX_> struct CopyModel { static constexpr int NX = NX_, NZ = 1; };
+template <class M> struct K5IsCopy { static constexpr bool value = false; };
+template <int NX_> struct K5IsCopy<CopyModel<NX_>> { static constexpr bool value = true; };
+
 struct K5Args {
     Ctrl* ctrl;
     const float* lw_in;        // log-weights of step t-1
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     constexpr int W = kK5Window, WIN = kK5WinStride, CH = IPT + 2;
     constexpr uint32_t MAXD = 4 * IPT;
     constexpr int NZ = Model::NZ;
+    constexpr bool COPY = K5IsCopy<Model>::value;      // resample only (no step t functor)
     constexpr int NM = NX + NX * (NX + 1) / 2;
     static_assert(W == THREADS * CH && WIN % 4 == 0 && 2 * W <= 4 * WIN, "window geometry");
 
@@ -118,45 +126,56 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     const int64_t t_end = k3_range_begin(blockIdx.x + 1, a.n_tiles, gridDim.x);
     auto swz = [](int f) -> int { return f ^ ((f >> 3) & (UPT - 1)); };
 
-    // log-weights and particles of one tile -> shared memory (cp.async; a guarded copy of the ragged last tile)
-    auto fetch = [&](int64_t tile) {
+    // log-weights / particles of one tile -> shared memory (cp.async; the ragged last tile is guarded).  Two
+    // commit groups per tile, both issued after phase D of the tile before (issuing the log-weights right after
+    // phase B measured 2.5 % slower); the particles are awaited only at S3.  `live` = false commits an empty group,
+    // so that "all but the newest group" (cp.async.wait_group 1) always names the right data.
+    auto fetch_lw = [&](int64_t tile, bool live) {
         const int64_t tb = tile * TILE;
-        if (tb + TILE <= a.n) {
+        if (live && tb + TILE <= a.n) {
 #pragma unroll
             for (int r = 0; r < UPT; ++r) {
-                const int f = r * THREADS + tid, fs = swz(f);
-                const unsigned dl = (unsigned)__cvta_generic_to_shared(&lw_s[fs]);
+                const int f = r * THREADS + tid;
+                const unsigned dl = (unsigned)__cvta_generic_to_shared(&lw_s[swz(f)]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dl), "l"(a.lw_in + tb + (int64_t)f * 4) : "memory");
-#pragma unroll
-                for (int d = 0; d < NX; ++d) {
-                    const unsigned dx = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + fs * 4);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dx),
-                                 "l"(xsrc + d * a.ld + tb + (int64_t)f * 4) : "memory");
-                }
             }
-        } else {
+        } else if (live) {
             const int n_in = (int)(a.n - tb);
 #pragma unroll
             for (int r = 0; r < UPT; ++r) {
-                const int f = r * THREADS + tid, fs = swz(f);
+                const int f = r * THREADS + tid;
                 float tmp[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (f * 4 < n_in) {
                     load4<float>(a.lw_in + tb + f * 4, tmp);              // rows are padded to a multiple of 4
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (f * 4 + j >= n_in) tmp[j] = -INFINITY;
-#pragma unroll
-                    for (int d = 0; d < NX; ++d) {
-                        const unsigned dx = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + fs * 4);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dx),
-                                     "l"(xsrc + d * a.ld + tb + (int64_t)f * 4) : "memory");
-                    }
                 }
-                lw_s[fs] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+                lw_s[swz(f)] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    if (t_begin < t_end) fetch(t_begin);
+    auto fetch_x = [&](int64_t tile, bool live) {
+        const int64_t tb = tile * TILE;
+        if (live) {
+            const int n_in = tb + TILE <= a.n ? TILE : (int)(a.n - tb);
+#pragma unroll
+            for (int r = 0; r < UPT; ++r) {
+                const int f = r * THREADS + tid;
+                if (f * 4 < n_in) {
+#pragma unroll
+                    for (int d = 0; d < NX; ++d) {
+                        const unsigned dx = (unsigned)__cvta_generic_to_shared(x_s + d * TILE + swz(f) * 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dx),
+                                     "l"(xsrc + d * a.ld + tb + (int64_t)f * 4) : "memory");
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    fetch_lw(t_begin, t_begin < t_end);
+    fetch_x(t_begin, t_begin < t_end);
 
     // exclusive CDF prefix of this CTA's first tile and the CDF total, from the range totals
     unsigned long long prefix, cdf_total;
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     // ---- step t: observation, online (max, sum e, sum e^2) of its log-weights, range totals of its CDF ----
     float fz[NZ];
 #pragma unroll
-    for (int k = 0; k < NZ; ++k) fz[k] = (float)a.z[k];
+    for (int k = 0; k < NZ; ++k) fz[k] = COPY ? 0.f : (float)a.z[k];
     float f_tm = -INFINITY, f_acc0 = 0.f, f_acc1 = 0.f;
     const float f_lw_uniform = (float)(-log((double)a.n));
     // range cursor: the pre-pass range (k3_range_begin over n_ranges) that holds the thread's current quad
@@ -219,6 +238,19 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     // bit-identical to the three-launch step's
     auto process_quad = [&](auto full_tag, float (&xt)[NX][4], const uint32_t gi0, const unsigned mask) {
         constexpr bool FULL = decltype(full_tag)::value;           // all four lanes belong to this tile
+        if constexpr (COPY) {
+            if (FULL) {
+#pragma unroll
+                for (int d = 0; d < NX; ++d) store4<float>(xdst + d * a.ld + gi0, xt[d]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((mask >> j) & 1u) {
+#pragma unroll
+                        for (int d = 0; d < NX; ++d) xdst[d * a.ld + gi0 + j] = xt[d][j];
+                    }
+            }
+        } else {
         if (gi0 >= cur_bnd) cursor_slow(gi0);
         float nrm[NX][4];
         Draw<NX>::run(a.keys, (uint64_t)(gi0 >> 2), a.t, nrm);
@@ -262,6 +294,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur_acc += quant_a(quant_p(lwq[j], a.kshift_bound));   // masked lanes: 0
+        }
     };
     using FullQuad = K5Flag<true>;
     using PartQuad = K5Flag<false>;
@@ -330,8 +363,8 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         const int64_t tile_base = tile * TILE;
         const unsigned long long tile_prefix = prefix;
 
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-        __syncthreads();   // S1: lw_s, x_s complete; every thread has left the previous round of phase E
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();   // S1: lw_s complete; every thread has left the previous round of phase E
 
         // ---- compaction: what the last round left over moves to the front of the window ------------------
         if (done4) {
@@ -366,7 +399,8 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
             if (lane >= o) incl_w += t;
         }
         if (lane == 31) s_warp_tot[warp] = incl_w;
-        __syncthreads();   // S2
+        __syncthreads();   // S2: lw_s is dead
+        const bool last = tile + 1 == t_end;
         unsigned long long warp_excl = 0, tile_total = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
@@ -391,13 +425,13 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         }
         if (tid == 0) s_E[0] = e_start;
         if (tid == THREADS - 1) s_E[1] = e_end;
-        const int heavy = __syncthreads_or(e_end - e_start > MAXD);   // S3
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");        // this tile's particles
+        const int heavy = __syncthreads_or(e_end - e_start > MAXD);   // S3: x_s complete
         const uint32_t E0 = s_E[0], E1 = s_E[1];
         const bool sane = E0 <= E1 && E1 <= Nn;
         const uint32_t count = sane ? E1 - E0 : 0u;
         if (restart) { g0 = E0 & ~3u; lead = E0 & 3u; fill = lead; restart = false; }
         const bool direct = !heavy && fill + count <= (uint32_t)WIN && E0 == g0 + fill;
-        const bool last = tile + 1 == t_end;
 
         if (direct) {
             // ---- phase D: expansion -- one payload store per offspring ------------------------------
@@ -454,8 +488,9 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                 }
             }
             fill += count;
-            __syncthreads();   // S4: the window holds the resampled outputs; lw_s / x_s are dead
-            if (!last) fetch(tile + 1);                        // the next tile travels during phase E
+            __syncthreads();   // S4: the window holds the resampled outputs; x_s is dead
+            fetch_lw(tile + 1, !last);                         // travels during phase E
+            fetch_x(tile + 1, !last);                          // travels during phase E and the next tile's B, C
 
             // ---- phase E: whole rounds of 256 quads (the CTA's last tile: everything that is left) --------
             if (last) {
@@ -549,7 +584,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
             }
             // the window loop has written the resampled particles of this tile to the destination buffer (block-
             // visible after the barrier): run the functor over them in place
-            if (count > 0u) {
+            if (!COPY && count > 0u) {
                 const uint32_t gq0 = E0 & ~3u;
                 const uint32_t nq = ((E1 + 3u) >> 2) - (gq0 >> 2);
                 for (uint32_t q = tid; q < nq; q += THREADS) {
@@ -568,16 +603,17 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                 }
             }
             __syncthreads();
-            if (!last) fetch(tile + 1);
+            fetch_lw(tile + 1, !last);
+            fetch_x(tile + 1, !last);
         }
 #pragma unroll
         for (int k = 0; k < NM; ++k) { macc_d[k] += (double)macc[k]; macc[k] = 0.f; }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
-    if (cur_r != 0xffffffffu && cur_acc) atomicAdd(rout + cur_r, cur_acc);
+    if (!COPY && cur_r != 0xffffffffu && cur_acc) atomicAdd(rout + cur_r, cur_acc);
 
-    {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
-        __syncthreads();                                     // the tile buffers are dead: reuse them as scratch
+    __syncthreads();                                         // the tile buffers are dead: reuse them as scratch
+    if (!COPY) {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
         const float wmax = warp_max(f_tm);
         if (lane == 0) s_fmax[warp] = wmax;
         __syncthreads();
@@ -621,14 +657,16 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     if (s_last) {
         __threadfence();
         finish_body(ctrl, a.fin, s_mom, s_m);
-        // every CTA has read the totals of step t-1: clear them for the launch after the next, and make the
-        // buffer this launch has accumulated into the current one
-        for (int i = tid; i < kRsumStride; i += THREADS) a.rsum[(size_t)sel * kRsumStride + i] = 0ull;
-        if (tid == 0) ctrl->rsum_sel = sel ^ 1;
-        __syncthreads();
-        K2Args f2 = a.fin2;
-        f2.ctrl = ctrl; f2.parts = a.parts; f2.n_parts = (int)gridDim.x;
-        finalize_body(f2, s_fout, s_ftmp);
+        if (!COPY) {
+            // every CTA has read the totals of step t-1: clear them for the launch after the next, and make the
+            // buffer this launch has accumulated into the current one
+            for (int i = tid; i < kRsumStride; i += THREADS) a.rsum[(size_t)sel * kRsumStride + i] = 0ull;
+            if (tid == 0) ctrl->rsum_sel = sel ^ 1;
+            __syncthreads();
+            K2Args f2 = a.fin2;
+            f2.ctrl = ctrl; f2.parts = a.parts; f2.n_parts = (int)gridDim.x;
+            finalize_body(f2, s_fout, s_ftmp);
+        }
         if (tid == 0) *a.ticket = 0u;
     }
 }

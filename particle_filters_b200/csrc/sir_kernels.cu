@@ -129,6 +129,19 @@ inline void quant_bound_for(int64_t n_global, double* lw_bound, float* kshift_bo
     *kshift_bound = (float)((double)fa_bits_for(n_global) - (double)lw_uniform * (double)kLog2eF);
 }
 
+// first tile of pre-pass range / resampler CTA b of `grid` (see K3a)
+__host__ __device__ inline int64_t k3_range_begin(int64_t b, int64_t n_tiles, int64_t grid) {
+    return (b * n_tiles) / grid;
+}
+// fp32 quantisation of one log-weight: a = rni(p), p = 2^(lw log2e + kshift) (see "Per-item quantisation" below)
+__device__ __forceinline__ float quant_p(float lw, float kshift) {
+    return ex2_approx(fminf(fmaf(lw, kLog2eF, kshift), 62.5f));       // NaN-free input (see K1)
+}
+__device__ __forceinline__ unsigned long long quant_a(float p) {
+    unsigned long long q;
+    asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
+    return q;
+}
 struct K2Args {
     Ctrl* ctrl;
     const double* parts;
@@ -167,6 +180,11 @@ template <typename real> struct K1Args {
     unsigned int* ticket;       // arrival counter for fuse_finalize (zero between launches)
     K2Args fin;
     ShardCtx shard;             // mail != nullptr: the last CTA publishes this shard's partial record instead
+    // fp32 bootstrap steps (uniform prior weights): K1 also delivers the range totals of the resampler's CDF,
+    // quantised against the a-priori bound (see finalize_body / fused_step.cuh); CTAs then own contiguous chunks
+    unsigned long long* rsum;   // two buffers of kRsumStride totals (nullptr: not wanted)
+    int32_t n_ranges;
+    float kshift_bound;
 };
 
 template <typename real, int NX>
@@ -242,7 +260,8 @@ template <typename real, class Model, bool CHECK, bool MOM, int NR>
 __device__ __forceinline__ void k1_chunk(const K1Args<real>& a, const Model& m, real* x, int64_t blk_base, int tid,
                                          bool uniform, real log_norm_prev, real lw_uniform, bool do_prop, bool do_w,
                                          const real (&z)[Model::NZ], const real (&shift)[Model::NX], real& tm,
-                                         real (&acc)[NR], real (&xs)[kK1Quads][Model::NX][4]) {
+                                         real (&acc)[NR], real (&xs)[kK1Quads][Model::NX][4],
+                                         const bool do_rsum = false, unsigned long long* racc = nullptr) {
     constexpr int NX = Model::NX;
     const real NEG_INF = -INFINITY;
     real lw[kK1Quads][4];
@@ -295,6 +314,12 @@ __device__ __forceinline__ void k1_chunk(const K1Args<real>& a, const Model& m, 
                     lw[q][j] = v;
                 }
                 store4<real>(a.logw + i0, out);
+                if constexpr (sizeof(real) == 4) {
+                    if (do_rsum) {      // fixed-point weight against the a-priori bound (padding: -inf -> 0)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *racc += quant_a(quant_p(out[j], a.kshift_bound));
+                    }
+                }
             }
         }
     }
@@ -378,21 +403,52 @@ k1_propagate_weight(K1Args<real> a, Model m) {
 
     const int64_t n_chunks = cdiv64(a.n, kK1Block);
     const int64_t n_full = a.n / kK1Block;       // chunks [0, n_full) need no bounds checks
+    // Range totals (fp32 bootstrap steps with the fused finalize): CTA b then owns the contiguous chunks of the
+    // pre-pass ranges [b R / G, (b + 1) R / G) -- a chunk is a resampling tile -- and flushes one exact 64-bit sum
+    // per range into the buffer the control block does NOT name (all zero by invariant); the last CTA flips it.
+    const bool do_rsum = sizeof(real) == 4 && a.rsum != nullptr && uniform && do_w && a.fuse_finalize;
+    const int rsel = ctrl->rsum_sel;
+    unsigned long long racc = 0ull;
+    int64_t c_first = blockIdx.x, c_end = n_chunks, c_stride = gridDim.x;
+    int r_cur = 0;
+    int64_t r_bnd = 0;                           // first chunk of the next range
+    if (do_rsum) {
+        const int rpc = a.n_ranges / (int)gridDim.x;
+        r_cur = (int)blockIdx.x * rpc;
+        c_first = k3_range_begin(r_cur, n_chunks, a.n_ranges);
+        c_end = k3_range_begin(r_cur + rpc, n_chunks, a.n_ranges);
+        c_stride = 1;
+        r_bnd = k3_range_begin(r_cur + 1, n_chunks, a.n_ranges);
+    }
+    auto flush_range = [&]() {                   // CTA-uniform: one 64-bit atomic per warp
+        const unsigned long long v = warp_sum(racc);
+        if ((tid & 31) == 0 && v) atomicAdd(a.rsum + (size_t)(rsel ^ 1) * kRsumStride + r_cur, v);
+        racc = 0ull;
+    };
     if (PREFETCH) {
         real cur[kK1Quads][NX][4], nxt[kK1Quads][NX][4];
-        int64_t chunk = blockIdx.x;
-        if (chunk < n_full) k1_load<real, NX, false>(a, x, chunk * kK1Block, tid, cur);
-        else if (chunk < n_chunks) k1_load<real, NX, true>(a, x, chunk * kK1Block, tid, cur);
-        for (; chunk < n_chunks; chunk += gridDim.x) {
-            const int64_t next = chunk + gridDim.x;
-            if (next < n_full) k1_load<real, NX, false>(a, x, next * kK1Block, tid, nxt);
-            else if (next < n_chunks) k1_load<real, NX, true>(a, x, next * kK1Block, tid, nxt);
+        int64_t chunk = c_first;
+        if (chunk < c_end) {
+            if (chunk < n_full) k1_load<real, NX, false>(a, x, chunk * kK1Block, tid, cur);
+            else k1_load<real, NX, true>(a, x, chunk * kK1Block, tid, cur);
+        }
+        for (; chunk < c_end; chunk += c_stride) {
+            const int64_t next = chunk + c_stride;
+            if (next < c_end) {
+                if (next < n_full) k1_load<real, NX, false>(a, x, next * kK1Block, tid, nxt);
+                else k1_load<real, NX, true>(a, x, next * kK1Block, tid, nxt);
+            }
+            if (do_rsum && chunk >= r_bnd) {
+                flush_range();
+                ++r_cur;
+                r_bnd = k3_range_begin(r_cur + 1, n_chunks, a.n_ranges);
+            }
             if (chunk < n_full)
                 k1_chunk<real, Model, false, MOM, NR>(a, m, x, chunk * kK1Block, tid, uniform, log_norm_prev, lw_uniform,
-                                                      do_prop, do_w, z, shift, tm, acc, cur);
+                                                      do_prop, do_w, z, shift, tm, acc, cur, do_rsum, &racc);
             else
                 k1_chunk<real, Model, true, MOM, NR>(a, m, x, chunk * kK1Block, tid, uniform, log_norm_prev, lw_uniform,
-                                                     do_prop, do_w, z, shift, tm, acc, cur);
+                                                     do_prop, do_w, z, shift, tm, acc, cur, do_rsum, &racc);
 #pragma unroll
             for (int q = 0; q < kK1Quads; ++q)
 #pragma unroll
@@ -401,20 +457,26 @@ k1_propagate_weight(K1Args<real> a, Model m) {
                     for (int j = 0; j < 4; ++j) cur[q][d][j] = nxt[q][d][j];
         }
     } else {
-        for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        for (int64_t chunk = c_first; chunk < c_end; chunk += c_stride) {
             const int64_t blk_base = chunk * kK1Block;
             real cur[kK1Quads][NX][4];
+            if (do_rsum && chunk >= r_bnd) {
+                flush_range();
+                ++r_cur;
+                r_bnd = k3_range_begin(r_cur + 1, n_chunks, a.n_ranges);
+            }
             if (chunk < n_full) {
                 k1_load<real, NX, false>(a, x, blk_base, tid, cur);
                 k1_chunk<real, Model, false, MOM, NR>(a, m, x, blk_base, tid, uniform, log_norm_prev, lw_uniform, do_prop,
-                                                      do_w, z, shift, tm, acc, cur);
+                                                      do_w, z, shift, tm, acc, cur, do_rsum, &racc);
             } else {
                 k1_load<real, NX, true>(a, x, blk_base, tid, cur);
                 k1_chunk<real, Model, true, MOM, NR>(a, m, x, blk_base, tid, uniform, log_norm_prev, lw_uniform, do_prop,
-                                                     do_w, z, shift, tm, acc, cur);
+                                                     do_w, z, shift, tm, acc, cur, do_rsum, &racc);
             }
         }
     }
+    if (do_rsum) flush_range();
     if (!do_w) return;
 
     // ---- block combine: common max, rescale, fixed-tree sums -----------------------------------
@@ -455,7 +517,14 @@ k1_propagate_weight(K1Args<real> a, Model m) {
         __syncthreads();
         if (s_last) {
             __threadfence();
-            finalize_body(a.fin, s_out, s_tmp);
+            K2Args f = a.fin;
+            f.producer_rsum = do_rsum ? 1 : 0;
+            if (do_rsum) {   // hand the range totals over: clear the old buffer, make the new one current
+                for (int i = tid; i < kRsumStride; i += kThreads) a.rsum[(size_t)rsel * kRsumStride + i] = 0ull;
+                if (tid == 0) const_cast<Ctrl*>(ctrl)->rsum_sel = rsel ^ 1;
+                __syncthreads();
+            }
+            finalize_body(f, s_out, s_tmp);
             if (tid == 0) *a.ticket = 0u;
         }
     } else if (a.shard.mail) {
@@ -793,14 +862,6 @@ __device__ inline void unit_to_array(const double2& u, double* v) { v[0] = u.x; 
 //  them is exact and order-independent;
 //  fp64 mode (parity): the thread's fp64 running sum is quantised instead, so the round-off of
 //  2^-F index units does not accumulate over a run of tiny weights.
-__device__ __forceinline__ float quant_p(float lw, float kshift) {
-    return ex2_approx(fminf(fmaf(lw, kLog2eF, kshift), 62.5f));       // NaN-free input (see K1)
-}
-__device__ __forceinline__ unsigned long long quant_a(float p) {
-    unsigned long long q;
-    asm("cvt.rni.u64.f32 %0, %1;" : "=l"(q) : "f"(p));
-    return q;
-}
 template <typename real> struct Quant;
 template <> struct Quant<float> {
     float fscale, kshift;
@@ -929,9 +990,6 @@ __device__ inline uint32_t fast_outputs_below(unsigned long long Cb /* = C + bia
 // read of the log-weights), with no inter-CTA dependency, no per-tile records and no scan kernel:
 // CTA b of the resampler sums the totals of the ranges below it (<= G values) in its prologue.
 // The quantisation is the one k3_resample applies item by item, so both kernels agree to the bit.
-__host__ __device__ inline int64_t k3_range_begin(int64_t b, int64_t n_tiles, int64_t grid) {
-    return (b * n_tiles) / grid;
-}
 // The pre-pass cuts the tiles into R ranges with R a multiple of every resampler grid (148 x 12 ranges
 // for grids of 148 x {4, 3, 2} CTAs): CTA b of a grid of G owns ranges [b R / G, (b + 1) R / G), whose
 // first tile is floor(b T / G) -- the plain and the fused resampler can consume the same pre-pass.
@@ -2230,6 +2288,9 @@ int stage(const Launch& l, int slot, const double* host, int count, double** dev
     return 0;
 }
 
+inline int sm_count();
+inline int sm_count_early() { return sm_count(); }
+
 template <typename real, class Model>
 int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, const void* noise_dev, uint64_t seed,
               int64_t t, const K2Args* fin, const ShardCtx* shard) {
@@ -2249,10 +2310,18 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
     memset(&a.fin, 0, sizeof(a.fin));
     memset(&a.shard, 0, sizeof(a.shard));
     if (shard && (mode & SMC_MODE_WEIGHT)) a.shard = *shard;
+    a.rsum = nullptr; a.n_ranges = 0; a.kshift_bound = 0.f;
     if (fin && (mode & SMC_MODE_WEIGHT)) {
         a.fuse_finalize = 1;
         a.fin = *fin;
         a.fin.ctrl = l.ctrl(); a.fin.parts = l.k1_parts(); a.fin.n_parts = (int)l.L.n_k1_blocks;
+        // fp32, large single-shard populations: K1 also delivers the range totals of the resampler's CDF when the
+        // step turns out to be a bootstrap step (uniform prior weights; decided on the device)
+        const int64_t ranges = (int64_t)sm_count_early() * 12;
+        if (sizeof(real) == 4 && !shard && d->n == d->n_global && l.L.n_tiles >= ranges && ranges <= kRsumStride &&
+            ranges % l.L.n_k1_blocks == 0 && d->nx <= kFusedNxMax && !getenv("SMC_NO_K1_RSUM")) {
+            a.rsum = l.agg(); a.n_ranges = (int32_t)ranges; a.kshift_bound = fin->kshift_bound;
+        }
     }
     // mode bit 4 (internal): the caller knows the step resamples -> skip the pre-resample moments
     if (mode & 4)
@@ -2514,6 +2583,55 @@ inline bool fused_legacy() {
 }
 inline int64_t k5_grid(int nx) { return (int64_t)sm_count() * (nx <= 1 ? SMC_K5_OCC : 2); }
 
+// K5 launch: `fin2` != nullptr for the fused instantiations (functor of step t + its finalize), nullptr for the
+// plain fp32 resampler (CopyModel)
+template <int NX, class Model>
+int launch_k5(const Launch& l, const Model& m, const void* lw_in, void* lw_out, const double* z_dev, uint64_t seed,
+              int64_t t, const FinishArgs& f, const K2Args* fin2) {
+    const smc_sir_desc* d = l.d;
+    K5Args a;
+    memset(&a, 0, sizeof(a));
+    a.ctrl = l.ctrl();
+    a.lw_in = static_cast<const float*>(lw_in);
+    a.lw_out = static_cast<float*>(lw_out);
+    a.x0 = static_cast<const float*>(d->x0_dev); a.x1 = static_cast<const float*>(d->x1_dev);
+    a.dst0 = static_cast<float*>(d->x0_dev); a.dst1 = static_cast<float*>(d->x1_dev);
+    a.rsum = l.agg();
+    a.mom_parts = (d->flags & SMC_FLAG_NO_MOMENTS) ? nullptr : l.mom_parts();
+    a.parts = l.k1_parts();
+    a.z = z_dev;
+    a.keys = philox_expand(seed);
+    a.t = (uint32_t)t;
+    a.n = d->n; a.ld = d->ld; a.n_tiles = l.L.n_tiles;
+    const int64_t grid = k5_grid(NX);
+    const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
+    SMC_REQUIRE(ranges % grid == 0 && l.L.n_tiles >= ranges, "smc: K5 needs at least %lld tiles", (long long)ranges);
+    a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
+    a.ticket = l.ticket() + 1;
+    a.fin = f; a.fin.mom_parts = l.mom_parts(); a.fin.n_mom_parts = (int)grid;
+    if (fin2) { a.fin2 = *fin2; a.kshift_bound = fin2->kshift_bound; }
+    auto kern = k5_resample_propagate<NX, Model>;
+    const size_t smem = k5_smem_bytes<NX>();
+    static bool attr_set = false;   // one flag per template instantiation
+    if (!attr_set) {
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, 256u, smem, l.st, a, m));
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+// whether the plain fp32 resampler can be K5<CopyModel> (else k3_resample)
+inline bool k5_copy_ok(const Launch& l) {
+    const smc_sir_desc* d = l.d;
+    if (d->dtype != SMC_F32 || d->nx > 2 || d->n != d->n_global || d->offset != 0) return false;
+    if (d->flags & (SMC_FLAG_WRITE_ANCESTORS | SMC_FLAG_POST_MOMENTS_GENERIC | SMC_FLAG_GENERIC_MOMENTS)) return false;
+    const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, d->nx);
+    return l.L.n_tiles >= (int64_t)sm_count() * 12 && ranges % k5_grid(d->nx) == 0 && !fused_legacy();
+}
+
 template <class Model>
 int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const double* z_dev, double resample_thresh,
                  uint64_t seed, int64_t t, double* stats_prev_dev, double* stats_row_dev, int phases) {
@@ -2542,41 +2660,8 @@ int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const doub
             a.fk.fin = fin2;
             if (int rc = launch_k3_t<float, Model::NX, false, Model>(l, a, l.L.n_tiles, m)) return rc;
         } else {
-            constexpr int NX = Model::NX;
-            K5Args a;
-            memset(&a, 0, sizeof(a));
-            a.ctrl = l.ctrl();
-            a.lw_in = static_cast<const float*>(d->logw_dev);
-            a.lw_out = static_cast<float*>(logw_out_dev);
-            a.x0 = static_cast<const float*>(d->x0_dev); a.x1 = static_cast<const float*>(d->x1_dev);
-            a.dst0 = static_cast<float*>(d->x0_dev); a.dst1 = static_cast<float*>(d->x1_dev);
-            a.rsum = l.agg();
-            a.mom_parts = (d->flags & SMC_FLAG_NO_MOMENTS) ? nullptr : l.mom_parts();
-            a.parts = l.k1_parts();
-            a.z = z_dev;
-            a.keys = philox_expand(seed);
-            a.t = (uint32_t)t;
-            a.n = d->n; a.ld = d->ld; a.n_tiles = l.L.n_tiles;
-            const int64_t grid = k5_grid(NX);
-            const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
-            SMC_REQUIRE(ranges % grid == 0 && l.L.n_tiles >= ranges,
-                        "smc: the fused step needs at least %lld tiles", (long long)ranges);
-            a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
-            a.kshift_bound = fin2.kshift_bound;
-            a.ticket = l.ticket() + 1;
-            a.fin = f; a.fin.mom_parts = l.mom_parts(); a.fin.n_mom_parts = (int)grid;
-            a.fin2 = fin2; a.fin2.producer_rsum = 1;
-            auto kern = k5_resample_propagate<NX, Model>;
-            const size_t smem = k5_smem_bytes<NX>();
-            static bool attr_set = false;   // one flag per template instantiation
-            if (!attr_set) {
-                SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                    cudaSharedmemCarveoutMaxShared));
-                attr_set = true;
-            }
-            SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, 256u, smem, l.st, a, m));
-            SMC_CHECK_CUDA(cudaGetLastError());
+            fin2.producer_rsum = 1;
+            if (int rc = launch_k5<Model::NX, Model>(l, m, d->logw_dev, logw_out_dev, z_dev, seed, t, f, &fin2)) return rc;
         }
     }
     if (!(phases & 2)) return 0;
@@ -2939,6 +3024,10 @@ int smc_sir_step_resample(const smc_sir_desc* d, int32_t phases, double* stats_r
         f.stats = stats_row_dev; f.nx = d->nx; f.inline_moments = 1;
         f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
         const bool want_m = !(d->flags & SMC_FLAG_NO_MOMENTS);
+        if (k5_copy_ok(l)) {     // fp32, one shard, no ancestor trace: the expansion resampler
+            if (d->nx == 1) return launch_k5<1, CopyModel<1>>(l, CopyModel<1>(), d->logw_dev, nullptr, nullptr, 0, 0, f, nullptr);
+            return launch_k5<2, CopyModel<2>>(l, CopyModel<2>(), d->logw_dev, nullptr, nullptr, 0, 0, f, nullptr);
+        }
         return d->dtype == SMC_F32
                    ? launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f)
                    : launch_k3<double>(l, false, d->logw_dev, d->nx, 0ull, 0, nullptr, 0, want_m, nullptr, 0, false, &f);
