@@ -84,6 +84,9 @@ typedef struct smc_sir_desc {
 static inline int64_t smc_stats_stride(int nx) { return SMC_STATS_HEADER + nx + (int64_t)nx * nx; }
 
 int smc_abi_version(void);
+/* Number of kernel launches of the SIR step kernels (K1, range pre-pass, K3, K5) this process has issued
+ * so far; bench.py reports the difference over its timed region as `gpu_launches`. */
+uint64_t smc_launch_count(void);
 const char *smc_last_error(void);
 uint64_t smc_sizeof_sir_desc(void);
 
@@ -217,15 +220,24 @@ int smc_sir_step_weight(const smc_sir_desc *d, int32_t model_id, const double *p
 int smc_sir_step_resample(const smc_sir_desc *d, int32_t phases, double *stats_row_dev, void *stream);
 
 /* Fused "resample step t-1, then propagate + weigh step t" for back-to-back runs of filters that
- * resample every step (resample_thresh > 1), fp32, single GPU, nx <= 2 spec models: the resampler's
- * copy-out hands every gathered particle straight to the model functor, so the resampled set never
- * travels through HBM (20 B instead of 28 B per particle-update) and a step is two launches.
+ * resample every step (resample_thresh > 1), fp32, single GPU, nx <= 2 spec models (kernel K5,
+ * csrc/fused_step.cuh; reference particle_filter.py:146-171, :209-210, :266-268 of step t-1 and
+ * :223-237, :253-263 of step t): the resampler expands the tile's offspring into shared memory and hands
+ * every resampled particle straight to the model functor, so the resampled set never travels through HBM
+ * -- 16 B per particle-update (R logw, R x, W x, W logw) in ONE launch.  There is no range pre-pass: the
+ * kernel that writes the log-weights of step t also adds their fixed-point values (quantised against the
+ * a-priori bound lw <= -log N of a bootstrap step) into the per-range totals the next launch takes its CDF
+ * prefixes from.  Should the bound leave a step's weights too little resolution (mean likelihood below
+ * 2^-16), the last CTA says so in the control block and the pre-pass of `phases` bit 2 -- which otherwise
+ * returns at once -- recomputes the totals against the normaliser.
  * Precondition: step t-1 has been weighed and finalized (smc_sir_step_weight or a previous fused call)
- * and its range pre-pass has run (smc_sir_step_resample phase 1 / a previous fused call).  Reads
+ * and its range totals exist (delivered by those calls, or by smc_sir_step_resample phase 1).  Reads
  * d->logw_dev, writes the log-weights of step t to logw_out_dev (a second array; swap them for the next
  * call), the moments of step t-1 to stats_prev_dev and the header of step t to stats_row_dev.  Finish
  * the run with smc_sir_step_resample(d', 2, last_row) on the descriptor holding the last weights.
- * phases: bit 1 = the fused kernel, bit 2 = the range pre-pass of step t (3 = both). */
+ * phases: bit 1 = the fused kernel, bit 2 = the conditional range pre-pass of step t (3 = both).
+ * SMC_FUSED_LEGACY=1 in the environment selects round 1's pipeline (k3_resample with the functor in its
+ * copy-out + an unconditional pre-pass, 20 B per particle-update) for A/B measurements. */
 int smc_sir_step_fused(const smc_sir_desc *d, void *logw_out_dev, int32_t model_id,
                        const double *params_host, int32_t n_params, const double *z_dev,
                        double resample_thresh, uint64_t seed, int64_t t, double *stats_prev_dev,
@@ -246,6 +258,10 @@ typedef struct smc_shard_ctx {
     uint64_t stamp;
 } smc_shard_ctx;
 uint64_t smc_mailbox_bytes(void);
+/* Byte offset of the mailbox's error word: non-zero after a flag wait on this rank timed out (20 s) because a
+ * peer never published -- bit 63 | stamp << 8 | exchange (1 record, 2 total, 3 moments) << 4 | peer rank.  The
+ * kernels then run on with stale slots instead of hanging; the host checks the word (ShardedSir.check). */
+uint64_t smc_mailbox_error_offset(void);
 int smc_sir_step_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_t model_id,
                          const double *params_host, int32_t n_params, const double *z_dev,
                          double resample_thresh, uint64_t seed, int64_t t, double *stats_row_dev,

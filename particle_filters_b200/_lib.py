@@ -59,6 +59,7 @@ _D = C.POINTER(C.c_double)
 _SIG = {
     # name: (restype, argtypes)
     "smc_abi_version": (C.c_int, []),
+    "smc_launch_count": (C.c_uint64, []),
     "smc_last_error": (C.c_char_p, []),
     "smc_sizeof_sir_desc": (C.c_uint64, []),
     "smc_sir_workspace_bytes": (C.c_uint64, [C.c_int64, C.c_int32, C.c_int32]),
@@ -92,6 +93,7 @@ _SIG = {
     "smc_sir_step_fused": (C.c_int, [C.POINTER(SirDesc), _P, C.c_int32, _D, C.c_int32, _P, C.c_double, C.c_uint64,
                                      C.c_int64, _P, _P, C.c_int32, _P]),
     "smc_mailbox_bytes": (C.c_uint64, []),
+    "smc_mailbox_error_offset": (C.c_uint64, []),
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_systematic_ancestors": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_uint64, _P]),

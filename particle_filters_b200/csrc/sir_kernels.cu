@@ -98,16 +98,36 @@ struct Mailbox {
     unsigned long long tot[kMaxShards];
     double rec[kMaxShards][32];
     double mom[kMaxShards][16];
+    unsigned long long error;    // != 0: a wait on this rank timed out (bit 63 | stamp << 8 | exchange << 4 | peer rank)
 };
 struct ShardCtx {
     Mailbox* const* mail;        // device array of n_shards mailbox pointers (own one included)
     int32_t rank, n_shards;
     unsigned long long stamp;    // this step's stamp (> 0)
 };
-__device__ inline void mailbox_wait(const volatile unsigned long long* flags, int n, unsigned long long stamp) {
+// Bounded spin: a rank that raised an error, ran a different number of steps or died must not hang its peers
+// inside a kernel for ever.  After kMailboxTimeoutNs without the expected stamp the waiting thread records the
+// failure in the own mailbox's `error` word (host: smc_mailbox_error / ShardedSir.check) and the kernel goes on
+// with whatever the slots hold -- its results are then garbage, but every rank reaches its next host call.
+constexpr unsigned long long kMailboxTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;     // 20 s
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ inline void mailbox_wait(const volatile unsigned long long* flags, int n, unsigned long long stamp,
+                                    unsigned long long* error_word = nullptr, unsigned long long what = 0) {
     // threads 0 .. n-1 of the CTA each watch one flag; CTA-wide barrier afterwards
     if ((int)threadIdx.x < n) {
-        while (flags[threadIdx.x] != stamp) __nanosleep(20);
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (flags[threadIdx.x] != stamp) {
+            __nanosleep(20);
+            if ((++spins & 0x3ffu) == 0u && globaltimer_ns() - t0 > kMailboxTimeoutNs) {
+                if (error_word) atomicMax(error_word, (stamp << 8) | (what << 4) | (unsigned long long)threadIdx.x | 0x8000000000000000ull);
+                break;
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -695,7 +715,7 @@ __global__ void __launch_bounds__(kThreads) k2_finalize_sharded(K2Args a, ShardC
     __shared__ double s_out[32];
     __shared__ double s_tmp[kWarps];
     Mailbox* own = sc.mail[sc.rank];
-    mailbox_wait(own->flag_rec, sc.n_shards, sc.stamp);
+    mailbox_wait(own->flag_rec, sc.n_shards, sc.stamp, &own->error, 1);
     a.parts = &own->rec[0][0];
     a.n_parts = sc.n_shards;
     a.rec_stride = 32;
@@ -1111,6 +1131,7 @@ __global__ void __launch_bounds__(kThreads) k3a_sum_ranges(const Ctrl* ctrl, con
                                                           unsigned long long* total_out, int force) {
     __shared__ unsigned long long s_tot[kWarps];
     unsigned long long t = 0;
+    rtot += (size_t)ctrl->rsum_sel * kRsumStride;
     if (force || ctrl->do_resample)
         for (int i = threadIdx.x; i < n_ranges; i += kThreads) t += rtot[i];
     t = warp_sum(t);
@@ -1332,7 +1353,7 @@ k3_resample(K3Args<real> a, FM fm) {
         const unsigned long long* totals = a.totals;
         if (a.shard.mail) {   // every rank's weight total of this step must have arrived in the own mailbox
             Mailbox* own = a.shard.mail[a.shard.rank];
-            mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp);
+            mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp, &own->error, 2);
             totals = own->tot;
         }
         unsigned long long part = 0, all = 0;
@@ -1997,7 +2018,7 @@ __global__ void __launch_bounds__(kThreads) k_finish_step_sharded(Ctrl* ctrl, Fi
     __shared__ double s_w[kWarps][16];
     __shared__ double s_m[16];
     Mailbox* own = sc.mail[sc.rank];
-    mailbox_wait(own->flag_mom, sc.n_shards, sc.stamp);
+    mailbox_wait(own->flag_mom, sc.n_shards, sc.stamp, &own->error, 3);
     f.mom_parts = &own->mom[0][0];
     f.n_mom_parts = sc.n_shards;
     f.mom_stride = 16;
@@ -2241,8 +2262,10 @@ struct Launch {
 #ifndef SMC_USE_PDL
 #define SMC_USE_PDL 0
 #endif
+static unsigned long long g_launch_count = 0;     // (host threads of one process share the engine's stream in practice)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    __atomic_add_fetch(&g_launch_count, 1ull, __ATOMIC_RELAXED);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -2674,6 +2697,7 @@ int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const doub
 extern "C" {
 
 int smc_abi_version(void) { return SMC_ABI_VERSION; }
+uint64_t smc_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 const char* smc_last_error(void) { return smc::g_err; }
 uint64_t smc_sizeof_sir_desc(void) { return sizeof(smc_sir_desc); }
 int64_t smc_partial_stride(int32_t nx) { return partial_stride(nx); }
@@ -3071,6 +3095,7 @@ int smc_sir_step_fused(const smc_sir_desc* d, void* logw_out_dev, int32_t model_
 
 // ---- multi-GPU: whole sharded step with mailbox exchanges (no collective calls) ----------------
 uint64_t smc_mailbox_bytes(void) { return sizeof(Mailbox); }
+uint64_t smc_mailbox_error_offset(void) { return offsetof(Mailbox, error); }
 
 int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t model_id, const double* params_host,
                          int32_t n_params, const double* z_dev, double resample_thresh, uint64_t seed, int64_t t,

@@ -19,7 +19,8 @@ Two ways the state-space model reaches the GPU:
 Extra keyword-only constructor arguments (additive): ``dtype`` ("f64" parity,
 "f32" throughput), ``noise`` ("reference": draws come from ``rng`` in the
 reference's call order and are uploaded; "philox": on-chip Philox4x32-10 keyed
-by ``seed``), ``seed``, ``device``.
+by ``seed``), ``seed``, ``device``, ``record_ancestors``, ``engine`` (adopt an
+existing :class:`~particle_filters_b200.engine.SirEngine`).
 """
 
 from __future__ import annotations
@@ -106,6 +107,7 @@ class ParticleFilter:
         seed: Optional[int] = None,
         device=None,
         record_ancestors: bool = False,
+        engine=None,
     ) -> None:
         self.g = g
         self.h = h
@@ -130,7 +132,17 @@ class ParticleFilter:
         self._dtype, self._noise, self._device = dtype, noise, device
         self._seed = int(self.rng.integers(0, 2 ** 63 - 1)) if (seed is None and noise == "philox") else int(seed or 0)
         self._spec = spec_of(g, h)
-        self._eng = None            # device-resident engine (spec models)
+        # device-resident engine (spec models).  ``engine=``: adopt an existing SirEngine of the right shape
+        # (its particle arrays stay where they are -- e.g. a 2^26-particle population that is already resident)
+        self._eng = None
+        if engine is not None:
+            if self._spec is None:
+                raise ValueError("engine= needs a spec model (g/h bound to a particle_filters_b200.ssm object)")
+            if (engine.n, engine.nx, engine.nz) != (self.Np, self.nx, self.nz) or \
+                    engine.npdtype != (np.float32 if dtype == "f32" else np.float64):
+                raise ValueError("engine= does not match this filter's (Np, nx, nz, dtype)")
+            self._eng = engine
+            self._functor = self._spec.device_functor(self.Q, self.R)
         self._bridge = {}           # bridge engines by particle count
         self._generation = 0
         self._t_phil = 0            # Philox step counter

@@ -1,24 +1,29 @@
 """Sharded SIR filter: one process per GPU, particles split into contiguous shards.
 
-SURVEY.md section 8e.  Per step every rank runs the fused propagate+likelihood kernel on
-its shard (Philox is keyed by the GLOBAL particle id), then
+SURVEY.md section 8e.  Rank r owns the global particle indices [r N / G, (r + 1) N / G) of both the
+inputs and the outputs of every step; Philox is keyed by the GLOBAL particle id and the resampling CDF
+is an exact integer scan, so a G-shard run selects the same ancestors as the single-GPU run.
 
-1. all-gather of ONE partial record per rank (max, sum e, sum e^2, weighted moments);
-   every rank reduces the G records in rank order -> identical log normaliser, ESS,
-   resampling decision and systematic uniform everywhere;
-2. all-gather of the shards' fixed-point weight totals (uint64); the exclusive prefix of
-   the lower ranks is this shard's CDF offset (integer arithmetic: the global CDF is
-   bit-identical to the single-GPU one);
-3. the resampling kernel stores every output particle straight into the buffer of the
-   rank that owns its index over NVLink (peer pointers obtained through CUDA IPC), so the
-   gather and the cross-shard ancestor migration are one kernel -- only particles whose
-   ancestor lives on another shard cross the link;
-4. all-gather of the post-resample moment record, which doubles as the barrier that orders
-   the peer stores before the next step.
+``exchange="mailbox"`` (default): no collective call in the step.  Every rank owns a mailbox in
+peer-mapped memory (CUDA IPC); the last CTA of the producing kernel stores the rank's record straight
+into the mailbox of EVERY rank over NVLink and raises a stamped flag there, the consuming kernel spins
+(bounded: 20 s, then an error word is set) on the flags in its own memory:
+
+1. partial record (max, sum e, sum e^2, weighted moments): last CTA of K1 -> ``k2_finalize_sharded``,
+   which reduces the G records in rank order (identical normaliser / ESS / decision / u everywhere);
+2. fixed-point weight total: last CTA of the range pre-pass -> prologue of the resampler; the exclusive
+   prefix over the lower ranks is this shard's CDF offset, the sum over all ranks the CDF total the
+   stratified positions are laid over;
+3. the resampling kernel stores every output particle into the buffer of the rank that owns its index
+   (NVLink peer stores for the few that cross a shard boundary) -- gather and cross-shard migration are
+   one kernel; its last CTA publishes the post-resample moment record, whose flag also certifies that all
+   migrated particles have landed -> ``k_finish_step_sharded``.
+
+``exchange="nccl"``: the same kernels with three NCCL all-gathers per step instead (baseline).
 
 No host synchronisation happens inside the step loop.  The pure-host helpers at the top
-(`combine_partial_records`, `shard_offsets`, `migration_plan`) restate the device
-arithmetic for the CPU (gloo) tests of the multi-rank logic.
+(``combine_partial_records``, ``shard_offsets``, ``migration_plan``) restate the device arithmetic for
+the CPU (gloo) tests of the multi-rank logic.
 """
 
 from __future__ import annotations
@@ -73,10 +78,14 @@ def shard_offsets(totals: List[int]) -> List[int]:
     return out
 
 
-def outputs_below(C_fix: int, u: float, n_global: int, f32: bool = False) -> int:
+def outputs_below(C_fix: int, u: float, n_global: int, f32: bool = False, total: int = 0) -> int:
     """Number of stratified positions (u + i) / N below the fixed-point CDF value C (away from
-    round-off ties this equals the device's closed form)."""
+    round-off ties this equals the device's closed form).  fp32 mode lays the positions over the ACTUAL
+    total of the fixed-point weights (csrc/sir_kernels.cu ``RhoMap``): C is first mapped to
+    floor(C N 2^32 / total)."""
     F = frac_bits_for(n_global, f32)
+    if f32 and total > 0:
+        C_fix = (int(C_fix) * n_global << 32) // int(total)
     uq = int(np.floor(np.ldexp(u, F)))
     e = (C_fix + ((1 << F) - 1 - uq)) >> F
     return int(min(max(e, 0), n_global))
@@ -90,8 +99,8 @@ def migration_plan(totals: List[int], u: float, n_global: int, f32: bool = False
     off = shard_offsets(totals) + [sum(int(t) for t in totals)]
     plan = np.zeros((G, G), dtype=np.int64)
     for s in range(G):
-        lo = outputs_below(off[s], u, n_global, f32)
-        hi = n_global if s == G - 1 else outputs_below(off[s + 1], u, n_global, f32)
+        lo = 0 if s == 0 else outputs_below(off[s], u, n_global, f32, off[-1])
+        hi = n_global if s == G - 1 else outputs_below(off[s + 1], u, n_global, f32, off[-1])
         for d in range(G):
             a, b = max(lo, d * shard), min(hi, (d + 1) * shard)
             plan[s, d] = max(0, b - a)
@@ -201,6 +210,20 @@ class ShardedSir:
         dist.all_gather_into_tensor(self.mom_all, self.mom_local)     # also orders the peer stores
         eng.finish_step(row=row, mom_parts=self.mom_all, n_mom_parts=self.G)
 
+    def check(self):
+        """Raise if a flag wait on this rank timed out (a peer never published: it failed, stepped a different
+        number of times, or died).  Synchronises the stream."""
+        if self.exchange != "mailbox":
+            return
+        dev = self.torch.device("cuda", self.torch.cuda.current_device())
+        off = int(self.lib.smc_mailbox_error_offset())
+        word = self.torch.as_tensor(_RawCuda(self._raw[2] + off, (1,), "<i8"), device=dev)
+        v = int(word.cpu().numpy().astype(np.uint64)[0])
+        if v:
+            what = {1: "partial record", 2: "weight total", 3: "moment record"}.get((v >> 4) & 0xF, "?")
+            raise _lib.SmcError(f"rank {self.rank}: timed out waiting for the {what} of rank {v & 0xF} "
+                                f"(stamp {(v >> 8) & ((1 << 55) - 1)}); the sharded filter state is invalid")
+
     def shard_totals(self) -> np.ndarray:
         """The G fixed-point weight totals of the last resampling step (rank order), as Python ints."""
         if self.exchange == "nccl":
@@ -233,9 +256,12 @@ def init_distributed():
 
 
 def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC, UNIT):
-    """bench.py's N > 1 arm: BASELINE config 3 (SV, N = 2^26 total) sharded over the ranks."""
+    """bench.py's N > 1 arm: BASELINE config 3 (SV, N = 2^26 total) sharded over the ranks (strong scaling),
+    preceded by a parity self-check against the single-GPU engine on rank 0 and followed by a weak-scaling
+    sub-record (2^26 particles PER GPU)."""
     import torch
 
+    from .engine import SirEngine
     from .ssm import StochVolSSM
 
     dist = init_distributed()
@@ -246,25 +272,69 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     Q, R = np.array([[SIGMA ** 2]]), np.array([[BETA ** 2]])
     mid, params = StochVolSSM(ALPHA, BETA).device_functor(Q, R)
     Y = sv_observations(W + K + 2)
-    sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=W + K + 2, exchange=getattr(args, "exchange", "mailbox"))
-    sh.eng.init_gaussian(np.zeros(1), np.array([[SIGMA / np.sqrt(1 - ALPHA ** 2)]]), 42)
-    sh.eng.set_observations(Y.reshape(-1, 1))
     thresh, seed = 2.0, 42
-    for k in range(W):
-        sh.step(mid, params, thresh, k, seed, k, k)
-    torch.cuda.synchronize()
+    L0 = np.array([[SIGMA / np.sqrt(1 - ALPHA ** 2)]])
+
+    def timed_run(n_total, k_steps):
+        sh = ShardedSir(n_total, 1, 1, dtype="f32", trace_len=W + k_steps + 2, exchange=getattr(args, "exchange", "mailbox"))
+        sh.eng.init_gaussian(np.zeros(1), L0, seed)
+        sh.eng.set_observations(Y.reshape(-1, 1))
+        for k in range(W):
+            sh.step(mid, params, thresh, k, seed, k, k)
+        torch.cuda.synchronize()
+        return sh
+
+    # ---- parity: the first W statistic rows and the particle set after W steps vs ONE GPU, same N and seed ----
+    sh = timed_run(N, K)
+    rows_w = sh.eng.trace[:W].cpu().numpy()
+    local = sh.eng.get_particles()[:, 0]
+    gathered = [None] * G
+    dist.all_gather_object(gathered, local)
+    parity = None
+    if rank == 0:
+        ref = SirEngine(N, 1, 1, dtype="f32", trace_len=W)
+        ref.init_gaussian(np.zeros(1), L0, seed)
+        ref.set_observations(Y[:W].reshape(-1, 1))
+        ref.enqueue(mid, params, W, thresh, seed, fused=False)
+        rrows = ref.trace[:W].cpu().numpy()
+        xref = ref.get_particles()[:, 0]
+        xsh = np.concatenate(gathered)
+        parity = {"steps_compared": W, "reference": "single-GPU three-launch engine, same N and seed, on rank 0",
+                  "identical_particle_fraction": float(np.mean(xsh == xref)),
+                  "decisions_equal": bool(np.array_equal(rows_w[:, 2], rrows[:, 2])),
+                  "uniforms_equal": bool(np.array_equal(rows_w[:, 3], rrows[:, 3])),
+                  "max_abs_log_norm_diff": float(np.max(np.abs(rows_w[:, 0] - rrows[:, 0]))),
+                  "max_rel_ess_diff": float(np.max(np.abs(rows_w[:, 1] - rrows[:, 1]) / rrows[:, 1])),
+                  "max_abs_mean_diff": float(np.max(np.abs(rows_w[:, 4] - rrows[:, 4])))}
+        parity["pass"] = bool(parity["decisions_equal"] and parity["uniforms_equal"] and
+                              parity["identical_particle_fraction"] > 0.999 and parity["max_abs_log_norm_diff"] < 1e-9
+                              and parity["max_rel_ess_diff"] < 1e-9 and parity["max_abs_mean_diff"] < 1e-6)
+        del ref, xref, xsh
+        torch.cuda.empty_cache()
+    del gathered, local
+
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         clocks.start()
-        time.sleep(0.3)           # let the sampler take its first reading before the timed region
+    # keep every GPU on the workload while the sampler takes its first readings (outside the timed region); a FIXED
+    # number of steps -- every rank must issue the same sequence of stamps
+    for kk in range(4000):
+        sh.step(mid, params, thresh, W, seed, W + kk, W)
+        if kk % 256 == 255:
+            torch.cuda.synchronize()
+    flag = torch.zeros(1, device="cuda")
+    dist.all_reduce(flag)                       # ranks leave the spin at different times: line them up
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib = _lib.load()
+    launches0 = int(lib.smc_launch_count())
     e0.record()
     for k in range(W, W + K):
         sh.step(mid, params, thresh, k, seed, k, k)
     e1.record()
     torch.cuda.synchronize()
+    launches = int(lib.smc_launch_count()) - launches0
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -283,11 +353,37 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     dist.barrier()
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    rows = sh.eng.trace[: W + K].cpu().numpy()
+    rows = sh.eng.trace[W: W + K].cpu().numpy()
     clk = clocks.stop() if rank == 0 else None
-    ok = bool(np.all(np.isfinite(rows[:, :5])) and np.all(rows[W:, 2] == 1.0))
+    sh.check()
+    ok = bool(np.all(np.isfinite(rows[:, :5])) and np.all(rows[:, 2] == 1.0))
+    sh.close()
+
+    # ---- weak scaling: 2^log2n particles PER GPU ----------------------------------------------------------
+    weak = None
+    if not getattr(args, "no_weak", False) and N * G <= (1 << 30):
+        Kw = min(K, 50)
+        shw = timed_run(N * G, Kw)
+        dist.barrier()
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for k in range(W, W + Kw):
+            shw.step(mid, params, thresh, k, seed, k, k)
+        w1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        msw = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(msw, op=dist.ReduceOp.MAX)
+        wrows = shw.eng.trace[W: W + Kw].cpu().numpy()
+        weak = {"n_particles_total": N * G, "n_particles_per_gpu": N, "steps": Kw, "ms_per_step": float(msw.item()) / Kw,
+                "value": N * G / (float(msw.item()) / Kw * 1e-3), "unit": UNIT,
+                "finite": bool(np.all(np.isfinite(wrows[:, :5])))}
+        shw.close()
+
     peak, peak_src = measured_peak()
     value = N / (ms_step * 1e-3)
+    step_bytes = 28.0        # the sharded step is the three-launch form: K1 12 B + range pre-pass 4 B + resampler 12 B
     if rank == 0:
         assert ok, "non-finite statistics in the sharded run"
         line = {
@@ -304,15 +400,16 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
             "clocks": clk,
             "e2e": {"value": N / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": 8,
                     "d2h_bytes_per_step": 8 * int(sh.eng.stride), "ms_per_step": float(e2e_dt.item()) * 1e3},
-            "gpu_launches": (5 if sh.exchange == "mailbox" else 7) * K,
-            "roofline": {"bound": "hbm", "kernel": "whole step (per-kernel split is taken at N=1)",
-                         "achieved": 24.0 * value / 1e9 / G, "peak": peak, "unit": "GB/s",
-                         "frac": 24.0 * value / 1e9 / G / peak, "traffic": None, "peak_source": peak_src},
-            "roofline_step": {"alg_bytes_per_particle_update": 32.0, "achieved": 32.0 * value / 1e9,
-                              "peak": peak * G, "unit": "GB/s", "frac": 32.0 * value / 1e9 / (peak * G)},
+            "gpu_launches": launches, "parity": parity, "weak_scaling": weak,
+            "roofline": {"bound": "hbm", "kernel": "whole sharded step (per-kernel split is taken at N=1)",
+                         "achieved": step_bytes * value / 1e9 / G, "peak": peak, "unit": "GB/s",
+                         "frac": step_bytes * value / 1e9 / G / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_moved_per_particle_update": step_bytes},
+            "roofline_step": {"bytes_moved_per_particle_update": step_bytes, "achieved": step_bytes * value / 1e9,
+                              "peak": peak * G, "unit": "GB/s", "frac": step_bytes * value / 1e9 / (peak * G),
+                              "contract_bytes_per_particle_update": 32.0},
             "cpu_baseline": None,
             "filter": {"mean_last": float(rows[-1, 4]), "ess_last": float(rows[-1, 1])},
         }
         print(json.dumps(line))
-    sh.close()
     dist.destroy_process_group()

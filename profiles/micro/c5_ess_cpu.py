@@ -26,6 +26,12 @@ def scenario(name, K):
         P0 = np.kron(np.eye(4), np.diag([1.0, 1.0, 0.01, 0.01]))
         m0 = np.linalg.solve(am.F, X[0])
         return am, X, Z, m0, P0
+    if name == "article":        # tests/golden/bench_c5_acoustic.npz: the reference simulator + notebook model
+        g = np.load(os.path.join(REPO, "tests", "golden", "bench_c5_acoustic.npz"))
+        am = AcousticCVModel(n_targets=4, psi=float(g["psi"]), d0=float(g["d0"]), Q1=g["Q"][:4, :4], sensors=g["S"],
+                             r_var=float(g["R"][0, 0]))
+        K = min(K, g["Z"].shape[0] - 1)
+        return am, g["X_true"][1:K + 1].reshape(K, 16), g["Z"][1:K + 1], g["mean0"], g["P0"]
     raise SystemExit("unknown scenario")
 
 

@@ -147,17 +147,18 @@ class AcousticCVModel:
     """
 
     def __init__(self, n_targets=1, grid=(3, 3), area=(40.0, 40.0), psi=10.0, d0=0.1,
-                 q_scale=1.0, r_var=0.01):
+                 q_scale=1.0, r_var=0.01, Q1=None, sensors=None):
         self.n_targets = n_targets
         self.nx = 4 * n_targets
         gx = np.linspace(0.0, area[0], grid[0])
         gy = np.linspace(0.0, area[1], grid[1])
-        self.S = np.array([[a, b] for a in gx for b in gy])
+        self.S = np.array([[a, b] for a in gx for b in gy]) if sensors is None else np.asarray(sensors, float)
         self.nz = self.S.shape[0]
         self.psi, self.d0 = psi, d0
         F1 = np.array([[1, 0, 1, 0], [0, 1, 0, 1], [0, 0, 1, 0], [0, 0, 0, 1.0]])
-        Q1 = q_scale * np.array([[3.0, 0, 0.1, 0], [0, 3.0, 0, 0.1], [0.1, 0, 0.03, 0],
-                                 [0, 0.1, 0, 0.03]])
+        if Q1 is None:
+            Q1 = q_scale * np.array([[3.0, 0, 0.1, 0], [0, 3.0, 0, 0.1], [0.1, 0, 0.03, 0],
+                                     [0, 0.1, 0, 0.03]])
         self.F = np.kron(np.eye(n_targets), F1)
         self.Q = np.kron(np.eye(n_targets), Q1)
         self.R = r_var * np.eye(self.nz)
