@@ -2659,7 +2659,9 @@ template <class Model>
 int launch_fused(const Launch& l, const Model& m, void* logw_out_dev, const double* z_dev, double resample_thresh,
                  uint64_t seed, int64_t t, double* stats_prev_dev, double* stats_row_dev, int phases) {
     const smc_sir_desc* d = l.d;
-    const bool legacy = fused_legacy();
+    // nx = 2: K5 holds two tiles + two windows per CTA (94 KB, 2 CTAs per SM, 116 registers) and measured 0.201 ms
+    // per 2^24 step against 0.152 ms of round 1's pipeline, which therefore still serves nx = 2
+    const bool legacy = fused_legacy() || Model::NX >= 2;
     if (phases & 1) {
         FinishArgs f;
         memset(&f, 0, sizeof(f));

@@ -102,22 +102,37 @@ class PFState:
 
 
 class DeviceLedhState(PFState):
-    """``PFState`` of a device-resident LEDH run: particles / weights are fetched on access."""
+    """``PFState`` of a device-resident LEDH run: particles / weights are fetched on first access.
+
+    The arrays live in the owner's engine until then, so a state is only readable while it is the owner's
+    LATEST one: once the filter has stepped again, an unread state raises instead of silently returning the
+    newer step's particles (the reference returns independent arrays per state -- read ``.particles`` /
+    ``.weights`` before the next ``step`` to keep them)."""
 
     def __init__(self, owner, mean, cov, diagnostics):
-        self._owner = owner
+        self._owner, self._gen = owner, owner._generation
         self._particles = self._weights = None
         self.mean, self.cov, self.diagnostics = mean, cov, diagnostics
+
+    def _is_current(self) -> bool:
+        return self._gen == self._owner._generation
+
+    def _check(self):
+        if not self._is_current():
+            raise RuntimeError("stale LEDH PFState: the filter has stepped since this state was returned; read "
+                               ".particles/.weights before the next step() to keep them")
 
     @property
     def particles(self):
         if self._particles is None:
+            self._check()
             self._particles = self._owner._dev_eng.get_particles()
         return self._particles
 
     @property
     def weights(self):
         if self._weights is None:
+            self._check()
             self._weights = self._owner._dev_eng.weights()
         return self._weights
 
@@ -191,6 +206,7 @@ class LEDHFlowPF:
             self._meas = self._spec.meas
         self._flow = {}
         self._dev_eng = None
+        self._generation = 0        # bumped by every device-resident step (see DeviceLedhState)
         self._seed = 0
         self._t = 0
 
@@ -323,8 +339,12 @@ class LEDHFlowPF:
         lib = _lib.load()
         nx, nz = sp.nx, sp.nz
         z_k = np.asarray(z_k, float).reshape(-1)
-        resident = isinstance(state, DeviceLedhState) and state._owner is self and state._particles is None \
-            and state._weights is None
+        # the engine still holds exactly this state: it is ours, it is the latest one, and nobody has taken (and
+        # possibly modified) its arrays
+        resident = isinstance(state, DeviceLedhState) and state._owner is self and state._is_current() \
+            and state._particles is None and state._weights is None
+        if isinstance(state, DeviceLedhState) and not resident and state._particles is None:
+            state._check()          # stale and never read: its arrays are gone
         N = self.cfg.n_particles if resident else np.asarray(state.particles).shape[0]
         if self._dev_eng is None or self._dev_eng.n != N:
             self._dev_eng = SirEngine(N, nx, nz, dtype=self._dtype, device=self._device, write_ancestors=True,
@@ -389,6 +409,7 @@ class LEDHFlowPF:
         cond = [float(np.linalg.cond(s0[j])) for j in range(n_steps)]
         self.last_ess = float(row[1])
         self.last_resampled = bool(row[2])
+        self._generation += 1
         return DeviceLedhState(self, mean, cov, {"condition_numbers": cond})
 
     # ------------------------------------------------------------------ helpers

@@ -242,8 +242,10 @@ class ScriptedTracker:
         return np.zeros(self.nx)
 
 
-def gen_ledh():
+def gen_ledh(only=None):
     def run(tag, model, *, N, L, T, ess_ratio, seed, mean0, cov0, x_true0, with_noise):
+        if only is not None and tag not in only:
+            return
         rng = np.random.default_rng(seed)
         nx, nz = model.nx, model.nz
         # scripted covariances: SPD, slowly contracting, slightly asymmetric (exercises :106)
@@ -295,6 +297,14 @@ def gen_ledh():
         mean0=np.array([12.0, 14.0, 0.5, -0.3, 30.0, 25.0, -0.4, 0.2]),
         cov0=np.diag([4.0, 4.0, 0.25, 0.25] * 2),
         x_true0=np.array([12.5, 13.0, 0.6, -0.2, 29.0, 26.0, -0.5, 0.3]), with_noise=False)
+    # BASELINE config 5's shape: 4 targets, 16-D joint state, 5 x 5 = 25 sensors, the article's process noise
+    # (simulator_Multi_acoustic_tracking.py:104), R = 0.01 I, L = 8 -- pins the compile-time 16 x 25 flow kernel
+    V1 = (1.0 / 20.0) * np.array([[1 / 3, 0, 0.5, 0], [0, 1 / 3, 0, 0.5], [0.5, 0, 1, 0], [0, 0.5, 0, 1.0]])
+    ac4 = AcousticCVModel(n_targets=4, grid=(5, 5), Q1=V1)
+    x4 = np.array([12.0, 6.0, 0.001, 0.001, 32.0, 32.0, -0.001, -0.005, 20.0, 13.0, -0.1, 0.01, 15.0, 35.0, 0.002, 0.002])
+    run("acoustic4", ac4, N=64, L=8, T=3, ess_ratio=0.5, seed=15,
+        mean0=x4 + np.tile([0.8, -0.6, 0.05, -0.05], 4), cov0=np.diag([1.0, 1.0, 0.05, 0.05] * 4),
+        x_true0=x4, with_noise=True)
 
 
 class ScriptedMeanTracker(ScriptedTracker):
@@ -388,6 +398,9 @@ def gen_rng_checksum():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--ledh-only":      # regenerate selected LEDH cases only
+        gen_ledh(only=set(sys.argv[2].split(",")))
+        sys.exit(0)
     gen_resample()
     gen_sir()
     gen_l96()

@@ -223,6 +223,13 @@ class AcousticCVModel:
         return -0.5 * (np.einsum("ni,ij,nj->n", d, self._Rinv, d) + self._logdet2piR)
 
 
+def acoustic_c5_model():
+    """BASELINE config 5's model shape: 4 targets (16-D joint state), 5 x 5 = 25 sensors, the article's process
+    noise V (reference simulator_Multi_acoustic_tracking.py:104), R = 0.01 I."""
+    V1 = (1.0 / 20.0) * np.array([[1 / 3, 0, 0.5, 0], [0, 1 / 3, 0, 0.5], [0.5, 0, 1, 0], [0, 0.5, 0, 1.0]])
+    return AcousticCVModel(n_targets=4, grid=(5, 5), Q1=V1)
+
+
 class Linear1DModel:
     """1-D linear system of the LEDH unit tests (tests/unit_tests/models/test_ledh_flow_pf.py:63-113)."""
 

@@ -9,7 +9,7 @@ import pytest
 from oracle import ledh_weighted_stats
 from oracle.ledh_numpy import ledh_flow
 from parity import assert_ancestors
-from ssm_zoo import AcousticCVModel, Linear1DModel
+from ssm_zoo import AcousticCVModel, Linear1DModel, acoustic_c5_model
 
 pytestmark = pytest.mark.gpu
 
@@ -39,6 +39,8 @@ def _cases():
         ("ledh_linear1d_resample.npz", Linear1DModel(), 1e-8, "linear"),
         ("ledh_acoustic1.npz", AcousticCVModel(n_targets=1, grid=(3, 3)), 1e-8, "acoustic"),
         ("ledh_acoustic2.npz", AcousticCVModel(n_targets=2, grid=(4, 4)), 2e-5, "acoustic"),
+        # BASELINE config 5's shape: pins k4_ledh_flow_fast<16, 25> to the unmodified reference
+        ("ledh_acoustic4.npz", acoustic_c5_model(), 2e-5, "acoustic"),
     ]
 
 
@@ -231,3 +233,74 @@ def test_ledh_shapes_small_and_odd_dims(N, nx, nz):
         outs.append(st)
     np.testing.assert_allclose(outs[0].particles, outs[1].particles, rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(outs[0].weights, outs[1].weights, rtol=1e-7, atol=1e-12)
+
+
+def _c5_filter(dtype, N, L=8, seed=3):
+    from particle_filters_b200 import AcousticMeasurement, LEDHConfig, LEDHFlowPF
+    from particle_filters_b200.ssm import LedhGaussianSSM
+
+    am = acoustic_c5_model()
+    ssm = LedhGaussianSSM(am.F, am.Q, AcousticMeasurement(am.S, am.psi, am.d0, n_targets=4), am.R)
+    P = np.kron(np.eye(4), np.diag([1.0, 1.0, 0.05, 0.05]))
+    tracker = ScriptedTracker([P + am.Q] * 8, am.nx)
+    f = LEDHFlowPF(tracker, ssm.g, ssm.h, ssm.jacobian_h, ssm.log_trans_pdf, ssm.log_like_pdf, am.R,
+                   LEDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=0.0, rng=np.random.default_rng(seed)),
+                   dtype=dtype)
+    return f, am, ssm
+
+
+def test_c5_shape_fp32_weights_track_fp64_weights():
+    """BASELINE config 5's shape (16-D, 25 sensors, R = 0.01 I): the fp32 flow must not corrupt the WEIGHTS -- the
+    Gaussian terms multiply errors of eta by Q^-1 and R^-1 = 100.  One device-resident step from the same
+    particles and the same process noise in both precisions: log-weights of every particle that matters agree
+    to 0.05 and the ESS to 10 %."""
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ledh_acoustic4.npz"))
+    from particle_filters_b200.ledh_particle_filter import PFState
+
+    N = 4096
+    rng = np.random.default_rng(8)
+    am = acoustic_c5_model()
+    x_true = np.array([12.0, 6.0, 0.001, 0.001, 32.0, 32.0, -0.001, -0.005, 20.0, 13.0, -0.1, 0.01, 15.0, 35.0, 0.002, 0.002])
+    x0 = x_true + rng.standard_normal((N, 16)) * np.tile([0.7, 0.7, 0.1, 0.1], 4)
+    w0 = np.full(N, 1.0 / N)
+    z = am.h(am.F @ x_true) + 0.1 * rng.standard_normal(am.nz)
+    V = rng.standard_normal((N, 16)) @ np.linalg.cholesky(am.Q).T
+    out = {}
+    for dtype in ("f64", "f32"):
+        f, _, _ = _c5_filter(dtype, N)
+        mean0, cov0 = ledh_weighted_stats(x0, w0)
+        st = f.step(PFState(particles=x0, weights=w0, mean=mean0, cov=cov0, diagnostics={}), z, None, lambda n_, d_: V)
+        out[dtype] = (np.asarray(st.weights).copy(), np.asarray(st.particles).copy(), f.last_ess)
+    w64, x64, ess64 = out["f64"]
+    w32, x32, ess32 = out["f32"]
+    assert abs(w64.sum() - 1) < 1e-9 and abs(w32.sum() - 1) < 1e-6
+    keep = w64 > 1e-6 * w64.max()                               # the particles that carry the estimate
+    assert keep.sum() >= 5
+    dlog = np.abs(np.log(w32[keep]) - np.log(w64[keep]))
+    assert dlog.max() < 0.05, (dlog.max(), keep.sum())
+    assert abs(ess32 - ess64) <= 0.1 * ess64 + 0.5, (ess32, ess64)
+    scale = np.maximum(1.0, np.abs(x64))
+    assert np.percentile(np.abs(x32 - x64) / scale, 99) < 2e-4
+    del g
+
+
+def test_device_ledh_state_is_generation_checked():
+    """A device-resident LEDH state is readable only while it is the filter's latest one: an unread
+    state of an earlier step must raise instead of returning the newer step's arrays; a state read in time
+    keeps its own arrays."""
+    N = 512
+    f, am, _ = _c5_filter("f64", N)
+    rng = np.random.default_rng(1)
+    x_true = np.array([12.0, 6.0, 0.0, 0.0, 32.0, 32.0, 0.0, 0.0, 20.0, 13.0, 0.0, 0.0, 15.0, 35.0, 0.0, 0.0])
+    st0 = f.init_from_gaussian(x_true, np.kron(np.eye(4), np.diag([0.5, 0.5, 0.01, 0.01])))
+    z = am.h(am.F @ x_true)
+    s1 = f.step(st0, z, None, "philox")
+    p1 = s1.particles.copy()                    # read in time: cached
+    s2 = f.step(s1, z, None, "philox")          # s1 was read -> re-uploaded, fine
+    s3 = f.step(s2, z, None, "philox")          # s2 unread and current -> stays resident
+    np.testing.assert_array_equal(s1.particles, p1)              # s1 still returns ITS arrays
+    with pytest.raises(RuntimeError, match="stale"):
+        _ = s2.particles                        # s2 was never read and the filter has moved on
+    assert s3.particles.shape == (N, 16) and abs(s3.weights.sum() - 1) < 1e-9
+    with pytest.raises(RuntimeError, match="stale"):
+        f.step(s2, z, None, "philox")           # stepping from a lost state must not silently use newer arrays

@@ -11,7 +11,7 @@ import pytest
 
 from oracle import (SIROracle, ledh_step, systematic_ancestors, systematic_ancestors_loop)
 from oracle.build import c_systematic_ancestors
-from ssm_zoo import AcousticCVModel, LGSSMModel, Linear1DModel, SVModel, Lorenz96Model
+from ssm_zoo import acoustic_c5_model, AcousticCVModel, LGSSMModel, Linear1DModel, SVModel, Lorenz96Model
 
 
 def test_golden_rng_stream_is_stable(golden):
@@ -99,6 +99,8 @@ def test_sir_oracle_reproduces_reference_run(golden, name, model):
     # stiff case: cond(S) up to 6e4 and a near-degenerate weight set amplify the
     # batched-vs-looped LAPACK round-off to ~3e-8 relative
     ("ledh_acoustic2.npz", AcousticCVModel(n_targets=2, grid=(4, 4)), 1e-6),
+    # BASELINE config 5's shape (16-D state, 25 sensors, R = 0.01 I): the stiffest case
+    ("ledh_acoustic4.npz", acoustic_c5_model(), 1e-6),
 ])
 def test_ledh_oracle_reproduces_reference_steps(golden, name, model, tol):
     g = golden(name)
