@@ -273,7 +273,7 @@ def test_c5_shape_fp32_weights_track_fp64_weights():
         out[dtype] = (np.asarray(st.weights).copy(), np.asarray(st.particles).copy(), f.last_ess)
     w64, x64, ess64 = out["f64"]
     w32, x32, ess32 = out["f32"]
-    assert abs(w64.sum() - 1) < 1e-9 and abs(w32.sum() - 1) < 1e-6
+    assert abs(w64.sum() - 1) < 1e-9 and abs(w32.sum() - 1) < 1e-4, (w64.sum(), w32.sum())   # fp32 log-weights
     keep = w64 > 1e-6 * w64.max()                               # the particles that carry the estimate
     assert keep.sum() >= 5
     dlog = np.abs(np.log(w32[keep]) - np.log(w64[keep]))
