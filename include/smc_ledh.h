@@ -28,7 +28,8 @@ enum {
 typedef struct smc_ledh_desc {
     int64_t n;             /* particles                                                            */
     int64_t ld;            /* row stride of the SoA arrays (multiple of 4, >= n)                   */
-    int32_t nx, nz;        /* 1 <= nx, nz <= 32                                                    */
+    int32_t nx, nz;        /* 1 <= nx, nz <= 512: up to 32 the per-particle matrices live in registers /
+                            * shared memory, beyond that in a global-memory workspace (smc_ledh_flow*)   */
     int32_t dtype;         /* SMC_F32 | SMC_F64                                                    */
     int32_t n_lambda_steps;
     void *eta0_dev;        /* in : nx rows, propagated particles eta_0            (:113-115)       */

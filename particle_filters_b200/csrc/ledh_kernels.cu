@@ -11,8 +11,9 @@
 
 namespace smc {
 
-constexpr int kLedhMaxDim = 32;
-constexpr int kLedhWarps = 4;     // particles (warps) per CTA
+constexpr int kLedhMaxDim = 32;      // shared-memory / register kernels (and the device-resident linear-Gaussian pieces)
+constexpr int kLedhBigMaxDim = 512;  // flow kernel with its matrices in a global-memory workspace
+constexpr int kLedhWarps = 4;        // particles (warps) per CTA
 
 // per-CTA constants staged once into shared memory
 template <typename real> struct LedhShared {
@@ -182,28 +183,37 @@ template <typename real> struct LedhArgs {
     int64_t n, ld;
     int nx, nz, n_hp, kind, L, step0;
     double lam0, dlam;                          // supplied mode: one step at lam0 (L = 1)
+    real* gws;                                  // global-memory workspace (dimensions beyond shared memory), else null
 };
 
-template <typename real>
+// GWS = false: constants and per-warp matrices in shared memory, one particle per warp, grid = particles / 4.
+// GWS = true : the same code with every matrix in a global-memory workspace (nx, nz up to 512: the reference's
+//              64-, 144- and 400-dimensional sensor-network notebooks) and a persistent grid -- each warp owns
+//              one workspace slot and loops over particles.  A warp only ever reads what it wrote itself (or the
+//              per-launch constants), so __syncwarp()'s memory ordering is all the coherence it needs.
+template <typename real, bool GWS>
 __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    real* sm = reinterpret_cast<real*>(smem_raw);
+    real* sm = GWS ? a.gws : reinterpret_cast<real*>(smem_raw);
     const int nx = a.nx, nz = a.nz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // block-shared constants
+    // block-shared constants (GWS: one global copy, written by CTA 0's launch-mate kernel below)
     real* sP = sm;            sm += nx * nx;
     real* sR = sm;            sm += nz * nz;
     real* sRinv = sm;         sm += nz * nz;
     real* sz = sm;            sm += nz;
     real* shp = sm;           sm += a.n_hp;
-    for (int i = tid; i < nx * nx; i += blockDim.x) sP[i] = (real)a.P[i];
-    for (int i = tid; i < nz * nz; i += blockDim.x) { sR[i] = (real)a.R[i]; sRinv[i] = (real)a.Rinv[i]; }
-    for (int i = tid; i < nz; i += blockDim.x) sz[i] = (real)a.z[i];
-    for (int i = tid; i < a.n_hp; i += blockDim.x) shp[i] = (real)a.hp[i];
-    __syncthreads();
+    if (!GWS) {
+        for (int i = tid; i < nx * nx; i += blockDim.x) sP[i] = (real)a.P[i];
+        for (int i = tid; i < nz * nz; i += blockDim.x) { sR[i] = (real)a.R[i]; sRinv[i] = (real)a.Rinv[i]; }
+        for (int i = tid; i < nz; i += blockDim.x) sz[i] = (real)a.z[i];
+        for (int i = tid; i < a.n_hp; i += blockDim.x) shp[i] = (real)a.hp[i];
+        __syncthreads();
+    }
     // per-warp workspace
     const int per_warp = 3 * nz * nx + nz * nz + 2 * nx * nx + 5 * nx + 3 * nz;
-    real* w = sm + warp * per_warp;
+    const int64_t slot = GWS ? (int64_t)blockIdx.x * kLedhWarps + warp : warp;
+    real* w = sm + slot * per_warp;
     real* H = w;              w += nz * nx;     // Jacobian, later S^-1 H
     real* PHt = w;            w += nx * nz;
     real* Hc = w;             w += nz * nx;     // copy of H kept for the solve right-hand side
@@ -219,8 +229,8 @@ __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a
     real* innov = w;          w += nz;
     real* rinn = w;           w += nz;
 
-    const int64_t i = (int64_t)blockIdx.x * kLedhWarps + warp;
-    if (i >= a.n) return;                         // whole warp leaves together (no block sync below)
+    const int64_t i_stride = GWS ? (int64_t)gridDim.x * kLedhWarps : a.n;
+    for (int64_t i = (int64_t)blockIdx.x * kLedhWarps + warp; i < a.n; i += i_stride) {   // whole warps (no block sync below)
     for (int d = lane; d < nx; d += 32) { eta[d] = a.eta[d * a.ld + i]; eta0[d] = a.eta0[d * a.ld + i]; }
     __syncwarp();
     real theta = a.theta[i];
@@ -296,6 +306,23 @@ __global__ void __launch_bounds__(32 * kLedhWarps) k4_ledh_flow(LedhArgs<real> a
     }
     for (int d = lane; d < nx; d += 32) a.eta[d * a.ld + i] = eta[d];
     if (lane == 0) a.theta[i] = theta;
+    __syncwarp();
+    }
+}
+// constants of the global-workspace mode, converted to `real` once per launch
+template <typename real> __global__ void k4_ledh_stage_constants(LedhArgs<real> a) {
+    real* sm = a.gws;
+    const int nx = a.nx, nz = a.nz;
+    real* sP = sm;            sm += nx * nx;
+    real* sR = sm;            sm += nz * nz;
+    real* sRinv = sm;         sm += nz * nz;
+    real* sz = sm;            sm += nz;
+    real* shp = sm;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = tid; i < nx * nx; i += nt) sP[i] = (real)a.P[i];
+    for (int i = tid; i < nz * nz; i += nt) { sR[i] = (real)a.R[i]; sRinv[i] = (real)a.Rinv[i]; }
+    for (int i = tid; i < nz; i += nt) sz[i] = (real)a.z[i];
+    for (int i = tid; i < a.n_hp; i += nt) shp[i] = (real)a.hp[i];
 }
 
 
@@ -594,14 +621,32 @@ int launch_flow(const smc_ledh_desc* d, const double* P, const double* R, const 
         SMC_LEDH_FAST(16, 25) SMC_LEDH_FAST(8, 16) SMC_LEDH_FAST(4, 9)
 #undef SMC_LEDH_FAST
     }
-    const int per_warp = 3 * nz * nx + nz * nz + 2 * nx * nx + 5 * nx + 3 * nz;
-    const size_t smem = sizeof(real) * ((size_t)nx * nx + 2 * (size_t)nz * nz + nz + a.n_hp + (size_t)kLedhWarps * per_warp);
-    SMC_REQUIRE(smem <= 227 * 1024, "smc_ledh: shared memory need %zu B exceeds 227 KiB (nx=%d nz=%d)", smem, nx, nz);
-    auto kern = k4_ledh_flow<real>;
-    SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)cdiv64(d->n, kLedhWarps);
-    kern<<<grid, 32 * kLedhWarps, smem, st>>>(a);
-    SMC_CHECK_CUDA(cudaGetLastError());
+    const size_t per_warp = 3 * (size_t)nz * nx + (size_t)nz * nz + 2 * (size_t)nx * nx + 5 * (size_t)nx + 3 * (size_t)nz;
+    const size_t n_const = (size_t)nx * nx + 2 * (size_t)nz * nz + nz + a.n_hp;
+    const size_t smem = sizeof(real) * (n_const + (size_t)kLedhWarps * per_warp);
+    a.gws = nullptr;
+    if (smem <= 227 * 1024 && nx <= kLedhMaxDim && nz <= kLedhMaxDim) {
+        auto kern = k4_ledh_flow<real, false>;
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)cdiv64(d->n, kLedhWarps);
+        kern<<<grid, 32 * kLedhWarps, smem, st>>>(a);
+        SMC_CHECK_CUDA(cudaGetLastError());
+    } else {
+        // dimensions beyond shared memory: per-warp matrices in a stream-ordered global workspace, persistent grid
+        int sms = 148, dev_id = 0;
+        if (cudaGetDevice(&dev_id) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+        int64_t grid = cdiv64(d->n, kLedhWarps);
+        if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
+        const size_t ws_elems = n_const + (size_t)grid * kLedhWarps * per_warp;
+        real* gws = nullptr;
+        SMC_CHECK_CUDA(cudaMallocAsync(&gws, ws_elems * sizeof(real), st));
+        a.gws = gws;
+        k4_ledh_stage_constants<real><<<32, 256, 0, st>>>(a);
+        SMC_CHECK_CUDA(cudaGetLastError());
+        k4_ledh_flow<real, true><<<(unsigned)grid, 32 * kLedhWarps, 0, st>>>(a);
+        SMC_CHECK_CUDA(cudaGetLastError());
+        SMC_CHECK_CUDA(cudaFreeAsync(gws, st));
+    }
     SMC_CHECK_CUDA(cudaFreeAsync(dev, st));
     return 0;
 }
@@ -609,8 +654,8 @@ int launch_flow(const smc_ledh_desc* d, const double* P, const double* R, const 
 int check_ledh(const smc_ledh_desc* d) {
     SMC_REQUIRE(d != nullptr, "smc_ledh: null descriptor");
     SMC_REQUIRE(d->n > 0 && d->ld >= d->n, "smc_ledh: bad n / ld");
-    SMC_REQUIRE(d->nx >= 1 && d->nx <= kLedhMaxDim && d->nz >= 1 && d->nz <= kLedhMaxDim,
-                "smc_ledh: dimensions must satisfy 1 <= nx, nz <= %d (got %d, %d)", kLedhMaxDim, d->nx, d->nz);
+    SMC_REQUIRE(d->nx >= 1 && d->nx <= kLedhBigMaxDim && d->nz >= 1 && d->nz <= kLedhBigMaxDim,
+                "smc_ledh: dimensions must satisfy 1 <= nx, nz <= %d (got %d, %d)", kLedhBigMaxDim, d->nx, d->nz);
     SMC_REQUIRE(d->dtype == SMC_F32 || d->dtype == SMC_F64, "smc_ledh: bad dtype");
     SMC_REQUIRE(d->eta0_dev && d->eta_dev && d->theta_log_dev, "smc_ledh: null buffer");
     return 0;
@@ -679,6 +724,7 @@ int smc_ledh_propagate_linear(const smc_ledh_desc* d, const void* x_dev, const d
                               const void* v_dev, uint64_t seed, int64_t t, void* stream) {
     if (int rc = check_ledh(d)) return rc;
     SMC_REQUIRE(x_dev && F_host && Lq_host, "smc_ledh_propagate_linear: null argument");
+    SMC_REQUIRE(d->nx <= kLedhMaxDim, "smc_ledh_propagate_linear: nx <= %d (per-thread state vectors)", kLedhMaxDim);
     SMC_REQUIRE(d->ld % 4 == 0, "smc_ledh_propagate_linear: ld must be a multiple of 4");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nx = d->nx;
@@ -710,6 +756,8 @@ int smc_ledh_gauss_terms(const smc_ledh_desc* d, const void* x_dev, const double
     if (int rc = check_ledh(d)) return rc;
     SMC_REQUIRE(x_dev && F_host && Qinv_host && Rinv_host && z_host && terms_dev && h_params_host && n_h_params > 0,
                 "smc_ledh_gauss_terms: null argument");
+    SMC_REQUIRE(d->nx <= kLedhMaxDim && d->nz <= kLedhMaxDim, "smc_ledh_gauss_terms: nx, nz <= %d (per-thread state vectors)",
+                kLedhMaxDim);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int nx = d->nx, nz = d->nz;
     const size_t cnt = 2 * (size_t)nx * nx + (size_t)nz * nz + nz + n_h_params;

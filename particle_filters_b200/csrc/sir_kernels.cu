@@ -2978,10 +2978,10 @@ int smc_sir_finish_step(const smc_sir_desc* d, double* stats_row_dev, const doub
     // POST_MOMENTS_GENERIC: the particle set was modified after K3 (regularisation jitter) or was
     // not produced by K3 at all (multinomial gather), so its moments are recomputed from memory
     const bool inl = inline_moments(d) && !(d->flags & SMC_FLAG_POST_MOMENTS_GENERIC);
-    if (!inl && !no_m && stats_row_dev && d->nx > kFusedNxMax) {
-        // high-dimensional states: one register-blocked X^T W X pass (weighted or uniform, decided on device)
+    if (!inl && !no_m && stats_row_dev && d->nx > kFusedNxMax && d->nx <= 64) {
+        // high-dimensional states: one register-blocked X^T W X pass (weighted or uniform, decided on device);
+        // beyond 64 dimensions (LEDH on 144- / 400-dimensional sensor networks) the any-nx kernel below
         SMC_REQUIRE(d->n == d->n_global, "smc: high-dimensional moments are single-shard only");
-        SMC_REQUIRE(d->nx <= 64, "smc: moments are compiled for nx <= 64");
         if (int rc = (d->dtype == SMC_F32 ? launch_syrk<float>(l, stats_row_dev) : launch_syrk<double>(l, stats_row_dev)))
             return rc;
     } else if (!inl && !no_m && stats_row_dev) {

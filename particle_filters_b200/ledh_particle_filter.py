@@ -204,6 +204,10 @@ class LEDHFlowPF:
         self._spec = ledh_spec_of(g, h, jacobian_h, log_trans_pdf, log_like_pdf)
         if self._spec is not None:
             self._meas = self._spec.meas
+            if max(self._spec.nx, self._spec.nz) > 32:
+                # the device-resident linear-Gaussian pieces keep a state vector per thread (<= 32 dimensions); larger
+                # models run the flow kernel in its global-workspace mode and evaluate g / log-densities on the host
+                self._spec = None
         self._flow = {}
         self._dev_eng = None
         self._generation = 0        # bumped by every device-resident step (see DeviceLedhState)

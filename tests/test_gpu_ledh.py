@@ -304,3 +304,90 @@ def test_device_ledh_state_is_generation_checked():
     assert s3.particles.shape == (N, 16) and abs(s3.weights.sum() - 1) < 1e-9
     with pytest.raises(RuntimeError, match="stale"):
         f.step(s2, z, None, "philox")           # stepping from a lost state must not silently use newer arrays
+
+
+@pytest.mark.parametrize("nx,nz,dtype,tol", [(48, 40, "f64", 1e-8), (64, 64, "f64", 1e-8), (144, 144, "f64", 1e-7),
+                                             (64, 64, "f32", 5e-3)])
+def test_flow_beyond_32_dimensions_uses_the_global_workspace(nx, nz, dtype, tol):
+    """The reference runs LEDH on 64-, 144- and 400-dimensional sensor-network models
+    (notebooks/PF_PF_results_reproduction_snlg.ipynb, ..._sn_skew.ipynb).  Above 32 dimensions the flow kernel keeps
+    its per-particle matrices in a global-memory workspace; same arithmetic, compared with the NumPy oracle flow
+    on a linear measurement model with a dense, well-conditioned H."""
+    import ctypes as C
+
+    import torch
+
+    from particle_filters_b200 import _lib
+
+    rng = np.random.default_rng(nx + nz)
+    N, L = 37, 3
+    H = rng.standard_normal((nz, nx)) / np.sqrt(nx)
+    G = rng.standard_normal((nx, nx)) * 0.1
+    P = 0.5 * np.eye(nx) + G @ G.T
+    R = 0.3 * np.eye(nz) + 0.05 * np.diag(rng.random(nz))
+    z = rng.standard_normal(nz)
+    eta0 = rng.standard_normal((N, nx))
+    eta_ref, theta_ref, cond_ref = ledh_flow(eta0, P, R, z, lambda X: X @ H.T, lambda X: np.broadcast_to(H, (len(X), nz, nx)), L)
+    lib = _lib.load()
+    td = torch.float64 if dtype == "f64" else torch.float32
+    ld = (N + 3) // 4 * 4
+    e0 = torch.zeros((nx, ld), dtype=td, device="cuda")
+    e0[:, :N] = torch.from_numpy(np.ascontiguousarray(eta0.T)).to(td)
+    e1 = e0.clone()
+    th = torch.zeros((ld,), dtype=td, device="cuda")
+    s0 = torch.zeros((L, nz, nz), dtype=torch.float64, device="cuda")
+    desc = _lib.LedhDesc(n=N, ld=ld, nx=nx, nz=nz, dtype=_lib.SMC_F64 if dtype == "f64" else _lib.SMC_F32, n_lambda_steps=L,
+                         eta0_dev=e0.data_ptr(), eta_dev=e1.data_ptr(), theta_log_dev=th.data_ptr(), s0_dev=s0.data_ptr())
+    kP, pP = _lib.as_doubles(P)
+    kR, pR = _lib.as_doubles(R)
+    kz, pz = _lib.as_doubles(z)
+    kh, ph = _lib.as_doubles(H)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.smc_ledh_flow(C.byref(desc), pP, pR, pz, _lib.SMC_LEDH_H_LINEAR, ph, kh.size, st))
+    torch.cuda.synchronize()
+    eta = e1[:, :N].double().cpu().numpy().T
+    theta = th[:N].double().cpu().numpy()
+    scale = np.maximum(1.0, np.abs(eta_ref))
+    assert np.max(np.abs(eta - eta_ref) / scale) < tol
+    assert np.max(np.abs(theta - theta_ref) / np.maximum(1.0, np.abs(theta_ref))) < 10 * tol
+    cond = [float(np.linalg.cond(s0[j].cpu().numpy())) for j in range(L)]
+    np.testing.assert_allclose(cond, cond_ref, rtol=1e-6 if dtype == "f64" else 1e-3)
+
+
+def test_ledh_filter_runs_at_64_dimensions_through_the_class_api():
+    """Drop-in check at a notebook-like size (nx = nz = 64, N = 200, host callbacks as the reference's notebooks pass
+    them): one step against the NumPy oracle step."""
+    from oracle.ledh_numpy import ledh_step
+    from particle_filters_b200.ledh_particle_filter import LEDHConfig, LEDHFlowPF, PFState
+
+    nx = nz = 64
+    N, L = 200, 4
+    rng = np.random.default_rng(5)
+    A = 0.9 * np.eye(nx)
+    Q, R = 0.2 * np.eye(nx), 0.5 * np.eye(nz)
+    Hm = np.eye(nz) + 0.05 * rng.standard_normal((nz, nx))
+    Qi, Ri = np.linalg.inv(Q), np.linalg.inv(R)
+
+    def logn(d, Pi):
+        return -0.5 * float(d @ Pi @ d)
+
+    P = 0.6 * np.eye(nx)
+    x0 = rng.standard_normal((N, nx))
+    w0 = np.full(N, 1.0 / N)
+    z = Hm @ (A @ x0[0]) + 0.3 * rng.standard_normal(nz)
+    V = rng.standard_normal((N, nx)) * np.sqrt(0.2)
+    f = LEDHFlowPF(ScriptedTracker([P], nx), lambda x, u=None, v=None: A @ x + (0.0 if v is None else v), lambda x: Hm @ x,
+                   lambda x: Hm, lambda xk, xp: logn(xk - A @ xp, Qi), lambda zz, x: logn(zz - Hm @ x, Ri), R,
+                   LEDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=0.0, rng=np.random.default_rng(0)))
+    mean0, cov0 = ledh_weighted_stats(x0, w0)
+    out = f.step(PFState(particles=x0, weights=w0, mean=mean0, cov=cov0, diagnostics={}), z, None, lambda n_, d_: V)
+    xo, wo, mo, co, info = ledh_step(
+        x0, w0, z, P, R, g_batch=lambda X, u, Vv: X @ A.T + Vv, h_batch=lambda X: X @ Hm.T,
+        jac_batch=lambda X: np.broadcast_to(Hm, (len(X), nz, nx)),
+        log_trans_batch=lambda Xk, Xp: -0.5 * np.einsum("ni,ij,nj->n", Xk - Xp @ A.T, Qi, Xk - Xp @ A.T),
+        log_like_batch=lambda zz, X: -0.5 * np.einsum("ni,ij,nj->n", zz - X @ Hm.T, Ri, zz - X @ Hm.T),
+        n_lambda_steps=L, resample_ess_ratio=0.0, v=V, rng=np.random.default_rng(0))
+    np.testing.assert_allclose(out.particles, xo, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(out.weights, wo, rtol=1e-6, atol=1e-14)
+    np.testing.assert_allclose(out.mean, mo, rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(out.cov, co, rtol=1e-7, atol=1e-8)
