@@ -426,7 +426,7 @@ k1_propagate_weight(K1Args<real> a, Model m) {
     // Range totals (fp32 bootstrap steps with the fused finalize): CTA b then owns the contiguous chunks of the
     // pre-pass ranges [b R / G, (b + 1) R / G) -- a chunk is a resampling tile -- and flushes one exact 64-bit sum
     // per range into the buffer the control block does NOT name (all zero by invariant); the last CTA flips it.
-    const bool do_rsum = sizeof(real) == 4 && a.rsum != nullptr && uniform && do_w && a.fuse_finalize;
+    const bool do_rsum = sizeof(real) == 4 && a.rsum != nullptr && uniform && do_w && (a.fuse_finalize || a.shard.mail != nullptr);
     const int rsel = ctrl->rsum_sel;
     unsigned long long racc = 0ull;
     int64_t c_first = blockIdx.x, c_end = n_chunks, c_stride = gridDim.x;
@@ -563,6 +563,25 @@ k1_propagate_weight(K1Args<real> a, Model m) {
             combine_partials(a.parts, (int)gridDim.x, ps, s_out, s_tmp, 0);
             if (tid < ps)
                 for (int g = 0; g < a.shard.n_shards; ++g) a.shard.mail[g]->rec[a.shard.rank][tid] = s_out[tid];
+            if (do_rsum) {
+                // bootstrap step: the shard's fixed-point weight total travels with the partial record, so the
+                // resampler needs no second exchange (and no range pre-pass); hand the range totals over
+                __shared__ unsigned long long s_rt[kWarps];
+                unsigned long long t = 0;
+                for (int i = tid; i < a.n_ranges; i += kThreads) t += __ldcg(a.rsum + (size_t)(rsel ^ 1) * kRsumStride + i);
+                t = warp_sum(t);
+                __syncthreads();
+                if ((tid & 31) == 0) s_rt[tid >> 5] = t;
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned long long tot = 0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) tot += s_rt[w];
+                    for (int g = 0; g < a.shard.n_shards; ++g) a.shard.mail[g]->tot[a.shard.rank] = tot;
+                    const_cast<Ctrl*>(ctrl)->rsum_sel = rsel ^ 1;
+                }
+                for (int i = tid; i < kRsumStride; i += kThreads) a.rsum[(size_t)rsel * kRsumStride + i] = 0ull;
+            }
             __threadfence_system();
             __syncthreads();
             if (tid < a.shard.n_shards)
@@ -719,6 +738,9 @@ __global__ void __launch_bounds__(kThreads) k2_finalize_sharded(K2Args a, ShardC
     a.parts = &own->rec[0][0];
     a.n_parts = sc.n_shards;
     a.rec_stride = 32;
+    // producer_rsum (host: K1 was launched with range totals) holds iff the step was a bootstrap step, which every
+    // rank decides alike from its replicated control block
+    a.producer_rsum = a.producer_rsum && a.ctrl->uniform != 0;
     finalize_body(a, s_out, s_tmp);
 }
 
@@ -1353,7 +1375,8 @@ k3_resample(K3Args<real> a, FM fm) {
         const unsigned long long* totals = a.totals;
         if (a.shard.mail) {   // every rank's weight total of this step must have arrived in the own mailbox
             Mailbox* own = a.shard.mail[a.shard.rank];
-            mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp, &own->error, 2);
+            if (!(sizeof(real) == 4 && ctrl->rsum_valid))       // bootstrap steps: the totals came with the partial records
+                mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp, &own->error, 2);
             totals = own->tot;
         }
         unsigned long long part = 0, all = 0;
@@ -2313,6 +2336,14 @@ int stage(const Launch& l, int slot, const double* host, int count, double** dev
 
 inline int sm_count();
 inline int sm_count_early() { return sm_count(); }
+// whether K1 may deliver the range totals of a bootstrap step (fp32, enough tiles for the 148 x 12 pre-pass ranges,
+// which every K1 CTA then owns a whole number of)
+inline bool k1_rsum_ok(const Launch& l) {
+    const smc_sir_desc* d = l.d;
+    const int64_t ranges = (int64_t)sm_count_early() * 12;
+    return d->dtype == SMC_F32 && l.L.n_tiles >= ranges && ranges <= kRsumStride && ranges % l.L.n_k1_blocks == 0 &&
+           d->nx <= kFusedNxMax && !getenv("SMC_NO_K1_RSUM");
+}
 
 template <typename real, class Model>
 int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, const void* noise_dev, uint64_t seed,
@@ -2338,13 +2369,13 @@ int launch_k1(const Launch& l, const Model& m, int mode, const double* z_dev, co
         a.fuse_finalize = 1;
         a.fin = *fin;
         a.fin.ctrl = l.ctrl(); a.fin.parts = l.k1_parts(); a.fin.n_parts = (int)l.L.n_k1_blocks;
-        // fp32, large single-shard populations: K1 also delivers the range totals of the resampler's CDF when the
-        // step turns out to be a bootstrap step (uniform prior weights; decided on the device)
-        const int64_t ranges = (int64_t)sm_count_early() * 12;
-        if (sizeof(real) == 4 && !shard && d->n == d->n_global && l.L.n_tiles >= ranges && ranges <= kRsumStride &&
-            ranges % l.L.n_k1_blocks == 0 && d->nx <= kFusedNxMax && !getenv("SMC_NO_K1_RSUM")) {
-            a.rsum = l.agg(); a.n_ranges = (int32_t)ranges; a.kshift_bound = fin->kshift_bound;
-        }
+    }
+    // fp32, large populations, finalize fused into K1 or sharded step: K1 also delivers the range totals of the
+    // resampler's CDF when the step turns out to be a bootstrap step (uniform prior weights; decided on the device)
+    if ((fin || shard) && (mode & SMC_MODE_WEIGHT) && k1_rsum_ok(l)) {
+        double lw_bound;
+        a.rsum = l.agg(); a.n_ranges = (int32_t)((int64_t)sm_count_early() * 12);
+        quant_bound_for(d->n_global, &lw_bound, &a.kshift_bound);
     }
     // mode bit 4 (internal): the caller knows the step resamples -> skip the pre-resample moments
     if (mode & 4)
@@ -3129,6 +3160,7 @@ int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_
     fin.inline_moments = 1; fin.f32 = d->dtype == SMC_F32;
     quant_bound_for(d->n_global, &fin.lw_bound, &fin.kshift_bound);
     fin.thresh = resample_thresh; fin.u_host = -1.0; fin.seed = seed; fin.t = (uint32_t)t;
+    fin.producer_rsum = k1_rsum_ok(l) ? 1 : 0;       // (and the step is a bootstrap step: decided on the device)
     k2_finalize_sharded<<<1, kThreads, 0, l.st>>>(fin, sc);
     SMC_CHECK_CUDA(cudaGetLastError());
     FinishArgs f;

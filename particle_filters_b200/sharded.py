@@ -307,8 +307,9 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
                   "max_rel_ess_diff": float(np.max(np.abs(rows_w[:, 1] - rrows[:, 1]) / rrows[:, 1])),
                   "max_abs_mean_diff": float(np.max(np.abs(rows_w[:, 4] - rrows[:, 4])))}
         parity["pass"] = bool(parity["decisions_equal"] and parity["uniforms_equal"] and
-                              parity["identical_particle_fraction"] > 0.999 and parity["max_abs_log_norm_diff"] < 1e-9
-                              and parity["max_rel_ess_diff"] < 1e-9 and parity["max_abs_mean_diff"] < 1e-6)
+                              parity["identical_particle_fraction"] > 0.999 and parity["max_abs_log_norm_diff"] < 1e-6
+                              and parity["max_rel_ess_diff"] < 1e-6 and parity["max_abs_mean_diff"] < 1e-6)
+        parity["tolerances"] = "particles bit-identical (> 99.9 %), |d log-norm| < 1e-6, rel dESS < 1e-6 (fp32 block sums over "                                "another partition), |d mean| < 1e-6"
         del ref, xref, xsh
         torch.cuda.empty_cache()
     del gathered, local

@@ -27,17 +27,24 @@ def main():
 
     dist = init_distributed()
     rank, G = dist.get_rank(), dist.get_world_size()
-    N, T, seed = 1 << 20, 12, 77
+    T, seed = 12, 77
     Q, R = np.array([[0.04]]), np.array([[0.5]])
     mid, params = StochVolSSM(0.95, 1.0).device_functor(Q, R)
     Y = np.random.default_rng(3).standard_normal(T) * 1.2
     ok = True
-    for thresh, exchange in ((0.7, "mailbox"), (2.0, "mailbox"), (0.7, "nccl"), (2.0, "nccl")):
+    # N = 2^20: shards of <= 128 tiles, range pre-pass + weight-total exchange; N = 2^24 * G / 2: shards large enough for
+    # K1 to deliver the range totals of bootstrap steps, so that the totals travel with the partial records
+    cases = [(1 << 20, 0.7, "mailbox"), (1 << 20, 2.0, "mailbox"), (1 << 20, 0.7, "nccl"), (1 << 20, 2.0, "nccl"),
+             ((1 << 23) * G, 2.0, "mailbox"), ((1 << 23) * G, 0.7, "mailbox")]
+    for N, thresh, exchange in cases:
+        if N > (1 << 27):
+            continue
         sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T, exchange=exchange)
         sh.eng.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
         sh.eng.set_observations(Y.reshape(-1, 1))
         for k in range(T):
             sh.step(mid, params, thresh, k, seed, k, k)
+        sh.check()
         rows = sh.eng.trace[:T].cpu().numpy()
         local = sh.eng.get_particles()[:, 0]
         tot = sh.shard_totals()
@@ -46,7 +53,7 @@ def main():
         if rank == 0:
             ref = SirEngine(N, 1, 1, dtype="f32", trace_len=T)
             ref.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
-            ref.run(mid, params, Y.reshape(-1, 1), thresh, seed)
+            ref.run(mid, params, Y.reshape(-1, 1), thresh, seed, fused=False)
             rrows = ref.trace[:T].cpu().numpy()
             xref = ref.get_particles()[:, 0]
             xsh = np.concatenate(gathered)
@@ -56,12 +63,15 @@ def main():
             mean_err = np.max(np.abs(rows[:, 4:6] - rrows[:, 4:6]))
             plan = migration_plan([int(t) for t in tot], float(rows[-1, 3]), N, f32=True)
             crossing = int(plan.sum() - np.trace(plan))
-            print(f"[sharded_check] G={G} {exchange} thresh={thresh}: resampled {int(rows[:, 2].sum())}/{T} steps, "
+            print(f"[sharded_check] G={G} N=2^{int(np.log2(N))} {exchange} thresh={thresh}: resampled {int(rows[:, 2].sum())}/{T} steps, "
                   f"identical particles {same * 100:.4f}%, decisions equal {dec_same}, "
                   f"stat rel err {stat_err:.2e}, mean/var abs err {mean_err:.2e}, "
                   f"last-step cross-shard particles {crossing} of {N}")
-            ok = ok and dec_same and same > 0.999 and stat_err < 1e-9 and mean_err < 1e-6
+            # (log normaliser / ESS: fp32 block sums over another partition at the large size)
+            ok = ok and dec_same and same > 0.999 and stat_err < (1e-9 if N <= (1 << 20) else 1e-5) and mean_err < 1e-6
             assert plan.sum() == N
+            del ref, xref, xsh
+            torch.cuda.empty_cache()
         sh.close()
     if rank == 0:
         print("[sharded_check] PASS" if ok else "[sharded_check] FAIL")
