@@ -506,8 +506,11 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
             if (fill > lead) consume((fill + 3u) >> 2, true);
             __syncthreads();
             restart = true; done4 = 0u; fill = 0u; lead = 0u;
+            // (which boundaries a tile gets depends on the tile alone -- exact iff some thread has more than MAXD
+            // outputs -- never on the window, so that this kernel and k3_resample always agree)
             uint32_t e[IPT];
-            exact_boundaries<IPT>(p, base_raw, rm, e);
+            if (heavy) exact_boundaries<IPT>(p, base_raw, rm, e);
+            else f32_boundaries<IPT>(p, Ps, e_end, rm.rho_f, e);
 #pragma unroll
             for (int k = 0; k < IPT; ++k) e[k] = umin(k >= klast ? Nn : e[k], e_end);
             auto x_of = [&](const int d, const int li) -> float {      // item li of the (swizzled) particle tile

@@ -658,10 +658,32 @@ __global__ void __launch_bounds__(kThreads) k2_reduce_partials(const double* par
 
 // K2 body: combine the partial records, publish normaliser / ESS / decision / u (+ weighted moments).
 // Runs in one 256-thread CTA: the stand-alone kernel below, or the last CTA of K1 to finish.
+__device__ inline void finalize_tail(const K2Args& a, const double* s_out);
 __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_tmp) {
     const int ps = a.inline_moments ? partial_stride(a.nx) : 3;
     combine_partials(a.parts, a.n_parts, ps, s_out, s_tmp, a.rec_stride);
     if (threadIdx.x != 0) return;
+    finalize_tail(a, s_out);
+}
+// One-warp form for a handful of records (<= 32, one per lane): the sharded resampler runs it in every CTA's
+// prologue, where a CTA-wide fp64 reduction in 4 x 148 CTAs at once would cost more than the launch it replaces.
+__device__ inline void finalize_warp(const K2Args& a, double* s_out) {
+    const int ps = a.inline_moments ? partial_stride(a.nx) : 3;
+    const int stride = a.rec_stride > 0 ? a.rec_stride : ps;
+    const int lane = threadIdx.x & 31;
+    const bool have = lane < a.n_parts;
+    const double r0 = have ? __ldcg(a.parts + (int64_t)lane * stride) : -INFINITY;
+    const double M = warp_max(r0);
+    const double sc = (have && r0 != -INFINITY) ? exp(r0 - M) : 0.0;
+    for (int k = 1; k < ps; ++k) {
+        const double v = have ? __ldcg(a.parts + (int64_t)lane * stride + k) : 0.0;
+        const double t = warp_sum(v * (k == 2 ? sc * sc : sc));
+        if (lane == 0) s_out[k] = t;
+    }
+    if (lane == 0) { s_out[0] = M; finalize_tail(a, s_out); }
+    __syncwarp();
+}
+__device__ inline void finalize_tail(const K2Args& a, const double* s_out) {
     Ctrl* c = a.ctrl;
     const double M = s_out[0], S = s_out[1], Q = s_out[2];
     const double log_norm = M + log(S);
@@ -681,7 +703,7 @@ __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_t
     ctrl_prepare_search(c, a.n_global, a.f32 != 0);
     if (a.f32) {
         // fp32 CDF: fixed-point weights a_i = rni(2^Fa exp(lw_i - lw_ref)).  Any reference lw_ref >= max lw_i
-        // that leaves the mean weight enough resolution will do, because the stratified positions are laid
+        // that leaves the weights that matter enough resolution will do, because the stratified positions are laid
         // over the ACTUAL total (see RhoMap).  A bootstrap step knows such a reference before it has seen a
         // single weight -- lw_i = -log N - quad_i / 2 <= -log N -- which is what lets the kernel that WRITES
         // the log-weights also deliver the range totals of the resampler's CDF (no pre-pass over them).
@@ -692,8 +714,12 @@ __device__ inline void finalize_body(const K2Args& a, double* s_out, double* s_t
             c->lw_ref = a.lw_bound;
             c->kshift = a.kshift_bound;
             c->rsum_valid = a.producer_rsum ? 1 : 0;
-        } else {                                            // N w_i = exp(lw_i - lw_ref), as in fp64 mode
-            c->kshift = (float)((double)Fa - c->lw_ref * (double)kLog2eF);
+        } else {
+            // otherwise the largest log-weight of the step: exact whatever the order of the reductions (unlike the
+            // normaliser, whose fp32 block sums differ in the last bits between launch shapes and shard counts), so
+            // every pipeline quantises alike; the heaviest particle gets 2^Fa, the total stays below 2^Fa N <= 2^62
+            c->lw_ref = M;
+            c->kshift = M == -INFINITY ? 0.f : (float)((double)Fa - M * (double)kLog2eF);
             c->rsum_valid = 0;
         }
     }
@@ -877,6 +903,11 @@ template <typename real> struct K3Args {
     ShardCtx shard;             // mail != nullptr: weight totals come from / moment record goes to the mailboxes
     FuseK1<real> fk;            // used by the fused instantiations only
     int32_t ranges_per_cta;     // pre-pass ranges owned by one CTA of this launch
+    // sharded bootstrap steps: the finalize runs in EVERY CTA's prologue (on a shared-memory copy of the control
+    // block, once all ranks' partial records have arrived) instead of in a launch of its own
+    int32_t prologue_finalize;
+    K2Args pfin;
+    unsigned int* gbar;         // grid-barrier counter of the in-kernel range pre-pass (fallback of such steps)
 };
 
 // Tile geometry: THREADS threads own IPT consecutive items each (fp32: 256 x 16 = 4096-particle
@@ -1302,11 +1333,32 @@ k3_resample(K3Args<real> a, FM fm) {
     __shared__ double s_m[16];
     __shared__ int s_last;
 
-    Ctrl* ctrl = a.ctrl;
+    Ctrl* const gctrl = a.ctrl;
+    Ctrl* ctrl = gctrl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
     pdl_trigger();
+    __shared__ Ctrl s_ctrl;
+    if (a.prologue_finalize) {
+        // Sharded bootstrap step: every CTA waits for the G partial records in its own mailbox and finalises the step
+        // on a private copy of the control block (identical arithmetic, identical result in every CTA of every
+        // rank); CTA 0 also writes the statistics row, the last CTA to finish copies the block back (nobody else
+        // touches the global one meanwhile).
+        __shared__ double s_pout[32];
+        for (int i = tid; i < (int)(sizeof(Ctrl) / 4); i += kK3Threads)
+            reinterpret_cast<uint32_t*>(&s_ctrl)[i] = reinterpret_cast<const uint32_t*>(gctrl)[i];
+        Mailbox* own = a.shard.mail[a.shard.rank];
+        mailbox_wait(own->flag_rec, a.shard.n_shards, a.shard.stamp, &own->error, 1);
+        K2Args f = a.pfin;
+        f.ctrl = &s_ctrl; f.parts = &own->rec[0][0]; f.n_parts = a.shard.n_shards; f.rec_stride = 32;
+        f.producer_rsum = f.producer_rsum && s_ctrl.uniform != 0;
+        if (blockIdx.x != 0) f.stats = nullptr;
+        if (warp == 0) finalize_warp(f, s_pout);
+        __syncthreads();
+        ctrl = &s_ctrl;
+    }
     if (!a.force && !ctrl->do_resample) {
+        if (a.prologue_finalize && blockIdx.x == 0 && tid == 0) *gctrl = s_ctrl;
         // nothing to resample: only the moment-shift refresh of the fused finish remains
         if (a.fuse_finish && blockIdx.x == 0 && tid == 0 && a.fin.stats && !a.fin.no_moments)
             for (int d = 0; d < a.fin.nx && d < kMaxNx; ++d) ctrl->shift[d] = a.fin.stats[SMC_STATS_HEADER + d];
@@ -1375,8 +1427,61 @@ k3_resample(K3Args<real> a, FM fm) {
         const unsigned long long* totals = a.totals;
         if (a.shard.mail) {   // every rank's weight total of this step must have arrived in the own mailbox
             Mailbox* own = a.shard.mail[a.shard.rank];
-            if (!(sizeof(real) == 4 && ctrl->rsum_valid))       // bootstrap steps: the totals came with the partial records
+            if (a.prologue_finalize && !(sizeof(real) == 4 && ctrl->rsum_valid)) {
+                // Rare: the a-priori bound left this step's weights too little resolution and no range pre-pass was
+                // launched (the step was enqueued as a bootstrap step).  Run it here: every CTA sums the ranges it
+                // owns against the normaliser, a grid barrier (all CTAs of this persistent grid are resident), CTA 0
+                // publishes the shard total to every rank.
+                unsigned long long* rt = const_cast<unsigned long long*>(a.rtot) + (size_t)ctrl->rsum_sel * kRsumStride;
+                for (int r = (int)blockIdx.x * a.ranges_per_cta; r < ((int)blockIdx.x + 1) * a.ranges_per_cta; ++r) {
+                    const int64_t tr0 = k3_range_begin(r, a.n_tiles, (int64_t)gridDim.x * a.ranges_per_cta);
+                    const int64_t tr1 = k3_range_begin(r + 1, a.n_tiles, (int64_t)gridDim.x * a.ranges_per_cta);
+                    unsigned long long acc = 0;
+                    double runf = 0.0;
+                    for (int64_t i = tr0 * TILE + tid; i < tr1 * TILE && i < a.n; i += kK3Threads)
+                        acc = quant.add_logw(acc, a.wsrc[i], runf);          // fp32: items are quantised one by one
+                    acc = warp_sum(acc);
+                    __syncthreads();
+                    if (lane == 0) s_warp_tot[warp] = acc;
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned long long t = 0;
+#pragma unroll
+                        for (int w = 0; w < kK3Warps; ++w) t += s_warp_tot[w];
+                        rt[r] = t;
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    atomicAdd(a.gbar, 1u);
+                    while (*(volatile unsigned int*)a.gbar < gridDim.x) __nanosleep(40);
+                }
+                __syncthreads();
+                __threadfence();
+                if (blockIdx.x == 0) {
+                    unsigned long long t = 0;
+                    const int nr = (int)gridDim.x * a.ranges_per_cta;
+                    for (int i = tid; i < nr; i += kK3Threads) t += __ldcg(rt + i);
+                    t = warp_sum(t);
+                    __syncthreads();
+                    if (lane == 0) s_warp_tot[warp] = t;
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned long long tot = 0;
+#pragma unroll
+                        for (int w = 0; w < kK3Warps; ++w) tot += s_warp_tot[w];
+                        for (int g = 0; g < a.shard.n_shards; ++g) a.shard.mail[g]->tot[a.shard.rank] = tot;
+                        __threadfence_system();
+                        for (int g = 0; g < a.shard.n_shards; ++g)
+                            *(volatile unsigned long long*)&a.shard.mail[g]->flag_tot[a.shard.rank] = a.shard.stamp;
+                    }
+                    __syncthreads();
+                }
                 mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp, &own->error, 2);
+            } else if (!(sizeof(real) == 4 && ctrl->rsum_valid)) {   // bootstrap steps: the totals came with the partial records
+                mailbox_wait(own->flag_tot, a.shard.n_shards, a.shard.stamp, &own->error, 2);
+            }
             totals = own->tot;
         }
         unsigned long long part = 0, all = 0;
@@ -1995,6 +2100,7 @@ k3_resample(K3Args<real> a, FM fm) {
         __syncthreads();
         if (s_last) {
             __threadfence();
+            if (a.prologue_finalize && tid == 0) { *gctrl = s_ctrl; *a.gbar = 0u; }
             if (NM > 0 && a.mom_parts) {
                 double acc[NMS];
 #pragma unroll
@@ -2572,17 +2678,22 @@ void fill_k3_args(const Launch& l, K3Args<real>& a, const void* wsrc, int nxf, u
     memset(&a.shard, 0, sizeof(a.shard));
     if (shard) a.shard = *shard;
     memset(&a.fk, 0, sizeof(a.fk));
+    a.prologue_finalize = 0;
+    memset(&a.pfin, 0, sizeof(a.pfin));
+    a.gbar = l.ticket() + 3;
 }
 
 template <typename real>
 int launch_k3(const Launch& l, bool linear_w, const void* wsrc, int nxf, unsigned long long cdf_offset, int force,
               void* const* peer, int n_shards, bool want_moments, const unsigned long long* totals = nullptr,
-              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr, const ShardCtx* shard = nullptr) {
+              int rank = 0, bool run_prepass = true, const FinishArgs* fin = nullptr, const ShardCtx* shard = nullptr,
+              const K2Args* prologue_fin = nullptr) {
     if (run_prepass) {
         if (int rc = launch_prepass<real>(l, linear_w, wsrc, nxf, force, nullptr)) return rc;
     }
     K3Args<real> a;
     fill_k3_args<real>(l, a, wsrc, nxf, cdf_offset, force, peer, n_shards, want_moments, totals, rank, fin, shard);
+    if (prologue_fin) { a.prologue_finalize = 1; a.pfin = *prologue_fin; }
     const int64_t nt = l.L.n_tiles;
     if (linear_w) {
         SMC_REQUIRE(nxf == 0, "smc: linear-weight resampling is ancestors-only");
@@ -3161,12 +3272,26 @@ int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_
     quant_bound_for(d->n_global, &fin.lw_bound, &fin.kshift_bound);
     fin.thresh = resample_thresh; fin.u_host = -1.0; fin.seed = seed; fin.t = (uint32_t)t;
     fin.producer_rsum = k1_rsum_ok(l) ? 1 : 0;       // (and the step is a bootstrap step: decided on the device)
-    k2_finalize_sharded<<<1, kThreads, 0, l.st>>>(fin, sc);
-    SMC_CHECK_CUDA(cudaGetLastError());
     FinishArgs f;
     memset(&f, 0, sizeof(f));
     f.stats = stats_row_dev; f.nx = d->nx; f.inline_moments = 1;
     f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+    if (resample_thresh > 1.0 && fin.producer_rsum && d->dtype == SMC_F32 && !getenv("SMC_SHARDED_5LAUNCH")) {
+        // Bootstrap filter on large shards: THREE launches, two exchanges.  K1 has published (partial record, weight
+        // total); the resampler finalises the step in every CTA's prologue once the G records are there, migrates by
+        // peer stores and publishes the moment record; the finish waits for the G moment flags.
+        const bool want_m = !(d->flags & SMC_FLAG_NO_MOMENTS);
+        rc = launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, ctx->peer_x_dev, G, want_m, nullptr, rank, false, nullptr,
+                              &sc, &fin);
+        if (rc) return rc;
+        __atomic_add_fetch(&g_launch_count, 1ull, __ATOMIC_RELAXED);
+        k_finish_step_sharded<<<1, kThreads, 0, l.st>>>(l.ctrl(), f, sc);
+        SMC_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    __atomic_add_fetch(&g_launch_count, 2ull, __ATOMIC_RELAXED);     // finalize + finish (the others count themselves)
+    k2_finalize_sharded<<<1, kThreads, 0, l.st>>>(fin, sc);
+    SMC_CHECK_CUDA(cudaGetLastError());
     if (resample_thresh > 0.0) {
         // 3. range pre-pass; its last CTA publishes the shard's weight total
         rc = d->dtype == SMC_F32 ? launch_prepass<float>(l, false, d->logw_dev, d->nx, 0, nullptr, &sc)

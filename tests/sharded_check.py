@@ -34,14 +34,21 @@ def main():
     ok = True
     # N = 2^20: shards of <= 128 tiles, range pre-pass + weight-total exchange; N = 2^24 * G / 2: shards large enough for
     # K1 to deliver the range totals of bootstrap steps, so that the totals travel with the partial records
-    cases = [(1 << 20, 0.7, "mailbox"), (1 << 20, 2.0, "mailbox"), (1 << 20, 0.7, "nccl"), (1 << 20, 2.0, "nccl"),
-             ((1 << 23) * G, 2.0, "mailbox"), ((1 << 23) * G, 0.7, "mailbox")]
-    for N, thresh, exchange in cases:
+    # ... in three launches per step (the resampler finalises in its prologue); "outliers": two observations 9 sigma out,
+    # where the a-priori bound leaves the weights no resolution and the resampler runs its in-kernel range pre-pass
+    Y_out = Y.copy()
+    Y_out[3], Y_out[7] = 9.0, -8.5
+    cases = [(1 << 20, 0.7, "mailbox", Y), (1 << 20, 2.0, "mailbox", Y), (1 << 20, 0.7, "nccl", Y), (1 << 20, 2.0, "nccl", Y),
+             ((1 << 23) * G, 2.0, "mailbox", Y), ((1 << 23) * G, 0.7, "mailbox", Y), ((1 << 23) * G, 2.0, "mailbox", Y_out)]
+    only = os.environ.get("SHARDED_CHECK_ONLY")          # debugging aid: "outliers" runs the last case only
+    if only == "outliers":
+        cases = cases[-1:]
+    for N, thresh, exchange, Yc in cases:
         if N > (1 << 27):
             continue
         sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T, exchange=exchange)
         sh.eng.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
-        sh.eng.set_observations(Y.reshape(-1, 1))
+        sh.eng.set_observations(Yc.reshape(-1, 1))
         for k in range(T):
             sh.step(mid, params, thresh, k, seed, k, k)
         sh.check()
@@ -53,7 +60,7 @@ def main():
         if rank == 0:
             ref = SirEngine(N, 1, 1, dtype="f32", trace_len=T)
             ref.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
-            ref.run(mid, params, Y.reshape(-1, 1), thresh, seed, fused=False)
+            ref.run(mid, params, Yc.reshape(-1, 1), thresh, seed, fused=False)
             rrows = ref.trace[:T].cpu().numpy()
             xref = ref.get_particles()[:, 0]
             xsh = np.concatenate(gathered)
@@ -63,7 +70,8 @@ def main():
             mean_err = np.max(np.abs(rows[:, 4:6] - rrows[:, 4:6]))
             plan = migration_plan([int(t) for t in tot], float(rows[-1, 3]), N, f32=True)
             crossing = int(plan.sum() - np.trace(plan))
-            print(f"[sharded_check] G={G} N=2^{int(np.log2(N))} {exchange} thresh={thresh}: resampled {int(rows[:, 2].sum())}/{T} steps, "
+            tag = " outliers" if Yc is Y_out else ""
+            print(f"[sharded_check] G={G} N=2^{int(np.log2(N))} {exchange} thresh={thresh}{tag}: resampled {int(rows[:, 2].sum())}/{T} steps, "
                   f"identical particles {same * 100:.4f}%, decisions equal {dec_same}, "
                   f"stat rel err {stat_err:.2e}, mean/var abs err {mean_err:.2e}, "
                   f"last-step cross-shard particles {crossing} of {N}")

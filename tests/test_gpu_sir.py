@@ -417,3 +417,39 @@ def test_fp32_systematic_offspring_counts_at_scale(z_obs):
     assert np.all(dev <= slack), (np.argmax(dev - slack), counts[np.argmax(dev - slack)], expect[np.argmax(dev - slack)])
     ess = eng.read_row(0)[1]
     assert (ess > 0.5 * N) if z_obs < 1 else (ess < 1e-3 * N)
+
+
+@pytest.mark.parametrize("z_obs", [0.4, 3.5, 7.5, 9.0])
+def test_expansion_resampler_selects_the_same_particles_as_the_marker_resampler(z_obs):
+    """The plain fp32 resampler exists twice: k3_resample (marker window; ancestor trace, fp64, shards) and
+    K5<CopyModel> (payload expansion; the single-GPU hot path).  Same CDF, same boundaries -> bit-identical
+    resampled sets, mild (ESS ~ N), moderately skewed and extremely skewed (a few heavy items own every output:
+    skewed-tile routes, quantisation fallback against the normaliser)."""
+    from particle_filters_b200 import StochVolSSM, _lib
+    from particle_filters_b200.engine import SirEngine
+
+    N = (1 << 23) + 4096 * 5 + 1237
+    mid, params = StochVolSSM(0.95, 1.0).device_functor(np.array([[0.04]]), np.array([[1.0]]))
+    outs = []
+    for variant in ("k3_markers", "k5_expansion"):
+        eng = SirEngine(N, 1, 1, dtype="f32", trace_len=2, write_ancestors=(variant == "k3_markers"))
+        eng.init_gaussian(np.zeros(1), np.array([[0.6]]), 5)
+        eng.set_observations(np.array([[z_obs]]))
+        if variant == "k3_markers":
+            eng.propagate_weight(mid, params, _lib.SMC_MODE_STEP, z_index=0, seed=5, t=0)
+            eng.finalize(2.0, u=-1.0, seed=5, t=0, row=0)
+            x_pre = eng.get_particles()[:, 0]
+            eng.resample(row=0)
+            eng.finish_step(row=0)
+            anc = eng.ancestors[:N].cpu().numpy().astype(np.int64)
+            x_post = eng.get_particles()[:, 0]
+            np.testing.assert_array_equal(x_post, x_pre[anc])
+        else:
+            eng.step(mid, params, 2.0, z_index=0, seed=5, t=0, row=0)       # K1 (+ range totals), pre-pass if needed, K5<Copy>
+            x_post = eng.get_particles()[:, 0]
+        outs.append((x_post, eng.read_row(0)))
+    (xa, ra), (xb, rb) = outs
+    bad = np.flatnonzero(xa != xb)
+    assert bad.size == 0, (bad.size, bad[:8], xa[bad[:4]], xb[bad[:4]])
+    np.testing.assert_allclose(rb[:2], ra[:2], rtol=1e-6)
+    np.testing.assert_allclose(rb[4:], ra[4:], rtol=0, atol=2e-4)
