@@ -7,6 +7,7 @@
 #include "smc_common.cuh"
 #include "../../include/smc_ledh.h"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace smc {
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(kThreads) k_affine_map(real* x, const double* 
 
 }  // namespace smc
 #include "ledh_fast.cuh"
+#include "ledh_info.cuh"
 namespace smc {
 
 // ---- device-resident linear-Gaussian pieces (thread per particle, constants in shared memory) ----
@@ -578,11 +580,79 @@ bool invert(const double* A, int n, std::vector<double>& inv) {
     return true;
 }
 
+// host Cholesky P = L L^T (lower); false when P is not positive definite
+bool cholesky_lower(const double* P, int n, std::vector<double>& Lc) {
+    Lc.assign((size_t)n * n, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c <= r; ++c) {
+            double acc = 0.5 * (P[r * n + c] + P[c * n + r]);
+            for (int k = 0; k < c; ++k) acc -= Lc[r * n + k] * Lc[c * n + k];
+            if (r == c) {
+                if (!(acc > 0.0)) return false;
+                Lc[r * n + r] = sqrt(acc);
+            } else {
+                Lc[r * n + c] = acc / Lc[c * n + c];
+            }
+        }
+    return true;
+}
+
+// information-form flow (ledh_info.cuh): fp32, R diagonal, nx in {4, 8, 16}.  Returns -1 when it does not apply.
+int launch_flow_info(const smc_ledh_desc* d, const double* P, const double* R, const double* z, int kind, const double* hp,
+                     int n_hp, int step0, int L, cudaStream_t st) {
+    const int nx = d->nx, nz = d->nz;
+    if (d->dtype != SMC_F32 || !(nx == 4 || nx == 8 || nx == 16) || nz > kLedhInfoMaxNz || getenv("SMC_LEDH_LITERAL")) return -1;
+    for (int r = 0; r < nz; ++r)
+        for (int c = 0; c < nz; ++c)
+            if (r != c && R[r * nz + c] != 0.0) return -1;
+            else if (r == c && !(R[r * nz + c] > 0.0)) return -1;
+    std::vector<double> Lc;
+    if (!cholesky_lower(P, nx, Lc)) return -1;
+    const size_t cnt = (size_t)nx * nx + (size_t)nz * nz + nz + (size_t)(n_hp > 0 ? n_hp : 0);
+    std::vector<double> host(cnt);
+    double* q = host.data();
+    memcpy(q, Lc.data(), sizeof(double) * nx * nx); q += nx * nx;
+    memcpy(q, R, sizeof(double) * nz * nz); q += nz * nz;
+    memcpy(q, z, sizeof(double) * nz); q += nz;
+    if (n_hp > 0) memcpy(q, hp, sizeof(double) * n_hp);
+    double* dev = nullptr;
+    SMC_CHECK_CUDA(cudaMallocAsync(&dev, cnt * sizeof(double), st));
+    SMC_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+    LedhInfoArgs a;
+    a.eta0 = static_cast<const float*>(d->eta0_dev);
+    a.eta = static_cast<float*>(d->eta_dev);
+    a.theta = static_cast<float*>(d->theta_log_dev);
+    a.s0 = d->s0_dev;
+    a.Lc = dev; a.R = dev + nx * nx; a.z = a.R + nz * nz; a.hp = a.z + nz;
+    a.n = d->n; a.ld = d->ld; a.nz = nz; a.n_hp = n_hp > 0 ? n_hp : 0; a.L = L; a.step0 = step0;
+    int rc = -1;
+#define SMC_LEDH_INFO(NX_, KIND_)                                                                           \
+    if (nx == NX_ && kind == KIND_) {                                                                       \
+        auto kf = k4_ledh_flow_info<NX_, KIND_>;                                                            \
+        const size_t sm = LedhInfoSmem<NX_>::bytes(nz, a.n_hp);                                             \
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));     \
+        const int ppc = kLedhInfoWarps * (32 / LedhInfoLanes<NX_>::value);                                  \
+        kf<<<(unsigned)cdiv64(d->n, ppc), 32 * kLedhInfoWarps, sm, st>>>(a);                                \
+        SMC_CHECK_CUDA(cudaGetLastError());                                                                 \
+        rc = 0;                                                                                             \
+    }
+    SMC_LEDH_INFO(16, SMC_LEDH_H_ACOUSTIC) SMC_LEDH_INFO(8, SMC_LEDH_H_ACOUSTIC) SMC_LEDH_INFO(4, SMC_LEDH_H_ACOUSTIC)
+    SMC_LEDH_INFO(16, SMC_LEDH_H_LINEAR) SMC_LEDH_INFO(8, SMC_LEDH_H_LINEAR) SMC_LEDH_INFO(4, SMC_LEDH_H_LINEAR)
+    SMC_LEDH_INFO(16, SMC_LEDH_H_EXP) SMC_LEDH_INFO(8, SMC_LEDH_H_EXP) SMC_LEDH_INFO(4, SMC_LEDH_H_EXP)
+#undef SMC_LEDH_INFO
+    SMC_CHECK_CUDA(cudaFreeAsync(dev, st));
+    return rc;
+}
+
 template <typename real>
 int launch_flow(const smc_ledh_desc* d, const double* P, const double* R, const double* z, int kind, const double* hp,
                 int n_hp, const double* Hsup, const double* hsup, double lam0, double dlam, int step0, int L,
                 cudaStream_t st) {
     const int nx = d->nx, nz = d->nz;
+    if (sizeof(real) == 4 && !Hsup) {   // fp32 throughput mode: nx x nx information form where it applies
+        const int rc = launch_flow_info(d, P, R, z, kind, hp, n_hp, step0, L, st);
+        if (rc >= 0) return rc;
+    }
     std::vector<double> Rinv;
     SMC_REQUIRE(invert(R, nz, Rinv), "smc_ledh: R is singular");
     // stream-ordered staging buffer: P | R | Rinv | z | hp
