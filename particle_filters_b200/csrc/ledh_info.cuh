@@ -206,7 +206,17 @@ __global__ void __launch_bounds__(32 * kLedhInfoWarps) k4_ledh_flow_info(LedhInf
         float ld1 = 0.f, ld2 = 0.f, d1 = 1.f;
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            const float p1 = bcast(C1[c], c), p2 = bcast(C2[c], c);        // pivots (positive: SPD)
+            // pivots.  M = I + (positive) Gh with Gh positive semi-definite, so every Schur complement is >= 1 in exact
+            // arithmetic; fp32 round-off can push the pivot of a direction the measurement says nothing about below
+            // that (even below zero) when another direction is extremely stiff (a particle on top of a sensor under a
+            // wide prior: cond(M) ~ 1e9): clamp to the exact lower bound instead of propagating NaNs
+            const float q1 = bcast(C1[c], c), q2 = bcast(C2[c], c);
+            const bool bad1 = !(q1 >= 1.0f), bad2 = !(q2 >= 1.0f);
+            const float p1 = bad1 ? 1.0f : q1, p2 = bad2 ? 1.0f : q2;
+            // (a direction whose pivot is lost is decoupled: its column below the diagonal is dropped too, so that the
+            // factor stays consistent and the triangular solves bounded)
+            if (bad1 && j > c) C1[c] = 0.f;
+            if (bad2 && j > c) C2[c] = 0.f;
             const float r1 = rsqrtf(p1), r2 = rsqrtf(p2);
             ld1 += __logf(p1); ld2 += __logf(p2);                          // log det = sum log pivots of L L^T... (pivot^2 = p)
             if (j == c) { d1 = p1 * r1; C1[c] = d1; C2[c] = p2 * r2; }

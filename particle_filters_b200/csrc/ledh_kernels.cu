@@ -490,7 +490,9 @@ __global__ void __launch_bounds__(kThreads) k_ledh_weights(real* logw, const dou
     double m = -INFINITY, s = 0, s2 = 0;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         const double v = log(wprev[i] + 1e-300) + (double)theta[i] + terms[i];
-        logw[i] = (real)v;
+        // NaN (a particle whose flow blew up) counts as zero weight, and is STORED as -inf: the resampler's
+        // quantisation assumes NaN-free log-weights, as K1 guarantees for its own
+        logw[i] = (v == v) ? (real)v : real(-INFINITY);
         if (!(v == v)) continue;
         if (v > m) { const double sc = exp(m - v); s *= sc; s2 *= sc * sc; m = v; }
         if (m != -INFINITY) { const double e = exp(v - m); s += e; s2 = fma(e, e, s2); }

@@ -2306,8 +2306,8 @@ __global__ void __launch_bounds__(kThreads) k_bridge_loglik(Ctrl* ctrl, real* lo
         }
         const double prev = wprev ? log((double)wprev[i] + 1e-300) : lw_uniform;   // :261
         double v = prev - 0.5 * quad;
-        logw[i] = (real)v;
-        if (!(v == v)) continue;              // NaN counts as zero weight
+        logw[i] = (v == v) ? (real)v : real(-INFINITY);   // NaN counts as zero weight (stored as -inf, see K1)
+        if (!(v == v)) continue;
         if (v > m) {
             const double sc = exp(m - v);     // m = -inf -> 0
             s *= sc; s2 *= sc * sc; m = v;

@@ -43,7 +43,14 @@ class SirEngine:
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        cur_dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = cur_dev if device is None else torch.device(device)
+        if self.device.type != "cuda" or (self.device.index is not None and self.device.index != cur_dev.index):
+            # libsmc launches on the CURRENT device and keeps per-process function attributes: one process per GPU
+            # (torchrun), select the GPU with torch.cuda.set_device() before building engines
+            raise ValueError(f"SirEngine runs on the process's current CUDA device ({cur_dev}); got device={device!r}. "
+                             "Call torch.cuda.set_device() first (one process per GPU).")
+        self.device = cur_dev
         self.n, self.nx, self.nz = int(n), int(nx), int(nz)
         self.n_global = self.n if n_global is None else int(n_global)
         self.offset = int(offset)
@@ -119,6 +126,13 @@ class SirEngine:
         host = torch.from_numpy(p.astype(self.npdtype, copy=False))
         self.x[0][:, : self.n].copy_(host, non_blocking=False)
         self.reset(shift)
+
+    def upload_particles(self, particles: np.ndarray):
+        """Overwrite the CURRENT particle buffer with host particles ``(n, nx)``; weights, normaliser and the rest of
+        the control block stay as they are (assigning ``state.particles`` in the reference leaves the weights alone)."""
+        torch = self.torch
+        p = np.ascontiguousarray(np.asarray(particles, dtype=np.float64).reshape(self.n, self.nx).T)
+        self.x[self.current_buffer()][:, : self.n].copy_(torch.from_numpy(p.astype(self.npdtype, copy=False)))
 
     def get_particles(self) -> np.ndarray:
         """Current particles as host float64 ``(n, nx)``."""

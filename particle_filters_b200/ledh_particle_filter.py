@@ -410,7 +410,12 @@ class LEDHFlowPF:
         cov = row[H0 + nx:].reshape(nx, nx).copy()
         cov = 0.5 * (cov + cov.T)
         s0 = buf.s0.cpu().numpy()
-        cond = [float(np.linalg.cond(s0[j])) for j in range(n_steps)]
+        cond = []
+        for j in range(n_steps):                                  # diagnostic of particle 0 (:152-157, bare except there too)
+            try:
+                cond.append(float(np.linalg.cond(s0[j])))
+            except Exception:
+                cond.append(float("nan"))
         self.last_ess = float(row[1])
         self.last_resampled = bool(row[2])
         self._generation += 1

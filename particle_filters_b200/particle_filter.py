@@ -146,6 +146,7 @@ class ParticleFilter:
         self._bridge = {}           # bridge engines by particle count
         self._generation = 0
         self._t_phil = 0            # Philox step counter
+        self._n_predict = 0         # predict-only calls (own Philox sub-stream)
         # additive diagnostics of the last update (the reference computes and discards them)
         self.last_log_norm = None
         self.last_ess = None
@@ -175,7 +176,15 @@ class ParticleFilter:
         return self._eng
 
     def _eng_upload_particles(self, particles):
-        self._eng.set_particles(particles, shift=np.mean(particles, axis=0))
+        self._eng.upload_particles(particles)        # weights untouched, as in the reference
+
+    @staticmethod
+    def _reject_control(u):
+        """Spec models compile ``g(x)`` without a control input: a ``u`` the reference would hand to ``g`` for every
+        particle (particle_filter.py:237) must not be dropped silently."""
+        if u is not None:
+            raise ValueError("spec models take no control input u; pass plain callables g(x, u) / h(x) to use one "
+                             "(host-callback bridge)")
 
     def _chol_Q(self, eps: float) -> Array:
         try:
@@ -284,14 +293,18 @@ class ParticleFilter:
         assert self.state is not None, "Filter not initialized."
         Lq = self._chol_Q(1e-10)
         if self._spec is not None:
+            self._reject_control(u)
             eng = self._eng
             self._generation += 1
             mid, params = self._functor
             noise = None
             if self._noise == "reference":
                 noise = eng.upload_soa(self.rng.standard_normal((self.Np, self.nx)), self.nx)
-            eng.propagate_weight(mid, params, _lib.SMC_MODE_PROPAGATE, noise=noise, seed=self._seed,
-                                 t=self._t_phil)
+            # Philox: predict-only calls draw from their own sub-stream (bit 30 of the step counter + a call count),
+            # so two predict() calls without an update do not reuse the noise of step()
+            t_noise = self._t_phil if self._noise == "reference" else (1 << 30) | (self._n_predict & ((1 << 30) - 1))
+            self._n_predict += 1
+            eng.propagate_weight(mid, params, _lib.SMC_MODE_PROPAGATE, noise=noise, seed=self._seed, t=t_noise)
             self.state = DevicePFState(self, self.state.mean, self.state.cov, self.state.t)
             return
         noise = self.rng.standard_normal((self.Np, self.nx))
@@ -388,6 +401,7 @@ class ParticleFilter:
         propagate+likelihood launch for spec models."""
         if self._spec is not None:
             assert self.state is not None, "Filter not initialized."
+            self._reject_control(u)
             return self._update_device(np.asarray(z, float), self.state.t + 1, _lib.SMC_MODE_STEP)
         self.predict(u)
         return self.update(z)

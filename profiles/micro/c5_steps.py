@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Per-step wall time of the C5 LEDH filter (class API) with SM clock / power samples: is the step time stationary?"""
-import os, subprocess, sys, time
+"""Per-step wall time, ESS and resampling flag of the C5 LEDH filter (class API) on the reference's acoustic scenario
+(tests/golden/bench_c5_acoustic.npz).   python profiles/micro/c5_steps.py [L] [dtype]"""
+import os, sys, time
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
@@ -11,34 +12,26 @@ def main():
     import torch
     from particle_filters_b200 import AcousticMeasurement, LEDHConfig, LEDHFlowPF
     from particle_filters_b200.ssm import LedhGaussianSSM
-    from ssm_zoo import AcousticCVModel
-    K, N, L = 24, 1 << 20, 8
-    am = AcousticCVModel(n_targets=4, grid=(5, 5), q_scale=0.05)
-    rng = np.random.default_rng(56)
-    x = np.array([12.0, 6, 0.05, 0.1, 32, 32, -0.1, -0.05, 20, 13, 0.0, 0.1, 15, 35, 0.1, -0.1])
-    Lq, r = np.linalg.cholesky(am.Q), np.sqrt(am.R[0, 0])
-    Z = np.empty((K, am.nz))
-    x0 = None
-    for t in range(K):
-        x = am.F @ x + Lq @ rng.standard_normal(16)
-        if t == 0:
-            x0 = x.copy()
-        Z[t] = am.h(x) + r * rng.standard_normal(am.nz)
-    P0 = np.kron(np.eye(4), np.diag([1.0, 1.0, 0.01, 0.01]))
-    meas = AcousticMeasurement(am.S, am.psi, am.d0, n_targets=4)
-    ssm = LedhGaussianSSM(am.F, am.Q, meas, am.R)
-    m0 = np.linalg.solve(am.F, x0)
-    pf = LEDHFlowPF(bc._EkfTracker(am, m0, P0), ssm.g, ssm.h, ssm.jacobian_h, ssm.log_trans_pdf, ssm.log_like_pdf, am.R,
-                    LEDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=0.5, rng=np.random.default_rng(0)),
-                    dtype="f32")
+    L = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    dtype = sys.argv[2] if len(sys.argv) > 2 else "f32"
+    N = 1 << (20 if dtype == "f32" else 17)
+    g = bc.fixture("bench_c5_acoustic.npz")
+    F, Q, R, S, Z, X = g["F"], g["Q"], g["R"], g["S"], g["Z"], g["X_true"]
+    m0, P0 = g["mean0"], g["P0"]
+    meas = AcousticMeasurement(S, float(g["psi"]), float(g["d0"]), n_targets=4)
+    ssm = LedhGaussianSSM(F, Q, meas, R)
+    pf = LEDHFlowPF(bc.EkfTracker(F, Q, R, ssm.h, ssm.jacobian_h, m0, P0), ssm.g, ssm.h, ssm.jacobian_h, ssm.log_trans_pdf,
+                    ssm.log_like_pdf, R, LEDHConfig(n_particles=N, n_lambda_steps=L, resample_ess_ratio=0.5,
+                                                    rng=np.random.default_rng(0)), dtype=dtype)
     st = pf.init_from_gaussian(m0, P0)
-    for k in range(K):
+    pos = [i for c in range(4) for i in (4 * c, 4 * c + 1)]
+    for k in range(12):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        st = pf.step(st, Z[k], process_noise_sampler="philox")
+        st = pf.step(st, Z[1 + k], process_noise_sampler="philox")
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
-        q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader"],
-                           capture_output=True, text=True).stdout.strip()
-        print(f"step {k:2d} {dt:8.1f} ms  ess {pf.last_ess:10.1f} resampled {pf.last_resampled}  | {q}", flush=True)
+        err = float(np.sqrt(np.mean((np.asarray(st.mean)[pos] - X[1 + k].reshape(-1)[pos]) ** 2)))
+        print(f"step {k:2d} {dt:8.1f} ms  ess {pf.last_ess:12.2f} resampled {pf.last_resampled}  pos rmse {err:7.2f}  "
+              f"mean finite {bool(np.all(np.isfinite(st.mean)))}", flush=True)
 
 
 if __name__ == "__main__":
