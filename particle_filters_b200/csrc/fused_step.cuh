@@ -35,6 +35,9 @@ namespace smc {
 #ifndef SMC_K5_OCC
 #define SMC_K5_OCC 4
 #endif
+#ifndef SMC_K5_UNROLL
+#define SMC_K5_UNROLL 1          // unroll factor of phase E's quad loop (tuning knob)
+#endif
 template <int NX> struct K5Occ { static constexpr int value = NX <= 1 ? SMC_K5_OCC : 2; };
 constexpr int kK5Tile = 4096;
 constexpr int kK5Window = 256 * 18;          // u16 marker slots of the skewed route (aliases the output window)
@@ -321,7 +324,9 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     };
     // one round of phase E over window quads [0, nq): moments of step t-1, functor of step t, stores.
     // `ragged`: quad 0 may start with `lead` foreign lanes and the last quad may be partial (masked path).
+    constexpr int kConsumeUnroll = SMC_K5_UNROLL;
     auto consume = [&](const uint32_t nq, const bool ragged) {
+#pragma unroll kConsumeUnroll
         for (uint32_t q = tid; q < nq; q += THREADS) {
             float xt[NX][4];
 #pragma unroll
