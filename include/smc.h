@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 1
+#define SMC_ABI_VERSION 2
 
 enum { SMC_F32 = 0, SMC_F64 = 1 };
 
@@ -256,6 +256,11 @@ typedef struct smc_shard_ctx {
     void *const *peer_x_dev;
     int32_t rank, n_shards;
     uint64_t stamp;
+    /* fused sharded step only (NULL otherwise): device table [log-weight array 0 of every rank][log-weight
+     * array 1 of every rank][range-total area of every rank]; a range-total area is smc_shard_rsum_bytes() of
+     * zeroed peer-mapped memory; rsum_area_dev = this rank's own area */
+    void *const *peer_aux_dev;
+    void *rsum_area_dev;
 } smc_shard_ctx;
 uint64_t smc_mailbox_bytes(void);
 /* Byte offset of the mailbox's error word: non-zero after a flag wait on this rank timed out (20 s) because a
@@ -266,6 +271,34 @@ int smc_sir_step_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_
                          const double *params_host, int32_t n_params, const double *z_dev,
                          double resample_thresh, uint64_t seed, int64_t t, double *stats_row_dev,
                          void *stream);
+
+/* Sharded form of smc_sir_step_fused: ONE launch and ONE exchange per step of a bootstrap filter (fp32,
+ * STOCH_VOL, shards of >= 12 x SM-count tiles), 16 B per particle-update.  A run is
+ *   smc_sir_weight_sharded            stamp s      K1 of the first step (publishes record + weight total)
+ *   smc_sir_step_fused_sharded x k    stamp s+1..  resample(t-1) -> propagate + weigh(t); first = 1 for the
+ *                                                  launch that follows K1; d->logw_dev = the array holding step
+ *                                                  t-1's log-weights, lw_out_sel = the OTHER array's index
+ *   smc_sir_fused_sharded_flush       stamp s+k+1  finalize of the last step, finish of the one before; with
+ *                                                  resample != 0 also the last step's resampling (pre-pass,
+ *                                                  resampler with migration, finish)
+ * Every launch's prologue waits (bounded) for the slot all ranks published at the end of the launch before,
+ * finalises step t-1 and finishes step t-2 in every CTA (identical arithmetic everywhere; CTA 0 writes
+ * stats_prev_dev = row t-1 and the moments of stats_prev2_dev = row t-2); resampled quads go through the
+ * functor on the rank that holds their ancestor and are stored -- particle, log-weight, fixed-point weight
+ * into the range totals -- into the memory of the rank that owns their index.  The particle sets are
+ * bit-identical to the single-GPU engine's (tests/sharded_check.py). */
+uint64_t smc_shard_rsum_bytes(void);
+int smc_sir_weight_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_t model_id,
+                           const double *params_host, int32_t n_params, const double *z_dev,
+                           double resample_thresh, uint64_t seed, int64_t t, void *stream);
+int smc_sir_step_fused_sharded(const smc_sir_desc *d, const smc_shard_ctx *ctx, int32_t lw_out_sel,
+                               int32_t first, int32_t model_id, const double *params_host,
+                               int32_t n_params, const double *z_dev, double resample_thresh,
+                               uint64_t seed, int64_t t, double *stats_prev2_dev,
+                               double *stats_prev_dev, void *stream);
+int smc_sir_fused_sharded_flush(const smc_sir_desc *d, const smc_shard_ctx *ctx, double resample_thresh,
+                                uint64_t seed, int64_t t_last, double *stats_prev2_dev,
+                                double *stats_prev_dev, int32_t resample, void *stream);
 
 /* Stand-alone pieces used by the drop-in classes' private helpers. */
 

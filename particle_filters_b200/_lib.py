@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMC_LIB_PATH", os.path.join(HERE, "_lib", "libsmc.so"))   # override: kernel tuning sweeps
 
-SMC_ABI_VERSION = 1
+SMC_ABI_VERSION = 2
 SMC_F32, SMC_F64 = 0, 1
 SMC_MODEL_STOCH_VOL, SMC_MODEL_LINEAR_GAUSSIAN, SMC_MODEL_LORENZ96 = 1, 2, 3
 SMC_MODE_PROPAGATE, SMC_MODE_WEIGHT, SMC_MODE_STEP = 1, 2, 3
@@ -51,7 +51,7 @@ class ShardCtx(C.Structure):
     """Mirror of ``smc_shard_ctx`` (include/smc.h)."""
 
     _fields_ = [("mail_dev", C.c_void_p), ("peer_x_dev", C.c_void_p), ("rank", C.c_int32), ("n_shards", C.c_int32),
-                ("stamp", C.c_uint64)]
+                ("stamp", C.c_uint64), ("peer_aux_dev", C.c_void_p), ("rsum_area_dev", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -96,6 +96,13 @@ _SIG = {
     "smc_mailbox_error_offset": (C.c_uint64, []),
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),
+    "smc_shard_rsum_bytes": (C.c_uint64, []),
+    "smc_sir_weight_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
+                                         C.c_double, C.c_uint64, C.c_int64, _P]),
+    "smc_sir_step_fused_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, C.c_int32, C.c_int32, _D,
+                                             C.c_int32, _P, C.c_double, C.c_uint64, C.c_int64, _P, _P, _P]),
+    "smc_sir_fused_sharded_flush": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_double, C.c_uint64, C.c_int64,
+                                              _P, _P, C.c_int32, _P]),
     "smc_systematic_ancestors": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_uint64, _P]),
     "smc_multinomial_workspace_bytes": (C.c_uint64, [C.c_int64]),
     "smc_multinomial_ancestors": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_uint64, C.c_int64, _P, _P,

@@ -55,6 +55,32 @@ template <int NX_> struct CopyModel { static constexpr int NX = NX_, NZ = 1; };
 template <class M> struct K5IsCopy { static constexpr bool value = false; };
 template <int NX_> struct K5IsCopy<CopyModel<NX_>> { static constexpr bool value = true; };
 
+// Sharded form (SHARDED = true): one shard of a G-way split population, ONE launch and ONE exchange per step.
+//  * every CTA's prologue waits (in the rank's own mailbox) for the slot the previous launch of every rank
+//    published, finalises step t-1 and finishes step t-2 on a shared-memory copy of the control block (one warp
+//    each, identical arithmetic on every CTA of every rank) and takes its CDF prefix from the G x G table of
+//    weight contributions plus the rank's own range totals;
+//  * a resampled quad goes through the functor on the rank that holds its ancestor and is then stored -- particle,
+//    log-weight, and its fixed-point weight into the range totals -- into the memory of the rank that owns its index
+//    (NVLink peer stores / 64-bit peer atomics for the few that cross a shard boundary);
+//  * the last CTA publishes the rank's slot of this launch to every mailbox; its flag also certifies that all this
+//    rank's peer stores have landed.
+//  A step whose weights the a-priori bound leaves without resolution runs the range pre-pass inside the kernel
+//  (every CTA its own ranges, a grid barrier, one extra exchange of the shard totals).
+struct K5Shard {
+    ShardCtx ctx;              // stamp = this launch's; the slot it consumes carries stamp - 1
+    int64_t n_global, offset, shard_n;
+    int32_t first;             // step t-1's log-weights were written by K1: records in flag_rec / rec / tot
+    float* const* peer_x0;     // per-rank particle buffers (device tables of G pointers)
+    float* const* peer_x1;
+    float* const* peer_lw_out; // per-rank log-weight arrays of step t
+    unsigned long long* const* peer_rsum;   // per-rank range-total areas: two buffers of kRsumStride, then G accumulators
+    int32_t rsel_in, rsel_out; // which buffer of the area this launch reads (first: the workspace's) / accumulates into
+    unsigned int* gbar;        // grid-barrier counter of the in-kernel pre-pass
+    K2Args pfin;               // finalize of step t-1
+    FinishArgs pfinish;        // finish of step t-2
+};
+
 struct K5Args {
     Ctrl* ctrl;
     const float* lw_in;        // log-weights of step t-1
@@ -75,11 +101,48 @@ struct K5Args {
     unsigned int* ticket;
     FinishArgs fin;            // finish of step t-1
     K2Args fin2;               // finalize of step t
+    K5Shard sh;                // sharded form only
 };
 
-template <int NX, class Model>
-__global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K5Args a, Model fm) {
+// one-warp finish of a resampled step from G moment records (finish_body's arithmetic on a handful of records):
+// posterior mean / covariance into the statistics row (`stats` nullable: the shift is refreshed all the same)
+__device__ inline void finish_warp(Ctrl* c, const FinishArgs& f, const double* mom, int n_parts, int stride,
+                                   double* stats, double* s_m) {
+    const int lane = threadIdx.x & 31, nm = moment_stride(f.nx);
+    if (lane < nm) {
+        double t = 0;
+        for (int p = 0; p < n_parts; ++p) t += __ldcg(mom + (int64_t)p * stride + lane);     // rank order
+        s_m[lane] = t;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double inv = 1.0 / (double)f.n_global;
+        double m1[kFusedNxMax], mean[kFusedNxMax];
+        for (int d = 0; d < f.nx; ++d) { m1[d] = s_m[d] * inv; mean[d] = c->shift[d] + m1[d]; }
+        if (stats) {
+            double* cov = stats + SMC_STATS_HEADER + f.nx;
+            int k = f.nx;
+            for (int d = 0; d < f.nx; ++d) {
+                stats[SMC_STATS_HEADER + d] = mean[d];
+                for (int d2 = 0; d2 <= d; ++d2) {
+                    const double v = s_m[k++] * inv - m1[d] * m1[d2];
+                    cov[d * f.nx + d2] = v;
+                    cov[d2 * f.nx + d] = v;
+                }
+            }
+        }
+        for (int d = 0; d < f.nx && d < kMaxNx; ++d) c->shift[d] = mean[d];
+    }
+    __syncwarp();
+}
+
+template <bool SHARDED> struct K5CtrlCopy { Ctrl c; unsigned long long contrib[kMaxShards]; double pout[32]; double m[16]; };
+template <> struct K5CtrlCopy<false> { int unused; };
+
+template <int NX, class Model, bool SHARDED = false>
+__global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resample_propagate(K5Args a, Model fm) {
     static_assert(Model::NX == NX, "functor / payload mismatch");
+    static_assert(!SHARDED || !K5IsCopy<Model>::value, "the sharded form always carries a functor");
     constexpr int THREADS = 256, WARPS = 8, IPT = 16, UPT = 4, TILE = kK5Tile;
     constexpr int W = kK5Window, WIN = kK5WinStride, CH = IPT + 2;
     constexpr uint32_t MAXD = 4 * IPT;
@@ -106,12 +169,58 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     double (*s_fred)[2] = reinterpret_cast<double (*)[2]>(s_ftmp + WARPS);        // [WARPS][2]
     float* s_fmax = reinterpret_cast<float*>(s_ftmp + WARPS + 2 * WARPS);         // [WARPS]
 
-    Ctrl* ctrl = a.ctrl;
+    Ctrl* const gctrl = a.ctrl;
+    Ctrl* ctrl = gctrl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
     pdl_trigger();
+    __shared__ K5CtrlCopy<SHARDED> s_sh;
+    [[maybe_unused]] Mailbox* own = nullptr;
+    [[maybe_unused]] const FusedSlot* slot_in = nullptr;
+    [[maybe_unused]] const int G = SHARDED ? a.sh.ctx.n_shards : 1;
+    if constexpr (SHARDED) {
+        // every CTA: wait for the G slots of the previous launch, then finalize(t-1) and finish(t-2) on a private copy
+        // of the control block (CTA 0 also writes the statistics rows; the last CTA copies the block back)
+        for (int i = tid; i < (int)(sizeof(Ctrl) / 4); i += THREADS)
+            reinterpret_cast<uint32_t*>(&s_sh.c)[i] = reinterpret_cast<const uint32_t*>(gctrl)[i];
+        if (tid < kMaxShards) s_sh.contrib[tid] = 0ull;
+        own = a.sh.ctx.mail[a.sh.ctx.rank];
+        const unsigned long long prev = a.sh.ctx.stamp - 1ull;
+        slot_in = &own->fs[prev & 1ull];
+        mailbox_wait(a.sh.first ? own->flag_rec : slot_in->flag, G, prev, &own->error, 4);
+        K2Args f = a.sh.pfin;
+        f.ctrl = &s_sh.c; f.n_parts = G;
+        if (a.sh.first) {
+            f.parts = &own->rec[0][0]; f.rec_stride = 32;
+            f.producer_rsum = f.producer_rsum && s_sh.c.uniform != 0;      // K1 delivered range totals iff the step was a bootstrap step
+        } else {
+            f.parts = &slot_in->rec[0][0]; f.rec_stride = 4;
+        }
+        if (blockIdx.x != 0) f.stats = nullptr;
+        if (warp == 0) finalize_warp(f, s_sh.pout);
+        if (warp == 1 && !a.sh.first && a.sh.pfinish.stats && !a.sh.pfinish.no_moments)
+            finish_warp(&s_sh.c, a.sh.pfinish, &slot_in->mom[0][0], G, 16, blockIdx.x == 0 ? a.sh.pfinish.stats : nullptr, s_sh.m);
+        __syncthreads();
+        ctrl = &s_sh.c;
+    }
     if (!ctrl->do_resample) {
         // (only a filter whose weights have all vanished gets here) nothing to resample: moment-shift refresh
+        if constexpr (SHARDED) {
+            // ... and an empty slot, so that no peer waits for this rank
+            if (blockIdx.x == 0) {
+                if (tid < G) {
+                    FusedSlot* so = &a.sh.ctx.mail[tid]->fs[a.sh.ctx.stamp & 1ull];
+                    so->rec[a.sh.ctx.rank][0] = -INFINITY; so->rec[a.sh.ctx.rank][1] = 0.0; so->rec[a.sh.ctx.rank][2] = 0.0;
+                    for (int g = 0; g < G; ++g) so->contrib[a.sh.ctx.rank][g] = 0ull;
+                    for (int k = 0; k < 16; ++k) so->mom[a.sh.ctx.rank][k] = 0.0;
+                }
+                if (tid == 0) *gctrl = s_sh.c;
+                __threadfence_system();
+                __syncthreads();
+                if (tid < G) *(volatile unsigned long long*)&a.sh.ctx.mail[tid]->fs[a.sh.ctx.stamp & 1ull].flag[a.sh.ctx.rank] = a.sh.ctx.stamp;
+            }
+            return;
+        }
         if (blockIdx.x == 0 && tid == 0 && a.fin.stats && !a.fin.no_moments)
             for (int d = 0; d < a.fin.nx && d < kMaxNx; ++d) ctrl->shift[d] = a.fin.stats[SMC_STATS_HEADER + d];
         return;
@@ -120,10 +229,23 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     const float* xsrc = cur ? a.x1 : a.x0;
     float* xdst = cur ? a.dst0 : a.dst1;
     const int sel = ctrl->rsum_sel;
+    // range totals: single GPU = the workspace's two buffers (ctrl->rsum_sel: the one to read); sharded = the rank's
+    // peer-mapped area (the first fused launch of a run still reads what K1 left in the workspace)
     const unsigned long long* rin = a.rsum + (size_t)sel * kRsumStride;
     unsigned long long* rout = a.rsum + (size_t)(sel ^ 1) * kRsumStride;
+    [[maybe_unused]] float* const* px = nullptr;                // sharded: per-rank destination tables
+    [[maybe_unused]] float* const* plw = nullptr;
+    [[maybe_unused]] const uint32_t shard_n = SHARDED ? (uint32_t)a.sh.shard_n : 0u;
+    if constexpr (SHARDED) {
+        px = cur ? a.sh.peer_x0 : a.sh.peer_x1;
+        plw = a.sh.peer_lw_out;
+        if (!a.sh.first) rin = a.sh.peer_rsum[a.sh.ctx.rank] + (size_t)a.sh.rsel_in * kRsumStride;
+        rout = a.sh.peer_rsum[a.sh.ctx.rank] + (size_t)a.sh.rsel_out * kRsumStride;
+    }
     const float kshift_in = ctrl->kshift;
-    const uint32_t Nn = (uint32_t)a.n;
+    const int64_t n_glob = SHARDED ? a.sh.n_global : a.n;
+    const int64_t g_off = SHARDED ? a.sh.offset : 0;            // global index of this shard's first particle
+    const uint32_t Nn = (uint32_t)n_glob;
 
     const int64_t t_begin = k3_range_begin(blockIdx.x, a.n_tiles, gridDim.x);
     const int64_t t_end = k3_range_begin(blockIdx.x + 1, a.n_tiles, gridDim.x);
@@ -183,12 +305,78 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     // exclusive CDF prefix of this CTA's first tile and the CDF total, from the range totals
     unsigned long long prefix, cdf_total;
     {
+        [[maybe_unused]] bool own_totals = false;      // sharded: shard totals from Mailbox::tot (K1 / in-kernel pre-pass)
+        if constexpr (SHARDED) {
+            own_totals = a.sh.first != 0;
+            if (!ctrl->rsum_valid) {
+                // The a-priori bound left this step's weights without resolution (or K1 delivered no totals): range
+                // pre-pass inside the kernel against the reference the finalize chose -- every CTA its own ranges, a
+                // grid barrier (the grid is resident: 3 CTAs per SM), CTA 0 publishes the shard total
+                unsigned long long* rt = const_cast<unsigned long long*>(rin);
+                for (int rr = 0; rr < a.ranges_per_cta; ++rr) {
+                    const int r = (int)blockIdx.x * a.ranges_per_cta + rr;
+                    const int64_t tr0 = k3_range_begin(r, a.n_tiles, a.n_ranges), tr1 = k3_range_begin(r + 1, a.n_tiles, a.n_ranges);
+                    unsigned long long acc = 0;
+                    for (int64_t i = tr0 * TILE + tid; i < tr1 * TILE && i < a.n; i += THREADS)
+                        acc += quant_a(quant_p(a.lw_in[i], kshift_in));
+                    acc = warp_sum(acc);
+                    __syncthreads();
+                    if (lane == 0) s_warp_tot[warp] = acc;
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned long long t = 0;
+#pragma unroll
+                        for (int w = 0; w < WARPS; ++w) t += s_warp_tot[w];
+                        rt[r] = t;
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    atomicAdd(a.sh.gbar, 1u);
+                    while (*(volatile unsigned int*)a.sh.gbar < gridDim.x) __nanosleep(40);
+                }
+                __syncthreads();
+                __threadfence();
+                if (blockIdx.x == 0) {
+                    unsigned long long t = 0;
+                    for (int i = tid; i < a.n_ranges; i += THREADS) t += __ldcg(rt + i);
+                    t = warp_sum(t);
+                    __syncthreads();
+                    if (lane == 0) s_warp_tot[warp] = t;
+                    __syncthreads();
+                    if (tid == 0) {
+                        unsigned long long tot = 0;
+#pragma unroll
+                        for (int w = 0; w < WARPS; ++w) tot += s_warp_tot[w];
+                        for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->tot[a.sh.ctx.rank] = tot;
+                        __threadfence_system();
+                        for (int g = 0; g < G; ++g)
+                            *(volatile unsigned long long*)&a.sh.ctx.mail[g]->flag_tot[a.sh.ctx.rank] = a.sh.ctx.stamp;
+                    }
+                    __syncthreads();
+                }
+                mailbox_wait(own->flag_tot, G, a.sh.ctx.stamp, &own->error, 2);
+                own_totals = true;
+            }
+        }
         unsigned long long part = 0, all = 0;
         const int mine = (int)blockIdx.x * a.ranges_per_cta;
         for (int i = tid; i < a.n_ranges; i += THREADS) {
             const unsigned long long v = __ldcg(rin + i);
             if (i < mine) part += v;
             all += v;
+        }
+        if constexpr (SHARDED) {
+            // the CDF runs over ALL shards: offset = the total weight of the lower ranks
+            all = 0;
+            if (tid < G) {
+                unsigned long long v = 0;
+                if (own_totals) v = __ldcg(&own->tot[tid]);
+                else for (int src = 0; src < G; ++src) v += __ldcg(&slot_in->contrib[src][tid]);
+                if (tid < a.sh.ctx.rank) part += v;
+                all = v;
+            }
         }
         part = warp_sum(part);
         all = warp_sum(all);
@@ -199,7 +387,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         for (int w = 0; w < WARPS; ++w) { prefix += s_warp_tot[w]; cdf_total += s_warp_all[w]; }
         __syncthreads();
     }
-    const RhoMap rm = make_rho(cdf_total, a.n, 0xffffffffull - ctrl->uq);
+    const RhoMap rm = make_rho(cdf_total, n_glob, 0xffffffffull - ctrl->uq);
 
     float shift[NX];
 #pragma unroll
@@ -213,12 +401,43 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
 #pragma unroll
     for (int k = 0; k < NZ; ++k) fz[k] = COPY ? 0.f : (float)a.z[k];
     float f_tm = -INFINITY, f_acc0 = 0.f, f_acc1 = 0.f;
-    const float f_lw_uniform = (float)(-log((double)a.n));
+    const float f_lw_uniform = (float)(-log((double)n_glob));
     // range cursor: the pre-pass range (k3_range_begin over n_ranges) that holds the thread's current quad
     const uint32_t cR = (uint32_t)a.n_ranges, cTd = (uint32_t)(a.n_tiles / a.n_ranges), cTm = (uint32_t)(a.n_tiles % a.n_ranges);
     uint32_t cur_r = 0xffffffffu, cur_bnd = 0u, cur_rem = 0u;
     unsigned long long cur_acc = 0ull;
-    auto cursor_slow = [&](const uint32_t gi0) {
+    // sharded: destination cursor -- the rank whose index range [d_lo, d_hi) holds the thread's current quad (a
+    // thread's quads have increasing global indices), and that rank's buffers
+    [[maybe_unused]] uint32_t d_lo = 0u, d_hi = 0u;
+    [[maybe_unused]] int d_rank = -1;
+    float* xq = xdst;                    // destination particle buffer, log-weight array and range totals of the quad
+    float* lwq_out = a.lw_out;
+    unsigned long long* rq = rout;
+    [[maybe_unused]] unsigned long long my_contrib = 0ull;    // sharded: weight this thread produced for rank d_rank
+    [[maybe_unused]] bool wrote_peer = false;
+    auto flush_acc = [&]() {
+        if (cur_acc) {
+            atomicAdd(rq + cur_r, cur_acc);
+            if constexpr (SHARDED) my_contrib += cur_acc;
+        }
+        cur_acc = 0ull;
+    };
+    [[maybe_unused]] auto retarget = [&](const uint32_t gi0) {
+        if (d_rank >= 0 && cur_r != 0xffffffffu) flush_acc();
+        if constexpr (SHARDED) {
+            if (d_rank >= 0 && my_contrib) atomicAdd(&s_sh.contrib[d_rank], my_contrib);     // (only threads that cross a shard boundary)
+            my_contrib = 0ull;
+        }
+        d_rank = (int)(gi0 / shard_n);
+        if constexpr (SHARDED) wrote_peer = wrote_peer || d_rank != a.sh.ctx.rank;
+        d_lo = (uint32_t)d_rank * shard_n; d_hi = d_lo + shard_n;
+        if constexpr (SHARDED) {
+            xq = px[d_rank]; lwq_out = plw[d_rank];
+            rq = a.sh.peer_rsum[d_rank] + (size_t)a.sh.rsel_out * kRsumStride;
+        }
+        cur_r = 0xffffffffu; cur_bnd = 0u; cur_acc = 0ull;
+    };
+    auto cursor_slow = [&](const uint32_t gi0) {                     // gi0: index within the destination shard
         if (cur_r == 0xffffffffu) {                                  // first quad of this thread: locate its range
             const unsigned long long tile = gi0 >> 12;
             const unsigned long long r = ((tile + 1ull) * cR - 1ull) / (unsigned long long)a.n_tiles;
@@ -228,8 +447,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
             cur_r = (uint32_t)r; cur_rem = s - (c ? cR : 0u); cur_bnd = (beg + cTd + c) << 12;
         } else {
             do {
-                if (cur_acc) atomicAdd(rout + cur_r, cur_acc);
-                cur_acc = 0ull;
+                flush_acc();
                 ++cur_r;
                 const uint32_t s = cur_rem + cTm, c = s >= cR ? 1u : 0u;
                 cur_rem = s - (c ? cR : 0u); cur_bnd += (cTd + c) << 12;
@@ -254,7 +472,12 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                     }
             }
         } else {
-        if (gi0 >= cur_bnd) cursor_slow(gi0);
+        uint32_t li0 = gi0;                                          // index within the destination shard
+        if constexpr (SHARDED) {
+            if (gi0 >= d_hi) retarget(gi0);
+            li0 = gi0 - d_lo;
+        }
+        if (li0 >= cur_bnd) cursor_slow(li0);
         float nrm[NX][4];
         Draw<NX>::run(a.keys, (uint64_t)(gi0 >> 2), a.t, nrm);
         float lwq[4];
@@ -272,15 +495,15 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         }
         if (FULL) {
 #pragma unroll
-            for (int d = 0; d < NX; ++d) store4<float>(xdst + d * a.ld + gi0, xt[d]);
-            store4<float>(a.lw_out + gi0, lwq);
+            for (int d = 0; d < NX; ++d) store4<float>(xq + d * a.ld + li0, xt[d]);
+            store4<float>(lwq_out + li0, lwq);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if ((mask >> j) & 1u) {
 #pragma unroll
-                    for (int d = 0; d < NX; ++d) xdst[d * a.ld + gi0 + j] = xt[d][j];
-                    a.lw_out[gi0 + j] = lwq[j];
+                    for (int d = 0; d < NX; ++d) xq[d * a.ld + li0 + j] = xt[d][j];
+                    lwq_out[li0 + j] = lwq[j];
                 }
         }
         const float cmax = fmaxf(fmaxf(lwq[0], lwq[1]), fmaxf(lwq[2], lwq[3]));
@@ -420,7 +643,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         const unsigned long long Ps = map_pos(base_raw, rm), Pe = map_pos(base_raw + run, rm);
         uint32_t e_start = umin((uint32_t)(Ps >> 32), Nn), e_end = umin((uint32_t)(Pe >> 32), Nn);
         int klast = IPT;               // first local item that owns the tail: cumsum[-1] = 1 (particle_filter.py:163)
-        if (tile_base + TILE >= a.n) { // the last tile
+        if (tile_base + TILE >= a.n && g_off + a.n >= n_glob) { // the last tile of the (global) population
             const int64_t j0 = tile_base + (int64_t)tid * IPT;
             if (j0 + IPT >= a.n) {
                 e_end = Nn;
@@ -580,10 +803,16 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                         int li1 = (int)ids[i];
                         if (li1 == 0) li1 = 1;                               // (only on inconsistent input)
                         float xv[NX];
+                        float* xo = xdst + gb + i;
+                        if constexpr (SHARDED) {
+                            const uint32_t gi = gb + (uint32_t)i, r = gi / shard_n;
+                            xo = px[r] + (gi - r * shard_n);
+                            wrote_peer = wrote_peer || (int)r != a.sh.ctx.rank;
+                        }
 #pragma unroll
                         for (int d = 0; d < NX; ++d) {
                             xv[d] = x_of(d, li1 - 1);
-                            xdst[d * a.ld + gb + i] = xv[d];
+                            xo[d * a.ld] = xv[d];
                         }
                         add_moments(xv);
                     }
@@ -604,8 +833,13 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
                         const uint32_t gi = gi0 + j;
                         const bool valid = gi >= E0 && gi < E1;
                         if (valid) mask |= 1u << j;
+                        const float* xi = xdst + gi;
+                        if constexpr (SHARDED) {
+                            const uint32_t r = gi0 / shard_n;             // (a quad never straddles two shards)
+                            xi = px[r] + (gi - r * shard_n);
+                        }
 #pragma unroll
-                        for (int d = 0; d < NX; ++d) xt[d][j] = valid ? xdst[d * a.ld + gi] : 0.f;
+                        for (int d = 0; d < NX; ++d) xt[d][j] = valid ? (SHARDED ? __ldcg(xi + d * a.ld) : xi[d * a.ld]) : 0.f;
                     }
                     process_quad(PartQuad(), xt, gi0, mask);
                 }
@@ -618,7 +852,7 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
         for (int k = 0; k < NM; ++k) { macc_d[k] += (double)macc[k]; macc[k] = 0.f; }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
-    if (!COPY && cur_r != 0xffffffffu && cur_acc) atomicAdd(rout + cur_r, cur_acc);
+    if (!COPY && cur_r != 0xffffffffu) flush_acc();
 
     __syncthreads();                                         // the tile buffers are dead: reuse them as scratch
     if (!COPY) {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
@@ -658,6 +892,71 @@ __global__ void __launch_bounds__(256, K5Occ<NX>::value) k5_resample_propagate(K
     }
     // the last CTA to arrive: finish of step t-1 (moments, buffer flip, shift refresh), hand-over of the
     // range-total buffers, finalize of step t (normaliser, ESS, decision, u, quantisation reference)
+    if constexpr (SHARDED) {
+        // the CTA's share of the weight this rank produced for every rank's index range; every peer store / peer
+        // atomic of this CTA is made visible system-wide before it takes its ticket
+        for (int g = 0; g < G; ++g) {
+            const unsigned long long v = warp_sum(d_rank == g ? my_contrib : 0ull);
+            if (lane == 0 && v) atomicAdd(&s_sh.contrib[g], v);
+        }
+        __syncthreads();
+        if (tid < G && s_sh.contrib[tid]) atomicAdd(a.sh.peer_rsum[a.sh.ctx.rank] + 2 * kRsumStride + tid, s_sh.contrib[tid]);
+        if (wrote_peer) __threadfence_system(); else __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            // the last CTA publishes this launch's slot to every rank: record of step t's log-weights, post-resample
+            // moments of step t-1, weight contributions; then the flag
+            __threadfence();
+            const int rank = a.sh.ctx.rank;
+            const unsigned long long slot = a.sh.ctx.stamp & 1ull;
+            combine_partials(a.parts, (int)gridDim.x, 3, s_fout, s_ftmp, 0);
+            if (tid < 3)
+                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].rec[rank][tid] = s_fout[tid];
+            if (a.mom_parts) {
+                double acc[NM];
+#pragma unroll
+                for (int k = 0; k < NM; ++k) acc[k] = 0.0;
+                for (int p = tid; p < (int)gridDim.x; p += THREADS)          // fixed record -> thread assignment
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) acc[k] += __ldcg(a.mom_parts + (int64_t)p * NM + k);
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < NM; ++k) {
+                    const double v = warp_sum(acc[k]);
+                    if (lane == 0) s_mom[warp][k] = v;
+                }
+                __syncthreads();
+                if (tid < NM) {
+                    double t = 0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) t += s_mom[w][tid];
+                    for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].mom[rank][tid] = t;
+                }
+            }
+            unsigned long long* acc_g = a.sh.peer_rsum[rank] + 2 * kRsumStride;
+            if (tid < G) {
+                const unsigned long long v = __ldcg(acc_g + tid);
+                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].contrib[rank][tid] = v;
+                acc_g[tid] = 0ull;
+            }
+            // every CTA of this rank has read the totals of step t-1: clear that buffer for the launch after the next
+            // (the peers accumulate into it only once they have seen this launch's flag)
+            if (!a.sh.first)
+                for (int i = tid; i < kRsumStride; i += THREADS) const_cast<unsigned long long*>(rin)[i] = 0ull;
+            if (tid == 0) {
+                s_sh.c.cur ^= 1;                                  // the resampled, propagated set is the current one
+                *gctrl = s_sh.c;
+                *a.sh.gbar = 0u;
+                *a.ticket = 0u;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < G) *(volatile unsigned long long*)&a.sh.ctx.mail[tid]->fs[slot].flag[rank] = a.sh.ctx.stamp;
+        }
+        return;
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);

@@ -99,7 +99,18 @@ struct Mailbox {
     double rec[kMaxShards][32];
     double mom[kMaxShards][16];
     unsigned long long error;    // != 0: a wait on this rank timed out (bit 63 | stamp << 8 | exchange << 4 | peer rank)
+    // single-exchange fused step (k5_resample_propagate, sharded form): everything launch t publishes -- the record
+    // of step t's log-weights, the post-resample moments of step t-1, the fixed-point weight this rank produced
+    // for every rank's index range -- under ONE flag.  Two slots (stamp & 1): a peer may finish launch t before this
+    // rank has read the slot of launch t-1, but cannot pass the prologue of launch t+1 without this rank's flag t.
+    struct FusedSlot {
+        unsigned long long flag[kMaxShards];
+        unsigned long long contrib[kMaxShards][kMaxShards];    // [producing rank][rank that owns the indices]
+        double rec[kMaxShards][4];                             // (max, sum e, sum e^2) of the producing rank
+        double mom[kMaxShards][16];
+    } fs[2];
 };
+using FusedSlot = Mailbox::FusedSlot;
 struct ShardCtx {
     Mailbox* const* mail;        // device array of n_shards mailbox pointers (own one included)
     int32_t rank, n_shards;
@@ -2788,6 +2799,95 @@ int launch_k5(const Launch& l, const Model& m, const void* lw_in, void* lw_out, 
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+// ---- sharded fused step: K5 on one shard, one launch and one exchange per step ---------------------------
+// flush of a sharded fused run: finalize of the last step and finish of the one before it from the slot the last
+// launch published (what the next launch's prologue would have done), into the GLOBAL control block
+__global__ void __launch_bounds__(kThreads) k5s_flush(Ctrl* ctrl, K2Args pfin, FinishArgs pfinish, ShardCtx sc,
+                                                      unsigned long long* rsum_area) {
+    __shared__ double s_pout[32];
+    __shared__ double s_m[16];
+    Mailbox* own = sc.mail[sc.rank];
+    const unsigned long long prev = sc.stamp - 1ull;
+    const FusedSlot* slot = &own->fs[prev & 1ull];
+    mailbox_wait(slot->flag, sc.n_shards, prev, &own->error, 4);
+    const int warp = threadIdx.x >> 5;
+    pfin.ctrl = ctrl; pfin.parts = &slot->rec[0][0]; pfin.rec_stride = 4; pfin.n_parts = sc.n_shards;
+    if (warp == 0) finalize_warp(pfin, s_pout);
+    if (warp == 1 && pfinish.stats && !pfinish.no_moments)
+        finish_warp(ctrl, pfinish, &slot->mom[0][0], sc.n_shards, 16, pfinish.stats, s_m);
+    // every rank has finished its last fused launch: nobody accumulates into this rank's range totals any more
+    for (int i = threadIdx.x; i < 2 * kRsumStride + kMaxShards; i += kThreads) rsum_area[i] = 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) ctrl->rsum_valid = 0;      // the resampling that follows takes its range totals from a pre-pass
+}
+
+inline int64_t k5s_grid() { return (int64_t)sm_count() * 3; }
+inline bool k5_sharded_ok(const Launch& l) {
+    const smc_sir_desc* d = l.d;
+    if (d->dtype != SMC_F32 || d->nx != 1 || d->n % 4096 != 0) return false;
+    if (d->flags & (SMC_FLAG_WRITE_ANCESTORS | SMC_FLAG_POST_MOMENTS_GENERIC | SMC_FLAG_GENERIC_MOMENTS)) return false;
+    const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, d->nx);
+    return l.L.n_tiles >= ranges && ranges % k5s_grid() == 0 && ranges <= kRsumStride;
+}
+
+template <class Model>
+int launch_k5_sharded(const Launch& l, const Model& m, const smc_shard_ctx* ctx, int lw_out_sel, int first,
+                      const double* z_dev, double resample_thresh, uint64_t seed, int64_t t, double* stats_prev2_dev,
+                      double* stats_prev_dev) {
+    constexpr int NX = Model::NX;
+    const smc_sir_desc* d = l.d;
+    const int G = ctx->n_shards;
+    K5Args a;
+    memset(&a, 0, sizeof(a));
+    a.ctrl = l.ctrl();
+    a.lw_in = static_cast<const float*>(d->logw_dev);
+    a.x0 = static_cast<const float*>(d->x0_dev); a.x1 = static_cast<const float*>(d->x1_dev);
+    a.dst0 = static_cast<float*>(d->x0_dev); a.dst1 = static_cast<float*>(d->x1_dev);
+    a.rsum = l.agg();
+    a.mom_parts = (d->flags & SMC_FLAG_NO_MOMENTS) ? nullptr : l.mom_parts();
+    a.parts = l.k1_parts();
+    a.z = z_dev;
+    a.keys = philox_expand(seed);
+    a.t = (uint32_t)t;
+    a.n = d->n; a.ld = d->ld; a.n_tiles = l.L.n_tiles;
+    const int64_t grid = k5s_grid();
+    const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
+    a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
+    a.ticket = l.ticket() + 1;
+    quant_bound_for(d->n_global, &a.sh.pfin.lw_bound, &a.sh.pfin.kshift_bound);
+    a.kshift_bound = a.sh.pfin.kshift_bound;
+    K5Shard& sh = a.sh;
+    sh.ctx.mail = reinterpret_cast<Mailbox* const*>(ctx->mail_dev);
+    sh.ctx.rank = ctx->rank; sh.ctx.n_shards = G; sh.ctx.stamp = ctx->stamp;
+    sh.n_global = d->n_global; sh.offset = d->offset; sh.shard_n = d->n;
+    sh.first = first;
+    float* const* px = reinterpret_cast<float* const*>(ctx->peer_x_dev);
+    void* const* aux = ctx->peer_aux_dev;
+    sh.peer_x0 = px; sh.peer_x1 = px + G;
+    sh.peer_lw_out = reinterpret_cast<float* const*>(aux + (size_t)lw_out_sel * G);
+    sh.peer_rsum = reinterpret_cast<unsigned long long* const*>(aux + 2 * (size_t)G);
+    sh.rsel_in = (int32_t)((ctx->stamp - 1) & 1); sh.rsel_out = (int32_t)(ctx->stamp & 1);
+    sh.gbar = l.ticket() + 3;
+    sh.pfin.stats = stats_prev_dev; sh.pfin.n_global = d->n_global; sh.pfin.nx = d->nx;
+    sh.pfin.inline_moments = first ? 1 : 0; sh.pfin.f32 = 1;
+    sh.pfin.thresh = resample_thresh; sh.pfin.u_host = -1.0; sh.pfin.seed = seed; sh.pfin.t = (uint32_t)(t - 1);
+    sh.pfin.producer_rsum = first ? (k1_rsum_ok(l) ? 1 : 0) : 1;
+    sh.pfinish.stats = first ? nullptr : stats_prev2_dev; sh.pfinish.nx = d->nx; sh.pfinish.inline_moments = 1;
+    sh.pfinish.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; sh.pfinish.n_global = d->n_global;
+    auto kern = k5_resample_propagate<NX, Model, true>;
+    const size_t smem = k5_smem_bytes<NX>();
+    static bool attr_set = false;   // one flag per template instantiation
+    if (!attr_set) {
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    SMC_CHECK_CUDA(launch_pdl(kern, (unsigned)grid, 256u, smem, l.st, a, m));
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // whether the plain fp32 resampler can be K5<CopyModel> (else k3_resample)
 inline bool k5_copy_ok(const Launch& l) {
     const smc_sir_desc* d = l.d;
@@ -3240,6 +3340,7 @@ int smc_sir_step_fused(const smc_sir_desc* d, void* logw_out_dev, int32_t model_
 // ---- multi-GPU: whole sharded step with mailbox exchanges (no collective calls) ----------------
 uint64_t smc_mailbox_bytes(void) { return sizeof(Mailbox); }
 uint64_t smc_mailbox_error_offset(void) { return offsetof(Mailbox, error); }
+uint64_t smc_shard_rsum_bytes(void) { return sizeof(unsigned long long) * (2 * kRsumStride + kMaxShards); }
 
 int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t model_id, const double* params_host,
                          int32_t n_params, const double* z_dev, double resample_thresh, uint64_t seed, int64_t t,
@@ -3311,6 +3412,91 @@ int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_
         f.n_mom_parts = 0;
         k_finish_step<<<1, kFinishThreads, 0, l.st>>>(l.ctrl(), f);
     }
+    SMC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- sharded fused run: K1 of the first step, then one k5_resample_propagate launch per step, then flush ----
+static int shard_ctx_check(const smc_sir_desc* d, const smc_shard_ctx* ctx, ShardCtx* sc) {
+    SMC_REQUIRE(ctx && ctx->mail_dev && ctx->peer_x_dev, "smc: shard context incomplete");
+    const int G = ctx->n_shards, rank = ctx->rank;
+    SMC_REQUIRE(G >= 1 && G <= kMaxShards && rank >= 0 && rank < G, "smc: bad shard geometry (rank %d of %d)", rank, G);
+    SMC_REQUIRE(d->n_global % G == 0 && d->n == d->n_global / G && d->offset == (int64_t)rank * d->n,
+                "smc: inconsistent shard geometry (rank %d of %d)", rank, G);
+    SMC_REQUIRE(ctx->stamp > 0, "smc: stamp must be positive and increase by one per launch group");
+    sc->mail = reinterpret_cast<Mailbox* const*>(ctx->mail_dev);
+    sc->rank = rank; sc->n_shards = G; sc->stamp = ctx->stamp;
+    return 0;
+}
+
+int smc_sir_weight_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t model_id, const double* params_host,
+                           int32_t n_params, const double* z_dev, double resample_thresh, uint64_t seed, int64_t t,
+                           void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    ShardCtx sc;
+    if (int rc = shard_ctx_check(d, ctx, &sc)) return rc;
+    SMC_REQUIRE(d->nx <= kFusedNxMax && inline_moments(d), "smc: sharded step requires nx <= %d", kFusedNxMax);
+    SMC_REQUIRE(params_host != nullptr && z_dev != nullptr, "smc: params / observation missing");
+    const int mode = SMC_MODE_STEP | (resample_thresh > 1.0 ? 4 : 0);
+    return d->dtype == SMC_F32
+               ? dispatch_k1<float>(l, model_id, params_host, n_params, mode, z_dev, nullptr, seed, t, nullptr, &sc)
+               : dispatch_k1<double>(l, model_id, params_host, n_params, mode, z_dev, nullptr, seed, t, nullptr, &sc);
+}
+
+int smc_sir_step_fused_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t lw_out_sel, int32_t first,
+                               int32_t model_id, const double* params_host, int32_t n_params, const double* z_dev,
+                               double resample_thresh, uint64_t seed, int64_t t, double* stats_prev2_dev,
+                               double* stats_prev_dev, void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    ShardCtx sc;
+    if (int rc = shard_ctx_check(d, ctx, &sc)) return rc;
+    SMC_REQUIRE(ctx->peer_aux_dev, "smc: the fused sharded step needs the peer tables of the log-weight arrays and range totals");
+    SMC_REQUIRE(ctx->stamp > 1, "smc: the fused sharded step follows smc_sir_weight_sharded (stamp - 1) or another fused step");
+    SMC_REQUIRE(k5_sharded_ok(l), "smc: the fused sharded step is the fp32, nx = 1 throughput path for shards of at least "
+                                  "%d tiles of 4096 particles", sm_count() * 12);
+    SMC_REQUIRE(resample_thresh > 1.0, "smc: the fused step is for filters that resample every step (thresh > 1)");
+    SMC_REQUIRE(lw_out_sel == 0 || lw_out_sel == 1, "smc: lw_out_sel selects one of the two log-weight arrays");
+    SMC_REQUIRE(model_id == SMC_MODEL_STOCH_VOL && n_params == 4 && d->nz == 1 && params_host && z_dev,
+                "smc: the fused sharded step is compiled for STOCH_VOL");
+    StochVolModel<float> m;
+    m.alpha = (float)params_host[0]; m.lq = (float)params_host[1]; m.beta = (float)params_host[2];
+    m.rinv = (float)(1.0 / params_host[3]);
+    return launch_k5_sharded(l, m, ctx, lw_out_sel, first, z_dev, resample_thresh, seed, t, stats_prev2_dev, stats_prev_dev);
+}
+
+int smc_sir_fused_sharded_flush(const smc_sir_desc* d, const smc_shard_ctx* ctx, double resample_thresh, uint64_t seed,
+                                int64_t t_last, double* stats_prev2_dev, double* stats_prev_dev, int32_t resample,
+                                void* stream) {
+    Launch l;
+    if (int rc = check_desc(d, &l, stream)) return rc;
+    ShardCtx sc;
+    if (int rc = shard_ctx_check(d, ctx, &sc)) return rc;
+    SMC_REQUIRE(ctx->peer_aux_dev && ctx->rsum_area_dev && ctx->stamp > 1, "smc: flush follows a fused sharded step");
+    K2Args fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.stats = stats_prev_dev; fin.n_global = d->n_global; fin.nx = d->nx; fin.inline_moments = 0; fin.f32 = 1;
+    quant_bound_for(d->n_global, &fin.lw_bound, &fin.kshift_bound);
+    fin.thresh = resample_thresh; fin.u_host = -1.0; fin.seed = seed; fin.t = (uint32_t)t_last; fin.producer_rsum = 1;
+    FinishArgs f;
+    memset(&f, 0, sizeof(f));
+    f.stats = stats_prev2_dev; f.nx = d->nx; f.inline_moments = 1;
+    f.no_moments = (d->flags & SMC_FLAG_NO_MOMENTS) ? 1 : 0; f.n_global = d->n_global;
+    __atomic_add_fetch(&g_launch_count, 1ull, __ATOMIC_RELAXED);
+    k5s_flush<<<1, kThreads, 0, l.st>>>(l.ctrl(), fin, f, sc, static_cast<unsigned long long*>(ctx->rsum_area_dev));
+    SMC_CHECK_CUDA(cudaGetLastError());
+    if (!resample) return 0;
+    // resampling of the last step (stamp of this call): range pre-pass, resampler with migration, finish
+    int rc = launch_prepass<float>(l, false, d->logw_dev, d->nx, 0, nullptr, &sc);
+    if (rc) return rc;
+    const bool want_m = !(d->flags & SMC_FLAG_NO_MOMENTS);
+    rc = launch_k3<float>(l, false, d->logw_dev, d->nx, 0ull, 0, ctx->peer_x_dev, ctx->n_shards, want_m, nullptr, ctx->rank,
+                          false, nullptr, &sc);
+    if (rc) return rc;
+    f.stats = stats_prev_dev;
+    __atomic_add_fetch(&g_launch_count, 1ull, __ATOMIC_RELAXED);
+    k_finish_step_sharded<<<1, kThreads, 0, l.st>>>(l.ctrl(), f, sc);
     SMC_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -39,7 +39,7 @@ class SirEngine:
     def __init__(self, n: int, nx: int, nz: int, *, dtype: str = "f32", device=None,
                  n_global: Optional[int] = None, offset: int = 0, write_ancestors: bool = False,
                  generic_moments: bool = False, post_moments_generic: bool = False, trace_len: int = 1,
-                 x_buffers=None):
+                 x_buffers=None, logw_buffer=None):
         torch = _torch()
         self.lib = _lib.load()
         self.torch = torch
@@ -65,7 +65,11 @@ class SirEngine:
                 assert all(tuple(b.shape) == (self.nx, self.ld) and b.dtype == self.tdtype for b in self.x)
             else:
                 self.x = [torch.zeros((self.nx, self.ld), dtype=self.tdtype, device=self.device) for _ in range(2)]
-            self.logw = torch.zeros((self.ld,), dtype=self.tdtype, device=self.device)
+            if logw_buffer is not None:    # caller-owned (peer-mapped) log-weight array
+                assert tuple(logw_buffer.shape) == (self.ld,) and logw_buffer.dtype == self.tdtype
+                self.logw = logw_buffer
+            else:
+                self.logw = torch.zeros((self.ld,), dtype=self.tdtype, device=self.device)
             need_anc = write_ancestors or self.nx > 4
             self.ancestors = (torch.zeros((self.ld,), dtype=torch.int32, device=self.device)
                               if need_anc else None)

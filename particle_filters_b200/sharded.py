@@ -140,15 +140,21 @@ class ShardedSir:
         self.exchange = exchange
         self.stamp = 0
         self._raw = []
-        for nbytes in (nx * ld * elt, nx * ld * elt, int(self.lib.smc_mailbox_bytes())):   # x0, x1, mailbox
+        # x0, x1, mailbox; for the fused sharded step also the two log-weight arrays and the range-total area
+        sizes = [nx * ld * elt, nx * ld * elt, int(self.lib.smc_mailbox_bytes()), ld * elt, ld * elt,
+                 int(self.lib.smc_shard_rsum_bytes())]
+        for nbytes in sizes:
             p = C.c_void_p()
             _lib.check(self.lib.smc_dev_alloc(C.c_uint64(nbytes), C.byref(p)))
             self._raw.append(p.value)
         typestr = "<f4" if dtype == "f32" else "<f8"
         xbufs = [torch.as_tensor(_RawCuda(p, (nx, ld), typestr), device=dev) for p in self._raw[:2]]
+        self.lw = [torch.as_tensor(_RawCuda(p, (ld,), typestr), device=dev) for p in self._raw[3:5]]
         self.eng = SirEngine(self.n, nx, nz, dtype=dtype, n_global=n_global, offset=self.rank * self.n,
-                             trace_len=trace_len, x_buffers=xbufs)
-        # exchange IPC handles; table = [buffer 0 of every rank][buffer 1 of every rank]
+                             trace_len=trace_len, x_buffers=xbufs, logw_buffer=self.lw[0])
+        self._lw_cur = 0                 # which of the two log-weight arrays the engine's descriptor points at
+        self._fused_open = False
+        # exchange IPC handles; table = [x0 of every rank][x1 ...][mailboxes][logw 0 ...][logw 1 ...][range totals ...]
         mine = []
         for p in self._raw:
             h = C.create_string_buffer(64)
@@ -156,10 +162,11 @@ class ShardedSir:
             mine.append(bytes(h.raw))
         allh = [None] * self.G
         dist.all_gather_object(allh, mine)
-        table = np.zeros(3 * self.G, dtype=np.int64)      # [x0 of every rank][x1 of every rank][mailboxes]
+        nb = len(self._raw)
+        table = np.zeros(nb * self.G, dtype=np.int64)
         self._opened = []
         for r in range(self.G):
-            for b in range(3):
+            for b in range(nb):
                 if r == self.rank:
                     table[b * self.G + r] = self._raw[b]
                 else:
@@ -169,7 +176,8 @@ class ShardedSir:
                     table[b * self.G + r] = q.value
         self.peer_table = torch.from_numpy(table).to(dev)
         self.ctx = _lib.ShardCtx(mail_dev=self.peer_table.data_ptr() + 8 * 2 * self.G,
-                                 peer_x_dev=self.peer_table.data_ptr(), rank=self.rank, n_shards=self.G, stamp=0)
+                                 peer_x_dev=self.peer_table.data_ptr(), rank=self.rank, n_shards=self.G, stamp=0,
+                                 peer_aux_dev=self.peer_table.data_ptr() + 8 * 3 * self.G, rsum_area_dev=self._raw[5])
         ps = int(self.lib.smc_partial_stride(nx))
         nm = nx + nx * (nx + 1) // 2
         self.rec_local = torch.zeros(ps, dtype=torch.float64, device=dev)
@@ -196,6 +204,67 @@ class ShardedSir:
         _lib.check(self.lib.smc_sir_step_sharded(eng._d, C.byref(self.ctx), model_id, pp, kp.size, eng._zptr(z_index),
                                                  float(thresh), C.c_uint64(seed), t, eng._row(row), eng.stream))
 
+    # ---- fused run: ONE launch and ONE exchange per step (bootstrap filters, fp32 SV; include/smc.h) ----------------
+    def can_fuse(self, model_id, thresh) -> bool:
+        n_tiles = self.n // 4096
+        return bool(self.exchange == "mailbox" and model_id == _lib.SMC_MODEL_STOCH_VOL and thresh > 1.0
+                    and self.eng.dtype_code == _lib.SMC_F32 and self.eng.nx == 1 and n_tiles >= 148 * 12
+                    and not os.environ.get("SMC_SHARDED_NO_FUSE"))
+
+    def fused_begin(self, model_id, params, thresh, z_index, seed, t):
+        """K1 of the run's first step (publishes the partial record and the weight total)."""
+        assert not self._fused_open
+        eng = self.eng
+        self.stamp += 1
+        self.ctx.stamp = self.stamp
+        kp, pp = _lib.as_doubles(params)
+        _lib.check(self.lib.smc_sir_weight_sharded(eng._d, C.byref(self.ctx), model_id, pp, kp.size, eng._zptr(z_index),
+                                                   float(thresh), C.c_uint64(seed), t, eng.stream))
+        self._fused_open, self._fused_first = True, True
+
+    def fused_step(self, model_id, params, thresh, z_index, seed, t, row):
+        """resample(t-1) -> propagate + weigh(t) in one launch; ``row`` = statistics row of step t (rows row-1 and
+        row-2 receive the header of step t-1 and the moments of step t-2 in this launch's prologue)."""
+        assert self._fused_open
+        eng = self.eng
+        self.stamp += 1
+        self.ctx.stamp = self.stamp
+        kp, pp = _lib.as_doubles(params)
+        out = self._lw_cur ^ 1
+        _lib.check(self.lib.smc_sir_step_fused_sharded(
+            eng._d, C.byref(self.ctx), out, 1 if self._fused_first else 0, model_id, pp, kp.size, eng._zptr(z_index),
+            float(thresh), C.c_uint64(seed), t, None if self._fused_first else eng._row(max(row - 2, 0)),
+            eng._row(max(row - 1, 0)), eng.stream))
+        self._fused_first = False
+        self._lw_cur = out
+        eng.logw = self.lw[out]
+        eng.desc.logw_dev = eng.logw.data_ptr()
+
+    def fused_end(self, thresh, seed, t_last, row_last, resample=True):
+        """Finalize of the last step, finish of the one before and (``resample``) the last step's resampling."""
+        assert self._fused_open and not self._fused_first
+        eng = self.eng
+        self.stamp += 1
+        self.ctx.stamp = self.stamp
+        _lib.check(self.lib.smc_sir_fused_sharded_flush(eng._d, C.byref(self.ctx), float(thresh), C.c_uint64(seed), t_last,
+                                                        eng._row(max(row_last - 1, 0)), eng._row(row_last),
+                                                        1 if resample else 0, eng.stream))
+        self._fused_open = False
+
+    def run(self, model_id, params, T, thresh, seed, t0=0, z0=0, row0=0, fused=None):
+        """T steps (observations z0.., statistics rows row0.., Philox steps t0..); no host synchronisation."""
+        if fused is None:
+            fused = self.can_fuse(model_id, thresh) and T >= 2
+        if not fused:
+            for k in range(T):
+                self.step(model_id, params, thresh, z0 + k, seed, t0 + k, row0 + k)
+            return False
+        self.fused_begin(model_id, params, thresh, z0, seed, t0)
+        for k in range(1, T):
+            self.fused_step(model_id, params, thresh, z0 + k, seed, t0 + k, row0 + k)
+        self.fused_end(thresh, seed, t0 + T - 1, row0 + T - 1)
+        return True
+
     def step_nccl(self, model_id, params, thresh, z_index, seed, t, row):
         eng, lib, dist = self.eng, self.lib, self.dist
         eng.propagate_weight(model_id, params, _lib.SMC_MODE_STEP, z_index=z_index, seed=seed, t=t)
@@ -220,7 +289,7 @@ class ShardedSir:
         word = self.torch.as_tensor(_RawCuda(self._raw[2] + off, (1,), "<i8"), device=dev)
         v = int(word.cpu().numpy().astype(np.uint64)[0])
         if v:
-            what = {1: "partial record", 2: "weight total", 3: "moment record"}.get((v >> 4) & 0xF, "?")
+            what = {1: "partial record", 2: "weight total", 3: "moment record", 4: "fused-step slot"}.get((v >> 4) & 0xF, "?")
             raise _lib.SmcError(f"rank {self.rank}: timed out waiting for the {what} of rank {v & 0xF} "
                                 f"(stamp {(v >> 8) & ((1 << 55) - 1)}); the sharded filter state is invalid")
 
@@ -279,10 +348,51 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
         sh = ShardedSir(n_total, 1, 1, dtype="f32", trace_len=W + k_steps + 2, exchange=getattr(args, "exchange", "mailbox"))
         sh.eng.init_gaussian(np.zeros(1), L0, seed)
         sh.eng.set_observations(Y.reshape(-1, 1))
-        for k in range(W):
-            sh.step(mid, params, thresh, k, seed, k, k)
+        sh.run(mid, params, W, thresh, seed)           # fused (one launch, one exchange per step) where it applies
         torch.cuda.synchronize()
         return sh
+
+    def measure(sh, n_steps, spin):
+        """Steady state on an initialised filter: `spin` untimed steps (clock warm-up; a FIXED number -- every rank
+        must issue the same sequence of stamps), then n_steps timed ones between CUDA events.  Fused: one launch per
+        step inside an open run (K1 before, flush + last resampling after, both outside the timed region).
+        Statistics rows of the timed steps: W+2 .. W+n_steps+1.  Returns (ms max over ranks, launches, rows)."""
+        fz = sh.can_fuse(mid, thresh)
+        zmax = Y.shape[0] - 1
+
+        def go(k0, cnt, row0=None, row=None):
+            for k in range(k0, k0 + cnt):
+                r = row if row is not None else row0 + (k - k0)
+                if fz:
+                    sh.fused_step(mid, params, thresh, min(k, zmax), seed, k, r)
+                else:
+                    sh.step(mid, params, thresh, min(k, zmax), seed, k, r)
+
+        if fz:
+            sh.fused_begin(mid, params, thresh, W, seed, W)
+        for kk in range(0, spin, 250):
+            go(W + 1 + kk, min(250, spin - kk), row=W + 2)
+            torch.cuda.synchronize()
+        flag = torch.zeros(1, device="cuda")
+        dist.all_reduce(flag)                       # ranks leave the spin at different times: line them up
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib = _lib.load()
+        launches0 = int(lib.smc_launch_count())
+        e0.record()
+        go(W + 1 + spin, n_steps, row0=W + 2)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = int(lib.smc_launch_count()) - launches0
+        if fz:
+            sh.fused_end(thresh, seed, W + spin + n_steps, W + n_steps + 1)
+            torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rows = sh.eng.trace[W + 2: W + n_steps + 2].cpu().numpy()
+        return float(ms.item()), launches, rows, fz
 
     # ---- parity: the first W statistic rows and the particle set after W steps vs ONE GPU, same N and seed ----
     sh = timed_run(N, K)
@@ -300,6 +410,8 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
         xref = ref.get_particles()[:, 0]
         xsh = np.concatenate(gathered)
         parity = {"steps_compared": W, "reference": "single-GPU three-launch engine, same N and seed, on rank 0",
+                  "sharded_pipeline": ("fused: one launch + one exchange per step" if sh.can_fuse(mid, thresh)
+                                       else "three / five launches per step"),
                   "identical_particle_fraction": float(np.mean(xsh == xref)),
                   "decisions_equal": bool(np.array_equal(rows_w[:, 2], rrows[:, 2])),
                   "uniforms_equal": bool(np.array_equal(rows_w[:, 3], rrows[:, 3])),
@@ -317,29 +429,9 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         clocks.start()
-    # keep every GPU on the workload while the sampler takes its first readings (outside the timed region); a FIXED
-    # number of steps -- every rank must issue the same sequence of stamps
-    for kk in range(4000):
-        sh.step(mid, params, thresh, W, seed, W + kk, W)
-        if kk % 256 == 255:
-            torch.cuda.synchronize()
-    flag = torch.zeros(1, device="cuda")
-    dist.all_reduce(flag)                       # ranks leave the spin at different times: line them up
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lib = _lib.load()
-    launches0 = int(lib.smc_launch_count())
-    e0.record()
-    for k in range(W, W + K):
-        sh.step(mid, params, thresh, k, seed, k, k)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = int(lib.smc_launch_count()) - launches0
-    dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms.item()) / K
+    # keep every GPU on the workload while the sampler takes its first readings (outside the timed region)
+    ms_total, launches, rows, fused = measure(sh, K, 4000)
+    ms_step = ms_total / K
     # end to end: host observation in, host moments out, every step, through the same engine
     Ke = max(3, min(K, 20))
     zpin = torch.zeros(1, dtype=torch.float64).pin_memory()
@@ -354,7 +446,6 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     dist.barrier()
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    rows = sh.eng.trace[W: W + K].cpu().numpy()
     clk = clocks.stop() if rank == 0 else None
     sh.check()
     ok = bool(np.all(np.isfinite(rows[:, :5])) and np.all(rows[:, 2] == 1.0))
@@ -365,26 +456,17 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
     if not getattr(args, "no_weak", False) and N * G <= (1 << 30):
         Kw = min(K, 50)
         shw = timed_run(N * G, Kw)
-        dist.barrier()
-        torch.cuda.synchronize()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        for k in range(W, W + Kw):
-            shw.step(mid, params, thresh, k, seed, k, k)
-        w1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        msw = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(msw, op=dist.ReduceOp.MAX)
-        wrows = shw.eng.trace[W: W + Kw].cpu().numpy()
-        weak = {"n_particles_total": N * G, "n_particles_per_gpu": N, "steps": Kw, "ms_per_step": float(msw.item()) / Kw,
-                "value": N * G / (float(msw.item()) / Kw * 1e-3), "unit": UNIT,
+        msw, _, wrows, _ = measure(shw, Kw, 0)
+        weak = {"n_particles_total": N * G, "n_particles_per_gpu": N, "steps": Kw, "ms_per_step": msw / Kw,
+                "value": N * G / (msw / Kw * 1e-3), "unit": UNIT,
                 "finite": bool(np.all(np.isfinite(wrows[:, :5])))}
         shw.close()
 
     peak, peak_src = measured_peak()
     value = N / (ms_step * 1e-3)
-    step_bytes = 28.0        # the sharded step is the three-launch form: K1 12 B + range pre-pass 4 B + resampler 12 B
+    # fused: one launch, 16 B per particle-update (R logw, R x, W x, W logw); otherwise the three-launch form: K1 12 B
+    # + resampler 12 B (+ 4 B range pre-pass on steps that need it)
+    step_bytes = 16.0 if fused else 24.0
     if rank == 0:
         assert ok, "non-finite statistics in the sharded run"
         line = {
@@ -395,7 +477,10 @@ def run_sharded_bench(args, sv_observations, measured_peak, ClockSampler, METRIC
                                    "systematic resampling every step with cross-shard migration "
                                    "(BASELINE.json configs[2])",
                        "n_particles": N, "nx": 1, "nz": 1, "parallelism": f"particle-sharded x{G}",
-                       "exchange": ("in-kernel NVLink peer stores + flags (no collective call)" if sh.exchange == "mailbox"
+                       "exchange": (("ONE launch + ONE exchange per step: fused resample -> propagate kernel on every shard, "
+                                     "records / migrating particles / range totals by in-kernel NVLink peer stores and "
+                                     "atomics, stamped flags (no collective call)") if fused else
+                                    "in-kernel NVLink peer stores + flags (no collective call)" if sh.exchange == "mailbox"
                                     else "3 NCCL all-gathers per step"),
                        "l2": "per-step working set 3 x N/G x 4 B; no flush (strong scaling shrinks it)"},
             "clocks": clk,

@@ -40,17 +40,29 @@ def main():
     Y_out[3], Y_out[7] = 9.0, -8.5
     cases = [(1 << 20, 0.7, "mailbox", Y), (1 << 20, 2.0, "mailbox", Y), (1 << 20, 0.7, "nccl", Y), (1 << 20, 2.0, "nccl", Y),
              ((1 << 23) * G, 2.0, "mailbox", Y), ((1 << 23) * G, 0.7, "mailbox", Y), ((1 << 23) * G, 2.0, "mailbox", Y_out)]
-    only = os.environ.get("SHARDED_CHECK_ONLY")          # debugging aid: "outliers" runs the last case only
+    # "fused": the single-launch, single-exchange step (k5_resample_propagate on shards); a second run on the same
+    # filter object checks the hand-over of the range-total buffers between runs
+    cases += [((1 << 23) * G, 2.0, "fused", Y), ((1 << 23) * G, 2.0, "fused", Y_out), ((1 << 24) * G, 2.0, "fused", Y_out)]
+    only = os.environ.get("SHARDED_CHECK_ONLY")          # debugging aid: "outliers" / "fused" run those cases only
     if only == "outliers":
-        cases = cases[-1:]
+        cases = cases[6:7]
+    if only == "fused":
+        cases = cases[7:]
     for N, thresh, exchange, Yc in cases:
         if N > (1 << 27):
             continue
-        sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T, exchange=exchange)
+        fused = exchange == "fused"
+        sh = ShardedSir(N, 1, 1, dtype="f32", trace_len=T, exchange="mailbox" if fused else exchange)
         sh.eng.init_gaussian(np.zeros(1), np.array([[0.6]]), seed)
         sh.eng.set_observations(Yc.reshape(-1, 1))
-        for k in range(T):
-            sh.step(mid, params, thresh, k, seed, k, k)
+        if fused:
+            assert sh.can_fuse(mid, thresh)
+            half = T // 2                                   # two fused runs back to back
+            assert sh.run(mid, params, half, thresh, seed, t0=0, z0=0, row0=0)
+            assert sh.run(mid, params, T - half, thresh, seed, t0=half, z0=half, row0=half)
+        else:
+            for k in range(T):
+                sh.step(mid, params, thresh, k, seed, k, k)
         sh.check()
         rows = sh.eng.trace[:T].cpu().numpy()
         local = sh.eng.get_particles()[:, 0]
