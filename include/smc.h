@@ -258,9 +258,10 @@ typedef struct smc_shard_ctx {
     uint64_t stamp;
     /* fused sharded step only (NULL otherwise): device table [log-weight array 0 of every rank][log-weight
      * array 1 of every rank][range-total area of every rank]; a range-total area is smc_shard_rsum_bytes() of
-     * zeroed peer-mapped memory; rsum_area_dev = this rank's own area */
+     * zeroed peer-mapped memory; rsum_area_dev / mailbox_dev = this rank's own area / mailbox */
     void *const *peer_aux_dev;
     void *rsum_area_dev;
+    void *mailbox_dev;            /* this rank's own mailbox (= mail_dev[rank]) */
 } smc_shard_ctx;
 uint64_t smc_mailbox_bytes(void);
 /* Byte offset of the mailbox's error word: non-zero after a flag wait on this rank timed out (20 s) because a

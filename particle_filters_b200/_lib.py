@@ -51,7 +51,8 @@ class ShardCtx(C.Structure):
     """Mirror of ``smc_shard_ctx`` (include/smc.h)."""
 
     _fields_ = [("mail_dev", C.c_void_p), ("peer_x_dev", C.c_void_p), ("rank", C.c_int32), ("n_shards", C.c_int32),
-                ("stamp", C.c_uint64), ("peer_aux_dev", C.c_void_p), ("rsum_area_dev", C.c_void_p)]
+                ("stamp", C.c_uint64), ("peer_aux_dev", C.c_void_p), ("rsum_area_dev", C.c_void_p),
+                ("mailbox_dev", C.c_void_p)]
 
 
 _P = C.c_void_p

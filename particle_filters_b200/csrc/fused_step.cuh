@@ -35,6 +35,9 @@ namespace smc {
 #ifndef SMC_K5_OCC
 #define SMC_K5_OCC 4
 #endif
+#ifndef SMC_K5S_OCC
+#define SMC_K5S_OCC 3            // resident CTAs per SM of the sharded form (80 registers, no spills worth mentioning)
+#endif
 #ifndef SMC_K5_UNROLL
 #define SMC_K5_UNROLL 1          // unroll factor of phase E's quad loop (tuning knob)
 #endif
@@ -75,6 +78,8 @@ struct K5Shard {
     float* const* peer_x1;
     float* const* peer_lw_out; // per-rank log-weight arrays of step t
     unsigned long long* const* peer_rsum;   // per-rank range-total areas: two buffers of kRsumStride, then G accumulators
+    Mailbox* own;              // this rank's mailbox and range-total area (= the tables' own entries: saves two
+    unsigned long long* own_rsum;           //  dependent loads on the critical path of every launch)
     int32_t rsel_in, rsel_out; // which buffer of the area this launch reads (first: the workspace's) / accumulates into
     unsigned int* gbar;        // grid-barrier counter of the in-kernel pre-pass
     K2Args pfin;               // finalize of step t-1
@@ -136,11 +141,20 @@ __device__ inline void finish_warp(Ctrl* c, const FinishArgs& f, const double* m
     __syncwarp();
 }
 
+// -DSMC_K5_TRACE (tuning builds only, profiles/micro/k5s_trace.py): per-CTA globaltimer stamps of the sharded form --
+// [launch parity][CTA][entry, after wait, after finalize, after prefix, after tiles, ticket, last-CTA done]
+#ifdef SMC_K5_TRACE
+__device__ unsigned long long g_k5_trace[2 * 1024 * 16];
+#define K5_TRACE(slot) do { if (SHARDED && threadIdx.x == 0) g_k5_trace[(((a.sh.ctx.stamp & 1ull) * 1024 + blockIdx.x) << 4) + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define K5_TRACE(slot) do { } while (0)
+#endif
+
 template <bool SHARDED> struct K5CtrlCopy { Ctrl c; unsigned long long contrib[kMaxShards]; double pout[32]; double m[16]; };
 template <> struct K5CtrlCopy<false> { int unused; };
 
 template <int NX, class Model, bool SHARDED = false>
-__global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resample_propagate(K5Args a, Model fm) {
+__global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value) k5_resample_propagate(K5Args a, Model fm) {
     static_assert(Model::NX == NX, "functor / payload mismatch");
     static_assert(!SHARDED || !K5IsCopy<Model>::value, "the sharded form always carries a functor");
     constexpr int THREADS = 256, WARPS = 8, IPT = 16, UPT = 4, TILE = kK5Tile;
@@ -174,20 +188,53 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();
     pdl_trigger();
+    K5_TRACE(0);
+#ifdef SMC_K5_TRACE
+    if (SHARDED && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_k5_trace[(((a.sh.ctx.stamp & 1ull) * 1024 + blockIdx.x) << 4) + 7] = smid;
+    }
+#endif
     __shared__ K5CtrlCopy<SHARDED> s_sh;
     [[maybe_unused]] Mailbox* own = nullptr;
     [[maybe_unused]] const FusedSlot* slot_in = nullptr;
     [[maybe_unused]] const int G = SHARDED ? a.sh.ctx.n_shards : 1;
+    // range totals of the log-weights to resample (eight per thread, all loads in flight at once) and, sharded, one
+    // entry of the G x G table of weight contributions per thread: thread (g, src) = (tid / 16, tid % 16)
+    static_assert(kRsumStride == 8 * THREADS, "range totals: eight per thread");
+    static_assert(kMaxShards == 16 && THREADS == 256, "one thread per (rank, producing rank) pair");
+    unsigned long long tv[8];
+    [[maybe_unused]] unsigned long long tc = 0ull;
+    auto load_totals = [&](const unsigned long long* r, [[maybe_unused]] const bool own_totals) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = tid + k * THREADS;
+            tv[k] = i < a.n_ranges ? __ldcg(r + i) : 0ull;
+        }
+        if constexpr (SHARDED) {
+            const int g = tid >> 4, src = tid & 15;
+            tc = 0ull;
+            if (g < G && src < G) {
+                if (!own_totals) tc = __ldcg(&slot_in->contrib[src][g]);     // (Mailbox::tot: K1 / in-kernel pre-pass)
+                else if (src == 0) tc = __ldcg(&own->tot[g]);
+            }
+        }
+    };
     if constexpr (SHARDED) {
         // every CTA: wait for the G slots of the previous launch, then finalize(t-1) and finish(t-2) on a private copy
         // of the control block (CTA 0 also writes the statistics rows; the last CTA copies the block back)
         for (int i = tid; i < (int)(sizeof(Ctrl) / 4); i += THREADS)
             reinterpret_cast<uint32_t*>(&s_sh.c)[i] = reinterpret_cast<const uint32_t*>(gctrl)[i];
         if (tid < kMaxShards) s_sh.contrib[tid] = 0ull;
-        own = a.sh.ctx.mail[a.sh.ctx.rank];
+        own = a.sh.own;
         const unsigned long long prev = a.sh.ctx.stamp - 1ull;
         slot_in = &own->fs[prev & 1ull];
         mailbox_wait(a.sh.first ? own->flag_rec : slot_in->flag, G, prev, &own->error, 4);
+        K5_TRACE(1);
+        // the range totals and the weight contributions travel while two warps finalise the step
+        load_totals(a.sh.first ? a.rsum + (size_t)s_sh.c.rsum_sel * kRsumStride
+                               : a.sh.own_rsum + (size_t)a.sh.rsel_in * kRsumStride, a.sh.first != 0);
         K2Args f = a.sh.pfin;
         f.ctrl = &s_sh.c; f.n_parts = G;
         if (a.sh.first) {
@@ -202,6 +249,7 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
             finish_warp(&s_sh.c, a.sh.pfinish, &slot_in->mom[0][0], G, 16, blockIdx.x == 0 ? a.sh.pfinish.stats : nullptr, s_sh.m);
         __syncthreads();
         ctrl = &s_sh.c;
+        K5_TRACE(2);
     }
     if (!ctrl->do_resample) {
         // (only a filter whose weights have all vanished gets here) nothing to resample: moment-shift refresh
@@ -239,16 +287,20 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
     if constexpr (SHARDED) {
         px = cur ? a.sh.peer_x0 : a.sh.peer_x1;
         plw = a.sh.peer_lw_out;
-        if (!a.sh.first) rin = a.sh.peer_rsum[a.sh.ctx.rank] + (size_t)a.sh.rsel_in * kRsumStride;
-        rout = a.sh.peer_rsum[a.sh.ctx.rank] + (size_t)a.sh.rsel_out * kRsumStride;
+        if (!a.sh.first) rin = a.sh.own_rsum + (size_t)a.sh.rsel_in * kRsumStride;
+        rout = a.sh.own_rsum + (size_t)a.sh.rsel_out * kRsumStride;
     }
     const float kshift_in = ctrl->kshift;
     const int64_t n_glob = SHARDED ? a.sh.n_global : a.n;
     const int64_t g_off = SHARDED ? a.sh.offset : 0;            // global index of this shard's first particle
     const uint32_t Nn = (uint32_t)n_glob;
 
-    const int64_t t_begin = k3_range_begin(blockIdx.x, a.n_tiles, gridDim.x);
-    const int64_t t_end = k3_range_begin(blockIdx.x + 1, a.n_tiles, gridDim.x);
+    // this CTA's ranges (measured and dropped: handing the CTAs of one SM unequal shares by arrival order -- the three
+    // co-resident CTAs finish 1 : 1.17 : 1.36 apart -- made every launch slower, profiles/r2_k5_shares.txt)
+    const int r_begin = (int)blockIdx.x * a.ranges_per_cta, r_end = r_begin + a.ranges_per_cta;
+    const int piece = (int)blockIdx.x;
+    const int64_t t_begin = k3_range_begin(r_begin, a.n_tiles, a.n_ranges);
+    const int64_t t_end = k3_range_begin(r_end, a.n_tiles, a.n_ranges);
     auto swz = [](int f) -> int { return f ^ ((f >> 3) & (UPT - 1)); };
 
     // log-weights / particles of one tile -> shared memory (cp.async; the ragged last tile is guarded).  Two
@@ -305,16 +357,14 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
     // exclusive CDF prefix of this CTA's first tile and the CDF total, from the range totals
     unsigned long long prefix, cdf_total;
     {
-        [[maybe_unused]] bool own_totals = false;      // sharded: shard totals from Mailbox::tot (K1 / in-kernel pre-pass)
+        if constexpr (!SHARDED) load_totals(rin, false);
         if constexpr (SHARDED) {
-            own_totals = a.sh.first != 0;
             if (!ctrl->rsum_valid) {
                 // The a-priori bound left this step's weights without resolution (or K1 delivered no totals): range
                 // pre-pass inside the kernel against the reference the finalize chose -- every CTA its own ranges, a
                 // grid barrier (the grid is resident: 3 CTAs per SM), CTA 0 publishes the shard total
                 unsigned long long* rt = const_cast<unsigned long long*>(rin);
-                for (int rr = 0; rr < a.ranges_per_cta; ++rr) {
-                    const int r = (int)blockIdx.x * a.ranges_per_cta + rr;
+                for (int r = r_begin; r < r_end; ++r) {
                     const int64_t tr0 = k3_range_begin(r, a.n_tiles, a.n_ranges), tr1 = k3_range_begin(r + 1, a.n_tiles, a.n_ranges);
                     unsigned long long acc = 0;
                     for (int64_t i = tr0 * TILE + tid; i < tr1 * TILE && i < a.n; i += THREADS)
@@ -357,24 +407,26 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
                     __syncthreads();
                 }
                 mailbox_wait(own->flag_tot, G, a.sh.ctx.stamp, &own->error, 2);
-                own_totals = true;
+                load_totals(rin, true);
             }
         }
         unsigned long long part = 0, all = 0;
-        const int mine = (int)blockIdx.x * a.ranges_per_cta;
-        for (int i = tid; i < a.n_ranges; i += THREADS) {
-            const unsigned long long v = __ldcg(rin + i);
-            if (i < mine) part += v;
-            all += v;
+        const int mine = r_begin;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (tid + k * THREADS < mine) part += tv[k];
+            all += tv[k];
         }
         if constexpr (SHARDED) {
-            // the CDF runs over ALL shards: offset = the total weight of the lower ranks
+            // the CDF runs over ALL shards: offset = the total weight of the lower ranks; 16-lane sums of the
+            // contribution table give the G shard totals
             all = 0;
-            if (tid < G) {
-                unsigned long long v = 0;
-                if (own_totals) v = __ldcg(&own->tot[tid]);
-                else for (int src = 0; src < G; ++src) v += __ldcg(&slot_in->contrib[src][tid]);
-                if (tid < a.sh.ctx.rank) part += v;
+            const int g = tid >> 4, src = tid & 15;
+            unsigned long long v = tc;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+            if (src == 0) {
+                if (g < a.sh.ctx.rank) part += v;
                 all = v;
             }
         }
@@ -388,6 +440,7 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
         __syncthreads();
     }
     const RhoMap rm = make_rho(cdf_total, n_glob, 0xffffffffull - ctrl->uq);
+    K5_TRACE(3);
 
     float shift[NX];
 #pragma unroll
@@ -852,9 +905,120 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
         for (int k = 0; k < NM; ++k) { macc_d[k] += (double)macc[k]; macc[k] = 0.f; }
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+    K5_TRACE(4);
+#ifdef SMC_K5_TRACE
+    if (SHARDED && threadIdx.x == 0) {     // outputs this CTA produced: CDF positions of its first and last tile
+        const unsigned long long base = (((a.sh.ctx.stamp & 1ull) * 1024 + blockIdx.x) << 4);
+        g_k5_trace[base + 8] = (unsigned long long)(t_end - t_begin);
+        g_k5_trace[base + 9] = map_pos(prefix, rm) >> 32;          // (prefix = CDF at the end of the CTA's last tile)
+    }
+#endif
     if (!COPY && cur_r != 0xffffffffu) flush_acc();
 
     __syncthreads();                                         // the tile buffers are dead: reuse them as scratch
+    if constexpr (SHARDED) {
+        // The same per-CTA records as below in three barriers instead of eight (this tail is on the critical path of
+        // every step of a strong-scaled filter): warp partials of everything, one barrier, the CTA sums, the ticket.
+        const float wmax = warp_max(f_tm);
+        if (lane == 0) s_fmax[warp] = wmax;
+        if (a.mom_parts) {
+#pragma unroll
+            for (int k = 0; k < NM; ++k) {
+                const double v = warp_sum(macc_d[k]);
+                if (lane == 0) s_mom[warp][k] = v;
+            }
+        }
+        // the CTA's share of the weight this rank produced for every rank's index range
+        for (int g = 0; g < G; ++g) {
+            const unsigned long long v = warp_sum(d_rank == g ? my_contrib : 0ull);
+            if (lane == 0 && v) atomicAdd(&s_sh.contrib[g], v);
+        }
+        // every peer store / peer atomic of this CTA is made visible system-wide before the CTA takes its ticket (by
+        // the threads that crossed a shard boundary; the rest of the CTA's stores are for the next launch on this GPU)
+        if (wrote_peer) __threadfence_system();
+        __syncthreads();
+        float bmax = s_fmax[0];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) bmax = s_fmax[w] > bmax ? s_fmax[w] : bmax;
+        const float sc = (f_tm == -INFINITY) ? 0.f : fast_exp(f_tm - bmax);
+        const float v0 = warp_sum(f_acc0 * sc), v1 = warp_sum(f_acc1 * sc * sc);
+        if (lane == 0) { s_fred[warp][0] = (double)v0; s_fred[warp][1] = (double)v1; }
+        if (a.mom_parts && tid < NM) {
+            double t = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) t += s_mom[w][tid];
+            a.mom_parts[(int64_t)piece * NM + tid] = t;
+            __threadfence();
+        }
+        if (tid >= 32 && tid < 32 + G && s_sh.contrib[tid - 32]) {
+            atomicAdd(a.sh.own_rsum + 2 * kRsumStride + (tid - 32), s_sh.contrib[tid - 32]);
+            __threadfence();
+        }
+        __syncthreads();
+        K5_TRACE(5);
+        if (tid == 0) {
+            double t0 = 0, t1 = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { t0 += s_fred[w][0]; t1 += s_fred[w][1]; }
+            double* out = a.parts + (int64_t)piece * 3;
+            out[0] = (double)bmax; out[1] = t0; out[2] = t1;
+            __threadfence();
+            s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_last) {
+            // the last CTA publishes this launch's slot to every rank: record of step t's log-weights, post-resample
+            // moments of step t-1, weight contributions; then the flag.  All loads first, then the reductions.
+            const int rank = a.sh.ctx.rank;
+            const unsigned long long slot = a.sh.ctx.stamp & 1ull;
+            double acc[NM];
+#pragma unroll
+            for (int k = 0; k < NM; ++k) acc[k] = 0.0;
+            if (a.mom_parts)
+                for (int p = tid; p < (int)gridDim.x; p += THREADS)          // fixed record -> thread assignment
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) acc[k] += __ldcg(a.mom_parts + (int64_t)p * NM + k);
+            unsigned long long* acc_g = a.sh.own_rsum + 2 * kRsumStride;
+            const unsigned long long cg = tid < G ? __ldcg(acc_g + tid) : 0ull;
+            combine_partials(a.parts, (int)gridDim.x, 3, s_fout, s_ftmp, 0);
+            if (tid < 3)
+                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].rec[rank][tid] = s_fout[tid];
+            if (a.mom_parts) {
+#pragma unroll
+                for (int k = 0; k < NM; ++k) {
+                    const double v = warp_sum(acc[k]);
+                    if (lane == 0) s_mom[warp][k] = v;
+                }
+                __syncthreads();
+                if (tid < NM) {
+                    double t = 0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) t += s_mom[w][tid];
+                    for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].mom[rank][tid] = t;
+                }
+            }
+            if (tid < G) {
+                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].contrib[rank][tid] = cg;
+                acc_g[tid] = 0ull;
+            }
+            // every CTA of this rank has read the totals of step t-1: clear that buffer for the launch after the next
+            // (the peers accumulate into it only once they have seen this launch's flag)
+            if (!a.sh.first)
+                for (int i = tid; i < kRsumStride; i += THREADS) const_cast<unsigned long long*>(rin)[i] = 0ull;
+            if (tid == 0) {
+                s_sh.c.cur ^= 1;                                  // the resampled, propagated set is the current one
+                *gctrl = s_sh.c;
+                *a.sh.gbar = 0u;
+                *a.ticket = 0u;
+            }
+            if (tid < 32) __threadfence_system();            // (every store into a mailbox came from warp 0)
+            __syncthreads();
+            if (tid < G) *(volatile unsigned long long*)&a.sh.ctx.mail[tid]->fs[slot].flag[rank] = a.sh.ctx.stamp;
+            K5_TRACE(6);
+        }
+        return;
+    }
     if (!COPY) {   // per-CTA (max, sum e, sum e^2) record of step t's log-weights (k1_propagate_weight's layout)
         const float wmax = warp_max(f_tm);
         if (lane == 0) s_fmax[warp] = wmax;
@@ -870,7 +1034,7 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
             double t0 = 0, t1 = 0;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) { t0 += s_fred[w][0]; t1 += s_fred[w][1]; }
-            double* out = a.parts + (int64_t)blockIdx.x * 3;
+            double* out = a.parts + (int64_t)piece * 3;
             out[0] = (double)bmax; out[1] = t0; out[2] = t1;
         }
     }
@@ -887,76 +1051,11 @@ __global__ void __launch_bounds__(256, SHARDED ? 3 : K5Occ<NX>::value) k5_resamp
             double s = 0;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) s += s_mom[w][tid];
-            a.mom_parts[(int64_t)blockIdx.x * NM + tid] = s;
+            a.mom_parts[(int64_t)piece * NM + tid] = s;
         }
     }
     // the last CTA to arrive: finish of step t-1 (moments, buffer flip, shift refresh), hand-over of the
     // range-total buffers, finalize of step t (normaliser, ESS, decision, u, quantisation reference)
-    if constexpr (SHARDED) {
-        // the CTA's share of the weight this rank produced for every rank's index range; every peer store / peer
-        // atomic of this CTA is made visible system-wide before it takes its ticket
-        for (int g = 0; g < G; ++g) {
-            const unsigned long long v = warp_sum(d_rank == g ? my_contrib : 0ull);
-            if (lane == 0 && v) atomicAdd(&s_sh.contrib[g], v);
-        }
-        __syncthreads();
-        if (tid < G && s_sh.contrib[tid]) atomicAdd(a.sh.peer_rsum[a.sh.ctx.rank] + 2 * kRsumStride + tid, s_sh.contrib[tid]);
-        if (wrote_peer) __threadfence_system(); else __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
-        __syncthreads();
-        if (s_last) {
-            // the last CTA publishes this launch's slot to every rank: record of step t's log-weights, post-resample
-            // moments of step t-1, weight contributions; then the flag
-            __threadfence();
-            const int rank = a.sh.ctx.rank;
-            const unsigned long long slot = a.sh.ctx.stamp & 1ull;
-            combine_partials(a.parts, (int)gridDim.x, 3, s_fout, s_ftmp, 0);
-            if (tid < 3)
-                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].rec[rank][tid] = s_fout[tid];
-            if (a.mom_parts) {
-                double acc[NM];
-#pragma unroll
-                for (int k = 0; k < NM; ++k) acc[k] = 0.0;
-                for (int p = tid; p < (int)gridDim.x; p += THREADS)          // fixed record -> thread assignment
-#pragma unroll
-                    for (int k = 0; k < NM; ++k) acc[k] += __ldcg(a.mom_parts + (int64_t)p * NM + k);
-                __syncthreads();
-#pragma unroll
-                for (int k = 0; k < NM; ++k) {
-                    const double v = warp_sum(acc[k]);
-                    if (lane == 0) s_mom[warp][k] = v;
-                }
-                __syncthreads();
-                if (tid < NM) {
-                    double t = 0;
-#pragma unroll
-                    for (int w = 0; w < WARPS; ++w) t += s_mom[w][tid];
-                    for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].mom[rank][tid] = t;
-                }
-            }
-            unsigned long long* acc_g = a.sh.peer_rsum[rank] + 2 * kRsumStride;
-            if (tid < G) {
-                const unsigned long long v = __ldcg(acc_g + tid);
-                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].contrib[rank][tid] = v;
-                acc_g[tid] = 0ull;
-            }
-            // every CTA of this rank has read the totals of step t-1: clear that buffer for the launch after the next
-            // (the peers accumulate into it only once they have seen this launch's flag)
-            if (!a.sh.first)
-                for (int i = tid; i < kRsumStride; i += THREADS) const_cast<unsigned long long*>(rin)[i] = 0ull;
-            if (tid == 0) {
-                s_sh.c.cur ^= 1;                                  // the resampled, propagated set is the current one
-                *gctrl = s_sh.c;
-                *a.sh.gbar = 0u;
-                *a.ticket = 0u;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < G) *(volatile unsigned long long*)&a.sh.ctx.mail[tid]->fs[slot].flag[rank] = a.sh.ctx.stamp;
-        }
-        return;
-    }
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);

@@ -132,15 +132,20 @@ __device__ inline void mailbox_wait(const volatile unsigned long long* flags, in
     if ((int)threadIdx.x < n) {
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
-        while (flags[threadIdx.x] != stamp) {
+        auto poll = [&]() {     // acquire load: every later read of this thread -- and, through the barrier, of the CTA --
+            unsigned long long v;   // sees what the publisher stored before it released the flag
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(const_cast<const unsigned long long*>(flags) + threadIdx.x) : "memory");
+            return v;
+        };
+        while (poll() != stamp) {
             __nanosleep(20);
             if ((++spins & 0x3ffu) == 0u && globaltimer_ns() - t0 > kMailboxTimeoutNs) {
                 if (error_word) atomicMax(error_word, (stamp << 8) | (what << 4) | (unsigned long long)threadIdx.x | 0x8000000000000000ull);
                 break;
             }
         }
+        // (no fence: a system-wide fence after the poll measured 4 us per launch in all 256 threads, ~2 us in G)
     }
-    __threadfence_system();
     __syncthreads();
 }
 
@@ -2821,7 +2826,7 @@ __global__ void __launch_bounds__(kThreads) k5s_flush(Ctrl* ctrl, K2Args pfin, F
     if (threadIdx.x == 0) ctrl->rsum_valid = 0;      // the resampling that follows takes its range totals from a pre-pass
 }
 
-inline int64_t k5s_grid() { return (int64_t)sm_count() * 3; }
+inline int64_t k5s_grid() { return (int64_t)sm_count() * SMC_K5S_OCC; }
 inline bool k5_sharded_ok(const Launch& l) {
     const smc_sir_desc* d = l.d;
     if (d->dtype != SMC_F32 || d->nx != 1 || d->n % 4096 != 0) return false;
@@ -2866,6 +2871,8 @@ int launch_k5_sharded(const Launch& l, const Model& m, const smc_shard_ctx* ctx,
     sh.peer_x0 = px; sh.peer_x1 = px + G;
     sh.peer_lw_out = reinterpret_cast<float* const*>(aux + (size_t)lw_out_sel * G);
     sh.peer_rsum = reinterpret_cast<unsigned long long* const*>(aux + 2 * (size_t)G);
+    sh.own = static_cast<Mailbox*>(ctx->mailbox_dev);
+    sh.own_rsum = static_cast<unsigned long long*>(ctx->rsum_area_dev);
     sh.rsel_in = (int32_t)((ctx->stamp - 1) & 1); sh.rsel_out = (int32_t)(ctx->stamp & 1);
     sh.gbar = l.ticket() + 3;
     sh.pfin.stats = stats_prev_dev; sh.pfin.n_global = d->n_global; sh.pfin.nx = d->nx;
@@ -3340,6 +3347,12 @@ int smc_sir_step_fused(const smc_sir_desc* d, void* logw_out_dev, int32_t model_
 // ---- multi-GPU: whole sharded step with mailbox exchanges (no collective calls) ----------------
 uint64_t smc_mailbox_bytes(void) { return sizeof(Mailbox); }
 uint64_t smc_mailbox_error_offset(void) { return offsetof(Mailbox, error); }
+#ifdef SMC_K5_TRACE
+int smc_k5_trace_read(unsigned long long* host_out) {      // tuning builds only: 2 x 1024 x 16 stamps
+    SMC_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, smc::g_k5_trace, sizeof(unsigned long long) * 2 * 1024 * 16));
+    return 0;
+}
+#endif
 uint64_t smc_shard_rsum_bytes(void) { return sizeof(unsigned long long) * (2 * kRsumStride + kMaxShards); }
 
 int smc_sir_step_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, int32_t model_id, const double* params_host,
@@ -3452,7 +3465,8 @@ int smc_sir_step_fused_sharded(const smc_sir_desc* d, const smc_shard_ctx* ctx, 
     if (int rc = check_desc(d, &l, stream)) return rc;
     ShardCtx sc;
     if (int rc = shard_ctx_check(d, ctx, &sc)) return rc;
-    SMC_REQUIRE(ctx->peer_aux_dev, "smc: the fused sharded step needs the peer tables of the log-weight arrays and range totals");
+    SMC_REQUIRE(ctx->peer_aux_dev && ctx->mailbox_dev && ctx->rsum_area_dev,
+                "smc: the fused sharded step needs the peer tables of the log-weight arrays and range totals");
     SMC_REQUIRE(ctx->stamp > 1, "smc: the fused sharded step follows smc_sir_weight_sharded (stamp - 1) or another fused step");
     SMC_REQUIRE(k5_sharded_ok(l), "smc: the fused sharded step is the fp32, nx = 1 throughput path for shards of at least "
                                   "%d tiles of 4096 particles", sm_count() * 12);

@@ -177,7 +177,8 @@ class ShardedSir:
         self.peer_table = torch.from_numpy(table).to(dev)
         self.ctx = _lib.ShardCtx(mail_dev=self.peer_table.data_ptr() + 8 * 2 * self.G,
                                  peer_x_dev=self.peer_table.data_ptr(), rank=self.rank, n_shards=self.G, stamp=0,
-                                 peer_aux_dev=self.peer_table.data_ptr() + 8 * 3 * self.G, rsum_area_dev=self._raw[5])
+                                 peer_aux_dev=self.peer_table.data_ptr() + 8 * 3 * self.G, rsum_area_dev=self._raw[5],
+                                 mailbox_dev=self._raw[2])
         ps = int(self.lib.smc_partial_stride(nx))
         nm = nx + nx * (nx + 1) // 2
         self.rec_local = torch.zeros(ps, dtype=torch.float64, device=dev)
