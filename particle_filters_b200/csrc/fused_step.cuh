@@ -104,6 +104,17 @@ struct K5Args {
     int32_t n_ranges, ranges_per_cta;
     float kshift_bound;        // quantisation shift of the a-priori bound (K2Args::kshift_bound)
     unsigned int* ticket;
+    // Placement board (nullable = static mapping, CTA b takes the b-th run of ranges_per_cta ranges).  The CTAs that
+    // share an SM do not advance at the same pace: with equal work the one with the lowest block index leaves the tile
+    // loop after 0.74 of the time the third one needs, and the SM ends the launch on a single CTA's eight warps
+    // (profiles/r2_k5_shares.txt).  With a board the work is cut into slots x n_waves PIECES, piece (s, k) = share[k] of
+    // the 12 consecutive ranges of slot s; the CTAs of an SM find one another on the SM's row of the board, rank
+    // themselves by block index and take the pieces of one slot, the lowest block index the largest.  Correctness never
+    // depends on the placement: a piece is claimed by compare-and-swap, a CTA that finds its piece taken (or its SM's
+    // row incomplete after 4 us) takes the next free one, and the per-CTA records are indexed by piece.
+    unsigned int* board;
+    int32_t n_waves, slots;
+    int8_t share[8];
     FinishArgs fin;            // finish of step t-1
     K2Args fin2;               // finalize of step t
     K5Shard sh;                // sharded form only
@@ -297,8 +308,54 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
 
     // this CTA's ranges (measured and dropped: handing the CTAs of one SM unequal shares by arrival order -- the three
     // co-resident CTAs finish 1 : 1.17 : 1.36 apart -- made every launch slower, profiles/r2_k5_shares.txt)
-    const int r_begin = (int)blockIdx.x * a.ranges_per_cta, r_end = r_begin + a.ranges_per_cta;
-    const int piece = (int)blockIdx.x;
+    int r_begin = (int)blockIdx.x * a.ranges_per_cta, r_end = r_begin + a.ranges_per_cta;
+    int piece = (int)blockIdx.x;
+    if (a.board) {
+        __shared__ int s_piece;
+        if (tid == 0) {
+            const int occ = a.n_waves;
+            unsigned int* taken = a.board + kBoardSms * 8;
+            unsigned int* slot_ctr = taken + kBoardPieces;
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            volatile unsigned int* row = a.board + (size_t)(smid % (unsigned)kBoardSms) * 8;
+            const unsigned arr = atomicAdd(const_cast<unsigned int*>(row), 1u);       // row[0]: arrivals on this SM
+            int want = -1;
+            if (arr < (unsigned)occ) {
+                row[1 + arr] = blockIdx.x + 1u;                                       // row[1 .. occ]: their block indices
+                const unsigned long long t0 = globaltimer_ns();
+                bool all = false;
+                int rank = 0;
+                while (!all && globaltimer_ns() - t0 < 4000ull) {
+                    all = true; rank = 0;
+                    for (int j = 0; j < occ; ++j) {
+                        const unsigned v = row[1 + j];
+                        if (v == 0u) all = false;
+                        else if (v - 1u < blockIdx.x) ++rank;
+                    }
+                }
+                if (all) {
+                    // the lowest block index of the SM draws the slot and posts it in row[7]
+                    unsigned slot1 = 0u;
+                    if (rank == 0) { slot1 = atomicAdd(slot_ctr, 1u) + 1u; row[7] = slot1; }
+                    else while ((slot1 = row[7]) == 0u && globaltimer_ns() - t0 < 8000ull) { }
+                    if (slot1 != 0u && slot1 <= (unsigned)a.slots) want = (int)(slot1 - 1u) * occ + rank;
+                }
+            }
+            // claim: the wanted piece, else the next free one (pieces and CTAs are equal in number)
+            int pc = want >= 0 ? want : (int)blockIdx.x;
+            const int n_pieces = a.slots * occ;
+            while (atomicCAS(taken + pc, 0u, 1u) != 0u) pc = pc + 1 == n_pieces ? 0 : pc + 1;
+            s_piece = pc;
+        }
+        __syncthreads();
+        piece = s_piece;
+        const int sl = piece / a.n_waves, w = piece % a.n_waves;
+        int before = 0;
+        for (int k = 0; k < w; ++k) before += a.share[k];
+        r_begin = sl * (a.n_ranges / a.slots) + before;
+        r_end = r_begin + a.share[w];
+    }
     const int64_t t_begin = k3_range_begin(r_begin, a.n_tiles, a.n_ranges);
     const int64_t t_end = k3_range_begin(r_end, a.n_tiles, a.n_ranges);
     auto swz = [](int f) -> int { return f ^ ((f >> 3) & (UPT - 1)); };
@@ -1006,6 +1063,7 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
             // (the peers accumulate into it only once they have seen this launch's flag)
             if (!a.sh.first)
                 for (int i = tid; i < kRsumStride; i += THREADS) const_cast<unsigned long long*>(rin)[i] = 0ull;
+            if (a.board) for (int i = tid; i < kBoardSms * 8 + kBoardPieces + 8; i += THREADS) a.board[i] = 0u;
             if (tid == 0) {
                 s_sh.c.cur ^= 1;                                  // the resampled, propagated set is the current one
                 *gctrl = s_sh.c;
@@ -1073,6 +1131,7 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
             f2.ctrl = ctrl; f2.parts = a.parts; f2.n_parts = (int)gridDim.x;
             finalize_body(f2, s_fout, s_ftmp);
         }
+        if (a.board) for (int i = tid; i < kBoardSms * 8 + kBoardPieces + 8; i += THREADS) a.board[i] = 0u;
         if (tid == 0) *a.ticket = 0u;
     }
 }

@@ -2399,6 +2399,7 @@ struct Launch {
     unsigned int* ticket() const { return reinterpret_cast<unsigned int*>(ws + L.ticket); }
     double* mom_parts() const { return reinterpret_cast<double*>(ws + L.mom_parts); }
     double* big_parts() const { return reinterpret_cast<double*>(ws + L.big_parts); }
+    unsigned int* board() const { return reinterpret_cast<unsigned int*>(ws + L.board); }
 };
 
 // Launch with programmatic stream serialization (see pdl_wait / pdl_trigger).  Measured on B200 at
@@ -2762,6 +2763,33 @@ inline bool fused_legacy() {
     if (v < 0) { const char* e = getenv("SMC_FUSED_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+// Shares of a slot's ranges for the CTAs of one SM, by their rank on the SM (K5Args::share).  Environment override
+// for measurements: SMC_K5_SHARES / SMC_K5S_SHARES = "5,4,3"; "0" = equal shares, static block -> ranges mapping.
+inline void k5_set_shares(K5Args& a, const Launch& l, int64_t grid, int64_t ranges, const char* env_name, const int* dflt) {
+    a.slots = sm_count();
+    a.n_waves = (int32_t)(grid / a.slots);
+    a.board = nullptr;
+    const int per_slot = (int)(ranges / a.slots);
+    int sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sum = 0;
+    bool ok = false;
+    const char* e = getenv(env_name);
+    if (e && e[0] == '0' && e[1] == 0) return;
+    if (e) {
+        int k = 0;
+        for (const char* q = e; *q && k < 8; ++k) { sh[k] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+        for (int i = 0; i < a.n_waves; ++i) sum += sh[i];
+        ok = k == a.n_waves && sum == per_slot;
+        for (int i = 0; i < a.n_waves; ++i) ok = ok && sh[i] >= 1;
+    }
+    if (!ok && dflt) {
+        sum = 0;
+        for (int i = 0; i < a.n_waves; ++i) { sh[i] = dflt[i]; sum += sh[i]; }
+        ok = sum == per_slot;
+    }
+    if (!ok || grid != (int64_t)a.slots * a.n_waves || grid > kBoardPieces || a.n_waves > 6) return;
+    for (int i = 0; i < 8; ++i) a.share[i] = (int8_t)sh[i];
+    a.board = l.board();
+}
 inline int64_t k5_grid(int nx) { return (int64_t)sm_count() * (nx <= 1 ? SMC_K5_OCC : 2); }
 
 // K5 launch: `fin2` != nullptr for the fused instantiations (functor of step t + its finalize), nullptr for the
@@ -2789,6 +2817,11 @@ int launch_k5(const Launch& l, const Model& m, const void* lw_in, void* lw_out, 
     SMC_REQUIRE(ranges % grid == 0 && l.L.n_tiles >= ranges, "smc: K5 needs at least %lld tiles", (long long)ranges);
     a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
     a.ticket = l.ticket() + 1;
+    // four CTAs per SM, 12 ranges per SM: measured 0.3462 ms against 0.3625 ms with equal shares at N = 2^26 (and 5,3,2,2:
+    // 0.3647, 4,4,3,1: 0.3530, 4,4,2,2: 0.3525; profiles/r2_k5_shares.txt); short launches keep the static mapping
+    static const int kShares4[4] = {4, 3, 3, 2};
+    const bool long_launch = l.L.n_tiles >= 16 * grid;
+    k5_set_shares(a, l, grid, ranges, "SMC_K5_SHARES", (NX == 1 && SMC_K5_OCC == 4 && long_launch) ? kShares4 : nullptr);
     a.fin = f; a.fin.mom_parts = l.mom_parts(); a.fin.n_mom_parts = (int)grid;
     if (fin2) { a.fin2 = *fin2; a.kshift_bound = fin2->kshift_bound; }
     auto kern = k5_resample_propagate<NX, Model>;
@@ -2859,6 +2892,7 @@ int launch_k5_sharded(const Launch& l, const Model& m, const smc_shard_ctx* ctx,
     const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
     a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
     a.ticket = l.ticket() + 1;
+    k5_set_shares(a, l, grid, ranges, "SMC_K5S_SHARES", nullptr);
     quant_bound_for(d->n_global, &a.sh.pfin.lw_bound, &a.sh.pfin.kshift_bound);
     a.kshift_bound = a.sh.pfin.kshift_bound;
     K5Shard& sh = a.sh;

@@ -88,9 +88,11 @@ static_assert(sizeof(Ctrl) <= 1024, "control block must fit its slot");
 
 // Workspace layout (all offsets 256-B aligned), computed identically on host and device.
 struct WsLayout {
-    size_t ctrl, params, k1_parts, tile_agg, ticket, mom_parts, big_parts, total;   // tile_agg: 16-B {aggregate, inclusive} records
+    size_t ctrl, params, k1_parts, tile_agg, ticket, mom_parts, big_parts, board, total;   // tile_agg: 16-B {aggregate, inclusive} records
     int64_t n_k1_blocks, n_tiles;
 };
+constexpr int kBoardSms = 512;            // %smid is taken modulo this
+constexpr int kBoardPieces = 1024;        // >= CTAs of a fused-step launch
 constexpr int kParamSlots = 4;            // host->device staging slots for small matrices
 constexpr int kParamSlotDoubles = 8192;   // 64 KiB each (up to 90 x 90)
 
@@ -128,6 +130,9 @@ inline WsLayout ws_layout(int64_t n, int nx, int dtype) {
     // per-CTA records of the X^T W X moment kernel (nx > kFusedNxMax): (1 + nx + nx^2) doubles each
     L.big_parts = off;
     if (nx > kFusedNxMax) off = align256(off + size_t(kSyrkMaxBlocks) * (1 + nx + size_t(nx) * nx) * sizeof(double));
+    // placement board of the fused step (fused_step.cuh): kBoardSms rows of 8 words, kBoardPieces claim flags, one
+    // slot counter; zero between launches
+    L.board = off;     off = align256(off + size_t(kBoardSms * 8 + kBoardPieces + 8) * sizeof(uint32_t));
     L.total = off;
     return L;
 }

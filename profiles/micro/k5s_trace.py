@@ -72,6 +72,14 @@ def main():
                   f"corr(duration, outputs) {np.corrcoef(tiles, outs)[0, 1]:.3f}")
             print(f"  least squares: duration = {coef[0]:.2f} us x input tiles + {coef[1]:.2f} us x (outputs / 4096) + {coef[2]:.1f} us; "
                   f"residual std {np.std(tiles - A @ coef):.1f} us")
+            by_rank = {}
+            for sm_id in per_sm:
+                bl = sorted(b for b in range(ncta) if int(smid[b]) == sm_id)
+                for r, b in enumerate(bl):
+                    by_rank.setdefault(r, []).append((float(tiles[b]), float(ntile[b])))
+            print("  by rank on the SM (block-index order): " + "; ".join(
+                f"rank {r}: {np.mean([v[0] for v in by_rank[r]]):.0f} us for {np.mean([v[1] for v in by_rank[r]]):.1f} tiles"
+                for r in sorted(by_rank)))
             order = np.argsort(tiles)
             print("  fastest CTAs (block, sm, us): " + " ".join(f"({b},{int(smid[b])},{tiles[b]:.0f})" for b in order[:8]))
             print("  slowest CTAs (block, sm, us): " + " ".join(f"({b},{int(smid[b])},{tiles[b]:.0f})" for b in order[-8:]))

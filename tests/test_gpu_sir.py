@@ -299,6 +299,25 @@ def test_sharded_step_matches_single_gpu_when_two_gpus_are_visible():
     assert res.returncode == 0 and "[sharded_check] PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+def test_fused_sharded_step_on_one_gpu_matches_the_single_gpu_engine():
+    """The single-launch, single-exchange sharded step (k5_resample_propagate, sharded form) with ONE shard: the
+    mailboxes, the range-total area and the log-weight arrays are the rank's own, so the whole protocol -- prologue
+    finalize / finish from the slot of the launch before, contribution table, in-kernel pre-pass on the outlier
+    steps, flush -- runs on a one-GPU box.  tests/sharded_check.py (cases "fused") requires bit-identical particles
+    against the three-launch single-GPU engine after 12 steps in two back-to-back runs, mild and 9-sigma observations."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SHARDED_CHECK_ONLY="fused", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0",
+               MASTER_ADDR="127.0.0.1", MASTER_PORT="29579")
+    res = subprocess.run([sys.executable, os.path.join(here, "sharded_check.py")], capture_output=True, text=True,
+                         timeout=600, env=env)
+    assert res.returncode == 0 and "[sharded_check] PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("identical particles 100.0000%") == 3, res.stdout[-2000:]
+
+
 @pytest.mark.parametrize("kind", ["sv", "lgssm", "sv_outliers"])
 def test_fused_resample_propagate_pipeline_matches_three_launch_step(kind):
     """run() of a bootstrap filter through smc_sir_step_fused (resampler of step t-1 feeding the functor
