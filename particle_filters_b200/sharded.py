@@ -19,6 +19,15 @@ into the mailbox of EVERY rank over NVLink and raises a stamped flag there, the 
    one kernel; its last CTA publishes the post-resample moment record, whose flag also certifies that all
    migrated particles have landed -> ``k_finish_step_sharded``.
 
+``ShardedSir.run`` / ``fused_begin`` / ``fused_step`` / ``fused_end``: the FUSED sharded step of bootstrap filters on
+large shards -- ONE launch and ONE exchange per step (csrc/fused_step.cuh, sharded form; include/smc.h,
+``smc_sir_step_fused_sharded``).  Every CTA's prologue finalises step t-1 and finishes step t-2 from the slot all ranks
+published at the end of the launch before; a resampled quad goes through the model functor on the rank that holds its
+ancestor and is stored -- particle, log-weight and fixed-point weight into the range totals -- into the memory of the
+rank that owns its index; the last CTA publishes the rank's record of step t, the moments of step t-1 and its row of the
+G x G table of weight contributions under one flag.  For this form the two log-weight arrays and a range-total area of
+every rank are peer-mapped as well.
+
 ``exchange="nccl"``: the same kernels with three NCCL all-gathers per step instead (baseline).
 
 No host synchronisation happens inside the step loop.  The pure-host helpers at the top
