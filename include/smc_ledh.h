@@ -41,6 +41,9 @@ typedef struct smc_ledh_desc {
 } smc_ledh_desc;
 
 uint64_t smc_sizeof_ledh_desc(void);
+/* Diagnostics of the fp32 information-form flow: how many flow calls needed a jittered Cholesky factor of P
+ * (relative jitter <= 1e-7) and how many fell back to the literal kernel because P had no factor at all. */
+void smc_ledh_info_counters(uint64_t *jittered, uint64_t *fell_back);
 
 /* K4: all pseudo-time steps lambda_j = j / L, j = 1..L, for every particle, on chip.
  * P_host (nx*nx, already symmetrised, :106), R_host (nz*nz), z_host (nz). */

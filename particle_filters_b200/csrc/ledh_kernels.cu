@@ -583,6 +583,7 @@ bool invert(const double* A, int n, std::vector<double>& inv) {
 }
 
 // host Cholesky P = L L^T (lower); false when P is not positive definite
+unsigned long long g_info_jitter = 0, g_info_fallback = 0;      // smc_ledh_info_counters
 bool cholesky_lower(const double* P, int n, std::vector<double>& Lc) {
     Lc.assign((size_t)n * n, 0.0);
     for (int r = 0; r < n; ++r)
@@ -608,8 +609,23 @@ int launch_flow_info(const smc_ledh_desc* d, const double* P, const double* R, c
         for (int c = 0; c < nz; ++c)
             if (r != c && R[r * nz + c] != 0.0) return -1;
             else if (r == c && !(R[r * nz + c] > 0.0)) return -1;
+    // P = L L^T.  A tracker's covariance can lose definiteness in the last bits ((I - K H) P is not symmetrised by the
+    // reference's EKF); the literal kernels do not care, the information form needs the factor: retry with a relative
+    // jitter far below the fp32 resolution of this mode (<= 1e-7 of the mean diagonal) before giving the step to the
+    // literal kernel (five times slower at 16 x 25)
     std::vector<double> Lc;
-    if (!cholesky_lower(P, nx, Lc)) return -1;
+    bool have = cholesky_lower(P, nx, Lc);
+    if (!have) {
+        double tr = 0.0;
+        for (int i = 0; i < nx; ++i) tr += fabs(P[i * nx + i]);
+        std::vector<double> Pj(P, P + (size_t)nx * nx);
+        for (double eps = 1e-13; eps <= 1e-7 && !have; eps *= 100.0) {
+            for (int i = 0; i < nx; ++i) Pj[i * nx + i] = P[i * nx + i] + eps * tr / nx;
+            have = cholesky_lower(Pj.data(), nx, Lc);
+        }
+        __atomic_add_fetch(&g_info_jitter, 1ull, __ATOMIC_RELAXED);
+    }
+    if (!have) { __atomic_add_fetch(&g_info_fallback, 1ull, __ATOMIC_RELAXED); return -1; }
     const size_t cnt = (size_t)nx * nx + (size_t)nz * nz + nz + (size_t)(n_hp > 0 ? n_hp : 0);
     std::vector<double> host(cnt);
     double* q = host.data();
@@ -738,6 +754,10 @@ int check_ledh(const smc_ledh_desc* d) {
 extern "C" {
 
 uint64_t smc_sizeof_ledh_desc(void) { return sizeof(smc_ledh_desc); }
+void smc_ledh_info_counters(uint64_t* jittered, uint64_t* fell_back) {
+    if (jittered) *jittered = __atomic_load_n(&g_info_jitter, __ATOMIC_RELAXED);
+    if (fell_back) *fell_back = __atomic_load_n(&g_info_fallback, __ATOMIC_RELAXED);
+}
 
 int smc_ledh_flow(const smc_ledh_desc* d, const double* P_host, const double* R_host, const double* z_host,
                   int32_t h_kind, const double* h_params_host, int32_t n_h_params, void* stream) {

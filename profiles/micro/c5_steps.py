@@ -25,13 +25,21 @@ def main():
                                                     rng=np.random.default_rng(0)), dtype=dtype)
     st = pf.init_from_gaussian(m0, P0)
     pos = [i for c in range(4) for i in (4 * c, 4 * c + 1)]
-    for k in range(12):
+    for k in range(int(os.environ.get("C5_STEPS", "12"))):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         st = pf.step(st, Z[1 + k], process_noise_sampler="philox")
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
         err = float(np.sqrt(np.mean((np.asarray(st.mean)[pos] - X[1 + k].reshape(-1)[pos]) ** 2)))
         print(f"step {k:2d} {dt:8.1f} ms  ess {pf.last_ess:12.2f} resampled {pf.last_resampled}  pos rmse {err:7.2f}  "
-              f"mean finite {bool(np.all(np.isfinite(st.mean)))}", flush=True)
+              f"mean finite {bool(np.all(np.isfinite(st.mean)))}  info-form (jittered, fell back) {counters()}", flush=True)
+
+
+def counters():
+    import ctypes as C
+    from particle_filters_b200 import _lib
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    _lib.load().smc_ledh_info_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 if __name__ == "__main__":
