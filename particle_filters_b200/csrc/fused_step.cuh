@@ -161,7 +161,10 @@ __device__ unsigned long long g_k5_trace[2 * 1024 * 16];
 #define K5_TRACE(slot) do { } while (0)
 #endif
 
-template <bool SHARDED> struct K5CtrlCopy { Ctrl c; unsigned long long contrib[kMaxShards]; double pout[32]; double m[16]; };
+template <bool SHARDED> struct K5CtrlCopy {
+    Ctrl c; unsigned long long contrib[kMaxShards]; double pout[32]; double m[16];
+    Mailbox* mail[kMaxShards];          // the ranks' mailboxes (fetched once, while the CTA waits for the flags)
+};
 template <> struct K5CtrlCopy<false> { int unused; };
 
 template <int NX, class Model, bool SHARDED = false>
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
         for (int i = tid; i < (int)(sizeof(Ctrl) / 4); i += THREADS)
             reinterpret_cast<uint32_t*>(&s_sh.c)[i] = reinterpret_cast<const uint32_t*>(gctrl)[i];
         if (tid < kMaxShards) s_sh.contrib[tid] = 0ull;
+        if (tid >= 32 && tid < 32 + G) s_sh.mail[tid - 32] = a.sh.ctx.mail[tid - 32];
         own = a.sh.own;
         const unsigned long long prev = a.sh.ctx.stamp - 1ull;
         slot_in = &own->fs[prev & 1ull];
@@ -1038,9 +1042,11 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
                     for (int k = 0; k < NM; ++k) acc[k] += __ldcg(a.mom_parts + (int64_t)p * NM + k);
             unsigned long long* acc_g = a.sh.own_rsum + 2 * kRsumStride;
             const unsigned long long cg = tid < G ? __ldcg(acc_g + tid) : 0ull;
+            K5_TRACE(10);
             combine_partials(a.parts, (int)gridDim.x, 3, s_fout, s_ftmp, 0);
+            K5_TRACE(11);
             if (tid < 3)
-                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].rec[rank][tid] = s_fout[tid];
+                for (int g = 0; g < G; ++g) s_sh.mail[g]->fs[slot].rec[rank][tid] = s_fout[tid];
             if (a.mom_parts) {
 #pragma unroll
                 for (int k = 0; k < NM; ++k) {
@@ -1052,13 +1058,14 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
                     double t = 0;
 #pragma unroll
                     for (int w = 0; w < WARPS; ++w) t += s_mom[w][tid];
-                    for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].mom[rank][tid] = t;
+                    for (int g = 0; g < G; ++g) s_sh.mail[g]->fs[slot].mom[rank][tid] = t;
                 }
             }
             if (tid < G) {
-                for (int g = 0; g < G; ++g) a.sh.ctx.mail[g]->fs[slot].contrib[rank][tid] = cg;
+                for (int g = 0; g < G; ++g) s_sh.mail[g]->fs[slot].contrib[rank][tid] = cg;
                 acc_g[tid] = 0ull;
             }
+            K5_TRACE(12);
             // every CTA of this rank has read the totals of step t-1: clear that buffer for the launch after the next
             // (the peers accumulate into it only once they have seen this launch's flag)
             if (!a.sh.first)
@@ -1066,13 +1073,17 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
             if (a.board) for (int i = tid; i < kBoardSms * 8 + kBoardPieces + 8; i += THREADS) a.board[i] = 0u;
             if (tid == 0) {
                 s_sh.c.cur ^= 1;                                  // the resampled, propagated set is the current one
-                *gctrl = s_sh.c;
                 *a.sh.gbar = 0u;
                 *a.ticket = 0u;
             }
+            K5_TRACE(13);
             if (tid < 32) __threadfence_system();            // (every store into a mailbox came from warp 0)
+            K5_TRACE(14);
             __syncthreads();
-            if (tid < G) *(volatile unsigned long long*)&a.sh.ctx.mail[tid]->fs[slot].flag[rank] = a.sh.ctx.stamp;
+            if (tid < G) *(volatile unsigned long long*)&s_sh.mail[tid]->fs[slot].flag[rank] = a.sh.ctx.stamp;
+            // (the control block is this GPU's own business: after the flags)
+            for (int i = tid; i < (int)(sizeof(Ctrl) / 4); i += THREADS)
+                reinterpret_cast<uint32_t*>(gctrl)[i] = reinterpret_cast<const uint32_t*>(&s_sh.c)[i];
             K5_TRACE(6);
         }
         return;

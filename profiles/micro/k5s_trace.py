@@ -54,6 +54,11 @@ def main():
             print(f"  last ticket at {rel(cur[:, 5]).max():6.1f} us, flag raised at {rel(np.array([done_cur]))[0]:6.1f} us")
             if os.environ.get("K5S_TRACE_DUMP"):
                 np.save(os.path.join(REPO, "gpurun_out", f"k5s_trace_{lg}.npy"), cur)
+            lc = int(np.argmax(cur[:, 6]))
+            tl = cur[lc]
+            print(f"  last CTA (block {lc}): ticket {rel(tl[5:6])[0]:.1f}; loads issued +{(tl[10]-tl[5])/1e3:.1f}; combine +{(tl[11]-tl[10])/1e3:.1f}; "
+                  f"moments + publish +{(tl[12]-tl[11])/1e3:.1f}; zero + ctrl +{(tl[13]-tl[12])/1e3:.1f}; fence +{(tl[14]-tl[13])/1e3:.1f}; "
+                  f"flag +{(tl[6]-tl[14])/1e3:.1f} us")
             tiles = (cur[:, 4] - cur[:, 3]) / 1e3
             smid = cur[:, 7]
             per_sm = {}
