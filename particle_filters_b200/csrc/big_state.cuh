@@ -71,6 +71,79 @@ __device__ __forceinline__ void l96_rk4(real (&x)[NX], real F, real dt) {
     l96_stage<real, NX, 4>(x, xt, acc, F, dt / real(6));
 }
 
+// fp32 throughput form of the same step: ONE stage body in a loop over the four stages.  The fully unrolled form
+// above is 760 floating-point instructions (12 KB of code) per RK4 step, and ncu showed the kernel's top stall to be
+// "no instruction" (1.9 stalled warps per issue, 57 % issue utilisation): four warps per scheduler at four places of
+// a loop that does not fit the instruction cache.  Here the stage state is walked in place by all four stages
+// (stage 1 starts from a copy of x), acc collects k1 + 2 k2 + 2 k3 + k4 by one FMA per stage (1 k + 0 and acc + 1 k are
+// exact), and the stage-4 update x += dt/6 acc follows the loop: every element sees the same operations with the same
+// roundings as in the unrolled form (bit-identical results) at 1.2 x the instructions and a quarter of the code.
+template <int NX>
+__device__ __forceinline__ void l96_rk4_compact(float (&x)[NX], float F, float dt) {
+    float xt[NX], acc[NX];
+    const float hdt = 0.5f * dt;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { xt[i] = x[i]; acc[i] = 0.f; }
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const float c = s < 2 ? hdt : dt;                       // (stage 4's stage state is not used)
+        const float ca = (s == 0 || s == 3) ? 1.f : 2.f;
+        const float old0 = xt[0];
+        float d2 = xt[NX - 2], d1 = xt[NX - 1];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const float cur = xt[i];
+            const float nxt = (i + 1 < NX) ? xt[(i + 1) % NX] : old0;
+            const float k = l96_term(nxt, d2, d1, cur, F);
+            acc[i] = fmaf(ca, k, acc[i]);
+            xt[i] = fmaf(c, k, x[i]);
+            d2 = d1; d1 = cur;
+        }
+    }
+    const float c6 = dt / 6.f;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = fmaf(c6, acc[i], x[i]);
+}
+// What ships: stages 1 and 4 as in the unrolled form (no copy of x, no wasted FMA), stages 2 and 3 share one body --
+// the unrolled form's 760 floating-point instructions per step in 9 KB of code.  Measured at C4 (N = 2^22, nx = 40, 20
+// sub-steps; ms per filter step): unrolled 5.67 (kernel 4.11, 57 % issue), compact 5.27 (kernel 3.70, 75 % issue, "no
+// instruction" stall 0.06), peeled 4.73; all three bit-identical (profiles/micro/l96_hash.py).  -DSMC_L96_COMPACT /
+// -DSMC_L96_UNROLLED select the other two.
+template <int NX>
+__device__ __forceinline__ void l96_rk4_peeled(float (&x)[NX], float F, float dt) {
+    float xt[NX], acc[NX];
+    const float hdt = 0.5f * dt;
+    l96_stage<float, NX, 1>(x, xt, acc, F, hdt);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const float c = s == 0 ? hdt : dt;
+        const float old0 = xt[0];
+        float d2 = xt[NX - 2], d1 = xt[NX - 1];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const float cur = xt[i];
+            const float nxt = (i + 1 < NX) ? xt[(i + 1) % NX] : old0;
+            const float k = l96_term(nxt, d2, d1, cur, F);
+            acc[i] = fmaf(2.f, k, acc[i]);
+            xt[i] = fmaf(c, k, x[i]);
+            d2 = d1; d1 = cur;
+        }
+    }
+    l96_stage<float, NX, 4>(x, xt, acc, F, dt / 6.f);
+}
+template <typename real, int NX> struct L96Step {
+    static __device__ __forceinline__ void run(real (&x)[NX], real F, real dt) { l96_rk4<real, NX>(x, F, dt); }
+};
+#ifndef SMC_L96_UNROLLED
+template <int NX> struct L96Step<float, NX> {
+#ifdef SMC_L96_COMPACT
+    static __device__ __forceinline__ void run(float (&x)[NX], float F, float dt) { l96_rk4_compact<NX>(x, F, dt); }
+#else
+    static __device__ __forceinline__ void run(float (&x)[NX], float F, float dt) { l96_rk4_peeled<NX>(x, F, dt); }
+#endif
+};
+#endif
+
 // the standard normal that draw_normals() hands to particle `gidx`, dimension d (same Philox block,
 // same Box-Muller lane), so results do not depend on which kernel propagates the particle
 __device__ inline float normal_one(const PhiloxKeys& keys, uint64_t gidx, uint32_t t, uint32_t d, float,
@@ -119,21 +192,56 @@ __global__ void __launch_bounds__(kL96Threads, sizeof(real) == 4 ? SMC_L96_MINB 
 
     const real NEG_INF = -INFINITY;
     real tm = NEG_INF, acc0 = 0, acc1 = 0;     // online (max, sum e, sum e^2)
-    for (int64_t i = (int64_t)blockIdx.x * kL96Threads + tid; i < a.n; i += (int64_t)gridDim.x * kL96Threads) {
+    // (warp-uniform trip count: the four lanes of a particle quad share their Philox blocks by shuffles)
+    const int lane = tid & 31;
+    const bool share_philox = sizeof(real) == 4 && a.noise == nullptr && (a.offset & 3) == 0 && NX % 4 == 0;
+    for (int64_t i0 = (int64_t)blockIdx.x * kL96Threads + (tid & ~31); i0 < a.n; i0 += (int64_t)gridDim.x * kL96Threads) {
+        const int64_t i = i0 + lane;
+        const bool live = i < a.n;
         real x[NX];
 #pragma unroll
-        for (int d = 0; d < NX; ++d) x[d] = x_all[d * a.ld + i];
+        for (int d = 0; d < NX; ++d) x[d] = live ? x_all[d * a.ld + i] : real(0);
         if (do_prop) {
-            for (int s = 0; s < p.n_sub; ++s) l96_rk4<real, NX>(x, p.F, p.dt);
+            for (int s = 0; s < p.n_sub; ++s) L96Step<real, NX>::run(x, p.F, p.dt);
+            if (share_philox) {
+                // draw_normals' layout: particle quad q = gidx >> 2, dimension d -> ONE Philox block (q, t, stream | d << 8)
+                // whose words (0, 1) / (2, 3) make the normals of lanes (0, 1) / (2, 3) of the quad.  normal_one() computes
+                // that block in each of the four lanes (40 blocks per particle, 15 % of this kernel's instructions); here
+                // lane m of the quad computes the blocks of the dimensions d = m (mod 4) and hands the words over.
+                const uint64_t gidx = (uint64_t)(a.offset + i);
+                const int j = lane & 3, pr = j >> 1;
+                const float k2pow32inv = 2.3283064365386963e-10f, k2pi = 6.2831853071795865f;
 #pragma unroll
-            for (int d = 0; d < NX; ++d) {
-                const real nrm = a.noise ? a.noise[d * a.ld + i]
-                                         : normal_one(a.keys, (uint64_t)(a.offset + i), a.t, (uint32_t)d, real(0));
-                x[d] = fma(p.lq[d], nrm, x[d]);
-                x_all[d * a.ld + i] = x[d];
+                for (int g = 0; g < NX / 4; ++g) {
+                    uint32_t r[4];
+                    philox_quad_keys(a.keys, gidx >> 2, a.t, kStreamProcess | ((uint32_t)(4 * g + j) << 8), r);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const int src = (lane & ~3) | m;
+                        const uint32_t w0 = __shfl_sync(0xffffffffu, r[0], src), w1 = __shfl_sync(0xffffffffu, r[1], src);
+                        const uint32_t w2 = __shfl_sync(0xffffffffu, r[2], src), w3 = __shfl_sync(0xffffffffu, r[3], src);
+                        const float u1 = fmaf((float)(pr ? w2 : w0), k2pow32inv, 0.5f * k2pow32inv);
+                        const float u2 = fmaf((float)(pr ? w3 : w1), k2pow32inv * k2pi, 0.5f * k2pow32inv * k2pi);
+                        const float rad = sqrt_approx(-1.3862943611198906f * lg2_approx(u1));
+                        float sn, cs;
+                        __sincosf(u2, &sn, &cs);
+                        const real nrm = (real)((j & 1) ? rad * sn : rad * cs);
+                        x[4 * g + m] = fma(p.lq[4 * g + m], nrm, x[4 * g + m]);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < NX; ++d) if (live) x_all[d * a.ld + i] = x[d];
+            } else {
+#pragma unroll
+                for (int d = 0; d < NX; ++d) {
+                    const real nrm = a.noise ? (live ? a.noise[d * a.ld + i] : real(0))
+                                             : normal_one(a.keys, (uint64_t)(a.offset + i), a.t, (uint32_t)d, real(0));
+                    x[d] = fma(p.lq[d], nrm, x[d]);
+                    if (live) x_all[d * a.ld + i] = x[d];
+                }
             }
         }
-        if (do_w) {
+        if (do_w && live) {
             // h(x) = x[0 :: obs_stride]; y = (z - h(x)) / chol(R)_kk  (particle_filter.py:257-260, R diagonal)
             real quad = 0;
             int kobs = 0;
@@ -161,7 +269,7 @@ __global__ void __launch_bounds__(kL96Threads, sizeof(real) == 4 ? SMC_L96_MINB 
     }
     if (!do_w) return;
     // ---- block combine (same record layout as k1_propagate_weight with 3 fields) -----------------
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = tid >> 5;
     const real wmax = warp_max(tm);
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
