@@ -89,6 +89,7 @@ int smc_abi_version(void);
 uint64_t smc_launch_count(void);
 const char *smc_last_error(void);
 uint64_t smc_sizeof_sir_desc(void);
+uint64_t smc_sizeof_shard_ctx(void);     /* sizeof(smc_shard_ctx), for binding self-checks */
 
 /* Workspace size for a shard (control block, block partials, pre-pass range totals, moment partials). */
 uint64_t smc_sir_workspace_bytes(int64_t n, int32_t nx, int32_t dtype);

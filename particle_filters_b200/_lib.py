@@ -98,6 +98,7 @@ _SIG = {
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_ledh_info_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "smc_sizeof_shard_ctx": (C.c_uint64, []),
     "smc_shard_rsum_bytes": (C.c_uint64, []),
     "smc_sir_weight_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                          C.c_double, C.c_uint64, C.c_int64, _P]),
@@ -155,6 +156,8 @@ def load() -> C.CDLL:
         raise SmcError("libsmc.so ABI version mismatch; rebuild")
     if lib.smc_sizeof_sir_desc() != C.sizeof(SirDesc):
         raise SmcError("smc_sir_desc layout mismatch between include/smc.h and _lib.py")
+    if lib.smc_sizeof_shard_ctx() != C.sizeof(ShardCtx):
+        raise SmcError("smc_shard_ctx layout mismatch between include/smc.h and _lib.py")
     if lib.smc_sizeof_ledh_desc() != C.sizeof(LedhDesc):
         raise SmcError("smc_ledh_desc layout mismatch between include/smc_ledh.h and _lib.py")
     _lib = lib

@@ -2985,6 +2985,7 @@ int smc_abi_version(void) { return SMC_ABI_VERSION; }
 uint64_t smc_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
 const char* smc_last_error(void) { return smc::g_err; }
 uint64_t smc_sizeof_sir_desc(void) { return sizeof(smc_sir_desc); }
+uint64_t smc_sizeof_shard_ctx(void) { return sizeof(smc_shard_ctx); }
 int64_t smc_partial_stride(int32_t nx) { return partial_stride(nx); }
 
 uint64_t smc_sir_workspace_bytes(int64_t n, int32_t nx, int32_t dtype) {
