@@ -113,6 +113,8 @@ struct K5Args {
     // depends on the placement: a piece is claimed by compare-and-swap, a CTA that finds its piece taken (or its SM's
     // row incomplete after 4 us) takes the next free one, and the per-CTA records are indexed by piece.
     unsigned int* board;
+    uint32_t board_wait_ns;    // how long a CTA waits for the other CTAs of its SM before it takes any free piece (4000;
+                               // SMC_K5_BOARD_WAIT_NS: the tests run with 0 and 150 as well -- all / some CTAs fall back)
     int32_t n_waves, slots;
     int8_t share[8];
     FinishArgs fin;            // finish of step t-1
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
                 const unsigned long long t0 = globaltimer_ns();
                 bool all = false;
                 int rank = 0;
-                while (!all && globaltimer_ns() - t0 < 4000ull) {
+                while (!all && globaltimer_ns() - t0 < (unsigned long long)a.board_wait_ns) {
                     all = true; rank = 0;
                     for (int j = 0; j < occ; ++j) {
                         const unsigned v = row[1 + j];
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256, SHARDED ? SMC_K5S_OCC : K5Occ<NX>::value)
                     // the lowest block index of the SM draws the slot and posts it in row[7]
                     unsigned slot1 = 0u;
                     if (rank == 0) { slot1 = atomicAdd(slot_ctr, 1u) + 1u; row[7] = slot1; }
-                    else while ((slot1 = row[7]) == 0u && globaltimer_ns() - t0 < 8000ull) { }
+                    else while ((slot1 = row[7]) == 0u && globaltimer_ns() - t0 < 2ull * a.board_wait_ns) { }
                     if (slot1 != 0u && slot1 <= (unsigned)a.slots) want = (int)(slot1 - 1u) * occ + rank;
                 }
             }

@@ -2789,6 +2789,8 @@ inline void k5_set_shares(K5Args& a, const Launch& l, int64_t grid, int64_t rang
     if (!ok || grid != (int64_t)a.slots * a.n_waves || grid > kBoardPieces || a.n_waves > 6) return;
     for (int i = 0; i < 8; ++i) a.share[i] = (int8_t)sh[i];
     a.board = l.board();
+    const char* w = getenv("SMC_K5_BOARD_WAIT_NS");
+    a.board_wait_ns = w ? (uint32_t)atoi(w) : 4000u;
 }
 inline int64_t k5_grid(int nx) { return (int64_t)sm_count() * (nx <= 1 ? SMC_K5_OCC : 2); }
 

@@ -438,6 +438,27 @@ def test_fp32_systematic_offspring_counts_at_scale(z_obs):
     assert (ess > 0.5 * N) if z_obs < 1 else (ess < 1e-3 * N)
 
 
+@pytest.mark.parametrize("wait_ns", ["4000", "150", "0"])
+def test_placement_board_of_the_fused_step_never_changes_a_result(wait_ns):
+    """k5_resample_propagate's placement board (the CTAs of one SM rank themselves by block index and take unequal
+    shares of the SM's ranges; fused_step.cuh) is a scheduling hint: any CTA -> piece assignment must give the same
+    particles and the same statistics.  The default build switches it on only for launches of >= 16 tiles per CTA; here
+    SMC_K5_SHARES forces it at test size, and SMC_K5_BOARD_WAIT_NS = 150 / 0 makes a random subset / every CTA miss its
+    SM's row and fall back to "any free piece".  The fused-vs-three-launch parity cases (bit-identical particle sets,
+    bit-identical repeat runs) and the expansion-vs-marker resampler cases must pass in all three settings."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SMC_K5_SHARES="4,3,3,2", SMC_K5_BOARD_WAIT_NS=wait_ns)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_sir.py"), "-q", "-x", "-m", "gpu", "-k",
+                          "(fused_resample_propagate_pipeline and sv) or expansion_resampler_selects"],
+                         capture_output=True, text=True, timeout=900, env=env, cwd=os.path.dirname(here))
+    assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "6 passed" in res.stdout, res.stdout[-1000:]
+
+
 @pytest.mark.parametrize("z_obs", [0.4, 3.5, 7.5, 9.0])
 def test_expansion_resampler_selects_the_same_particles_as_the_marker_resampler(z_obs):
     """The plain fp32 resampler exists twice: k3_resample (marker window; ancestor trace, fp64, shards) and
