@@ -2894,7 +2894,11 @@ int launch_k5_sharded(const Launch& l, const Model& m, const smc_shard_ctx* ctx,
     const int64_t ranges = k3_ranges(l.L.n_tiles, d->dtype, NX);
     a.n_ranges = (int32_t)ranges; a.ranges_per_cta = (int32_t)(ranges / grid);
     a.ticket = l.ticket() + 1;
-    k5_set_shares(a, l, grid, ranges, "SMC_K5S_SHARES", nullptr);
+    // three CTAs per SM: 5,4,3 measured 365.8 against 372.9 us per step on a 2^26 shard, no gain at 2^25 and a loss on
+    // short launches (the claim costs ~3 us in the prologue): only the largest shards take the board
+    static const int kShares3[3] = {5, 4, 3};
+    k5_set_shares(a, l, grid, ranges, "SMC_K5S_SHARES",
+                  (SMC_K5S_OCC == 3 && l.L.n_tiles >= 32 * grid) ? kShares3 : nullptr);
     quant_bound_for(d->n_global, &a.sh.pfin.lw_bound, &a.sh.pfin.kshift_bound);
     a.kshift_bound = a.sh.pfin.kshift_bound;
     K5Shard& sh = a.sh;
