@@ -1,6 +1,6 @@
 // K5: the fused step of the run() pipeline -- "resample step t-1, propagate + weigh step t" in ONE launch,
 // 16 B per particle-update (R logw, R x, W x, W logw), for filters that resample every step (bootstrap
-// filters; fp32, one shard).  Included by sir_kernels.cu (namespace smc).
+// filters; fp32).  Included by sir_kernels.cu (namespace smc).
 //
 // Reference semantics: models/particle_filter.py:146-171 (systematic resampling), :209-210 (gather, uniform
 // weights), :266-268 (post-resample moments) of step t-1, then :223-237 (predict) and :253-263 (log-weights,
@@ -26,7 +26,15 @@
 // does not depend on the order).  The last CTA decides (finalize_body) whether the bound left the weights
 // enough resolution; if not -- an observation that costs the whole cloud more than ~11 nats -- it says so in
 // the control block and the (otherwise empty) pre-pass launch that follows re-quantises against the
-// normaliser.
+// largest log-weight of the step.
+//
+// Two more things live in this file:
+//  * the SHARDED form (template flag; K5Shard below): the same kernel on one shard of a G-way split population, one
+//    launch and one exchange per step -- finalize / finish in every CTA's prologue from the slot all ranks published at
+//    the end of the launch before, outputs stored into the memory of the rank that owns their index, in-kernel range
+//    pre-pass on outlier steps;
+//  * the placement board (K5Args::board): the CTAs that share an SM rank themselves by block index and take unequal
+//    shares of the SM's ranges, because they do not advance at the same pace (profiles/r2_k5_shares.txt).
 #pragma once
 
 namespace smc {
