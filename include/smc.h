@@ -302,6 +302,15 @@ int smc_sir_fused_sharded_flush(const smc_sir_desc *d, const smc_shard_ctx *ctx,
                                 uint64_t seed, int64_t t_last, double *stats_prev2_dev,
                                 double *stats_prev_dev, int32_t resample, void *stream);
 
+/* ParticleFilter.step(z) (particle_filter.py:271-287) in ONE call for spec models with on-chip noise: copies the
+ * observation z_host (nz doubles, pinned or pageable) to z_dev, enqueues smc_sir_step, copies the statistics row
+ * (n_row doubles) to row_host and synchronises the stream -- the class API's per-step host <-> device traffic
+ * without three round trips through the Python binding. */
+int smc_sir_step_host(const smc_sir_desc *d, int32_t model_id, const double *params_host,
+                      int32_t n_params, double *z_dev, const double *z_host, double resample_thresh,
+                      double u_host, uint64_t seed, int64_t t, double *stats_row_dev,
+                      double *row_host, int32_t n_row, void *stream);
+
 /* Stand-alone pieces used by the drop-in classes' private helpers. */
 
 /* ParticleFilter._systematic_resample(weights) (particle_filter.py:146-171):

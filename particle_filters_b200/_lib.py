@@ -98,6 +98,8 @@ _SIG = {
     "smc_sir_step_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,
                                        C.c_double, C.c_uint64, C.c_int64, _P, _P]),
     "smc_ledh_info_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "smc_sir_step_host": (C.c_int, [C.POINTER(SirDesc), C.c_int32, _D, C.c_int32, _P, _P, C.c_double, C.c_double,
+                                    C.c_uint64, C.c_int64, _P, _P, C.c_int32, _P]),
     "smc_sizeof_shard_ctx": (C.c_uint64, []),
     "smc_shard_rsum_bytes": (C.c_uint64, []),
     "smc_sir_weight_sharded": (C.c_int, [C.POINTER(SirDesc), C.POINTER(ShardCtx), C.c_int32, _D, C.c_int32, _P,

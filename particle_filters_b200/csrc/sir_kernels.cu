@@ -3568,6 +3568,21 @@ int smc_sir_step(const smc_sir_desc* d, int32_t model_id, const double* params_h
     return smc_sir_finish_step(d, stats_row_dev, nullptr, 0, stream);
 }
 
+int smc_sir_step_host(const smc_sir_desc* d, int32_t model_id, const double* params_host, int32_t n_params,
+                      double* z_dev, const double* z_host, double resample_thresh, double u_host, uint64_t seed,
+                      int64_t t, double* stats_row_dev, double* row_host, int32_t n_row, void* stream) {
+    // ParticleFilter.step(z) in one call: observation in, statistics row out, one stream synchronisation
+    SMC_REQUIRE(d && z_dev && z_host && stats_row_dev && row_host && n_row > 0, "smc_sir_step_host: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SMC_CHECK_CUDA(cudaMemcpyAsync(z_dev, z_host, sizeof(double) * (size_t)d->nz, cudaMemcpyHostToDevice, st));
+    if (int rc = smc_sir_step(d, model_id, params_host, n_params, z_dev, nullptr, resample_thresh, u_host, seed, t,
+                              stats_row_dev, stream))
+        return rc;
+    SMC_CHECK_CUDA(cudaMemcpyAsync(row_host, stats_row_dev, sizeof(double) * (size_t)n_row, cudaMemcpyDeviceToHost, st));
+    SMC_CHECK_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int smc_systematic_ancestors(const double* w_dev, int64_t n, double u, int32_t* ancestors_dev, void* ws_dev,
                              uint64_t ws_bytes, void* stream) {
     smc_sir_desc d;

@@ -246,6 +246,18 @@ class SirEngine:
             C.c_void_p(noise.data_ptr()) if noise is not None else None,
             float(thresh), float(u), C.c_uint64(seed), t, self._row(row), self.stream))
 
+    def step_host(self, model_id: int, params_c, z: np.ndarray, thresh: float, seed: int = 0, t: int = 0,
+                  row: int = 0) -> np.ndarray:
+        """One whole step with the observation coming from and the statistics row going to the host, in a single
+        library call (pinned staging on both sides, one stream synchronisation).  ``params_c`` = the
+        ``_lib.as_doubles(params)`` pair, kept by the caller across steps."""
+        kp, pp = params_c
+        self._z_pin.numpy()[:] = np.asarray(z, dtype=np.float64).reshape(-1)
+        check(self.lib.smc_sir_step_host(
+            self._d, model_id, pp, kp.size, self._zptr(0), C.c_void_p(self._z_pin.data_ptr()), float(thresh), -1.0,
+            C.c_uint64(seed), t, self._row(row), C.c_void_p(self._row_pin.data_ptr()), int(self.stride), self.stream))
+        return self._row_pin.numpy().copy()
+
     def step_weight(self, model_id: int, params, thresh: float, z_index: int = 0, noise=None, u: float = -1.0,
                     seed: int = 0, t: int = 0, row: int = 0):
         """First half of ``step``: K1 with the finalize folded into its last CTA (one launch)."""

@@ -345,12 +345,15 @@ class ParticleFilter:
         eng = self._eng
         self._generation += 1
         mid, params = self._functor
-        eng.set_observation(z, 0)
         host_rng = self._noise == "reference" or self.resample_method != "systematic"
         if not host_rng and mode == _lib.SMC_MODE_STEP and not self.regularize_after_resample:
-            # whole step on the device clock: K1 (+ finalize), range pre-pass, K3 (+ finish)
-            eng.step(mid, params, self.resample_thresh, z_index=0, seed=self._seed, t=self._t_phil)
-            return self._publish_device_state(eng, t_next)
+            # whole step on the device clock -- K1 (+ finalize), range pre-pass, resampler (+ finish) -- and the step's
+            # host traffic (z in, statistics row out) in ONE library call
+            if getattr(self, "_functor_c", None) is None or self._functor_c[2] is not params:
+                self._functor_c = _lib.as_doubles(params) + (params,)
+            row = eng.step_host(mid, self._functor_c[:2], z, self.resample_thresh, seed=self._seed, t=self._t_phil)
+            return self._publish_device_state(eng, t_next, row)
+        eng.set_observation(z, 0)
         noise = None
         if (mode & _lib.SMC_MODE_PROPAGATE) and self._noise == "reference":
             noise = eng.upload_soa(self.rng.standard_normal((self.Np, self.nx)), self.nx)
@@ -376,9 +379,10 @@ class ParticleFilter:
         eng.finish_step()
         return self._publish_device_state(eng, t_next)
 
-    def _publish_device_state(self, eng, t_next: int) -> PFState:
+    def _publish_device_state(self, eng, t_next: int, row=None) -> PFState:
         self._t_phil += 1
-        row = eng.read_row()
+        if row is None:
+            row = eng.read_row()
         self.last_log_norm, self.last_ess, self.last_resampled = float(row[0]), float(row[1]), bool(row[2])
         mean = row[_lib.SMC_STATS_HEADER:_lib.SMC_STATS_HEADER + self.nx].copy()
         cov = row[_lib.SMC_STATS_HEADER + self.nx:].reshape(self.nx, self.nx).copy()
