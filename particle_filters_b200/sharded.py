@@ -116,6 +116,38 @@ def migration_plan(totals: List[int], u: float, n_global: int, f32: bool = False
     return plan
 
 
+def quantised_weights_f32(logw: np.ndarray, n_global: int) -> np.ndarray:
+    """Fixed-point weights of a bootstrap step in the fp32 mode, against the a-priori bound lw <= -log N
+    (csrc/sir_kernels.cu ``quant_bound_for`` / ``quant_p`` / ``quant_a``): a = rni(2^(lw log2e + kshift)) with
+    kshift = Fa + log2 N, Fa = min(36, 62 - ceil(log2 N)).  Python ints (the sums are exact on the device too)."""
+    lg = 0
+    while (1 << lg) < n_global:
+        lg += 1
+    fa = min(36, 62 - lg)
+    kshift = np.float32(fa + np.log2(float(n_global)))
+    p = np.exp2(np.float32(1.4426950408889634) * np.asarray(logw, np.float32) + kshift)
+    return np.rint(p.astype(np.float64)).astype(object)
+
+
+def contribution_row(a_out: np.ndarray, first_output_index: int, n_global: int, n_shards: int) -> List[int]:
+    """What ONE rank publishes in its slot of the fused sharded step (csrc/fused_step.cuh, sharded form): the
+    fixed-point weight of the step-t particles it PRODUCED (outputs ``first_output_index ..`` of the resampling of step
+    t-1, after the functor), split by the rank that OWNS each output index."""
+    shard = n_global // n_shards
+    row = [0] * n_shards
+    for k, a in enumerate(a_out):
+        row[(first_output_index + k) // shard] += int(a)
+    return row
+
+
+def shard_totals_from_contributions(table) -> List[int]:
+    """Column sums of the G x G contribution table ([producing rank][owning rank]) = the shards' weight totals of the
+    NEXT resampling; every rank computes them alike in the prologue of the next launch (exclusive prefix over the lower
+    ranks = the rank's CDF offset)."""
+    G = len(table)
+    return [sum(int(table[src][dst]) for src in range(G)) for dst in range(G)]
+
+
 # ------------------------------------------------------------------------------------------------
 # device side
 # ------------------------------------------------------------------------------------------------

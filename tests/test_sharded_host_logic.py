@@ -106,6 +106,78 @@ def test_sharded_protocol_two_gloo_ranks():
     assert results[0][2] == results[1][2] and results[0][2] >= 0
 
 
+def _fused_worker(rank, world, port, q):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+
+    from oracle import systematic_ancestors
+    from particle_filters_b200.sharded import (contribution_row, migration_plan, outputs_below, quantised_weights_f32,
+                                               shard_offsets, shard_totals_from_contributions)
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # One fused step seen from rank `rank`: it holds shard `rank` of the step-(t-1) population, resamples it (its
+        # outputs are the indices [lo, hi) of the global resampled set, which may belong to the other rank), pushes
+        # them through the "functor" (here: new log-weights drawn per GLOBAL output index, like Philox) and publishes its
+        # row of the contribution table.  Check: column sums = the true per-shard totals of the step-t weights.
+        N = 1 << 13
+        n = N // world
+        rng = np.random.default_rng(5)
+        lw_prev = (-0.5 * (rng.standard_normal(N) * 1.7) ** 2 - np.log(N)).astype(np.float32)   # bootstrap: <= -log N
+        a_prev = quantised_weights_f32(lw_prev, N)
+        totals_prev = [int(sum(a_prev[r * n:(r + 1) * n])) for r in range(world)]
+        u = 0.3819660113
+        total = sum(totals_prev)
+        off = shard_offsets(totals_prev)
+        lo = 0 if rank == 0 else outputs_below(off[rank], u, N, f32=True, total=total)
+        hi = N if rank == world - 1 else outputs_below(off[rank] + totals_prev[rank], u, N, f32=True, total=total)
+        # the step-t log-weight of global output index i depends on i alone (Philox is keyed by the global index)
+        lw_new_all = (-0.5 * (np.random.default_rng(99).standard_normal(N) * 1.3) ** 2 - np.log(N)).astype(np.float32)
+        a_new_all = quantised_weights_f32(lw_new_all, N)
+        row = contribution_row(a_new_all[lo:hi], lo, N, world)
+        table = [None] * world
+        dist.all_gather_object(table, row)
+        totals_new = shard_totals_from_contributions(table)
+        truth = [int(sum(a_new_all[r * n:(r + 1) * n])) for r in range(world)]
+        assert totals_new == truth, (totals_new, truth)
+        # the output ranges of the ranks tile [0, N) and agree with the migration plan and with the oracle's ancestors
+        ranges = [None] * world
+        dist.all_gather_object(ranges, (lo, hi))
+        assert ranges[0][0] == 0 and ranges[-1][1] == N and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        plan = migration_plan(totals_prev, u, N, f32=True)
+        assert plan.sum() == N and plan[rank].sum() == hi - lo
+        w = np.array([float(v) for v in a_prev]) / float(total)
+        anc = systematic_ancestors(w, u)
+        mine = np.nonzero((anc >= rank * n) & (anc < (rank + 1) * n))[0]
+        assert abs(lo - mine.min()) <= 1 and abs(hi - (mine.max() + 1)) <= 1                 # round-off ties only
+        q.put((rank, "ok", int(plan.sum() - np.trace(plan))))
+    except Exception as exc:  # pragma: no cover
+        q.put((rank, f"FAIL: {exc!r}", -1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_sharded_contribution_table_two_gloo_ranks():
+    """Host restatement of what the fused sharded step exchanges (one slot per launch): every rank's row of the G x G
+    table of fixed-point weight contributions; its column sums are the shard totals of the next resampling."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 150)
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, crossing in results:
+        assert status == "ok", f"rank {rank}: {status}"
+    assert results[0][2] == results[1][2] and results[0][2] > 0        # some particles do cross the shard boundary
+
+
 def test_combine_partial_records_matches_flat_reduction():
     from particle_filters_b200.sharded import combine_partial_records
 
