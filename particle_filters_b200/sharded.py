@@ -119,7 +119,9 @@ def migration_plan(totals: List[int], u: float, n_global: int, f32: bool = False
 def quantised_weights_f32(logw: np.ndarray, n_global: int) -> np.ndarray:
     """Fixed-point weights of a bootstrap step in the fp32 mode, against the a-priori bound lw <= -log N
     (csrc/sir_kernels.cu ``quant_bound_for`` / ``quant_p`` / ``quant_a``): a = rni(2^(lw log2e + kshift)) with
-    kshift = Fa + log2 N, Fa = min(36, 62 - ceil(log2 N)).  Python ints (the sums are exact on the device too)."""
+    kshift = Fa + log2 N, Fa = min(36, 62 - ceil(log2 N)).  Python ints (the sums are exact on the device too).  The
+    device evaluates 2^x with ex2.approx (2 ulp), so these integers are a restatement of the PROTOCOL (what is summed and
+    exchanged), not a bit-for-bit oracle of the device's weights."""
     lg = 0
     while (1 << lg) < n_global:
         lg += 1
